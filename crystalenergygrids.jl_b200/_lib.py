@@ -1,0 +1,290 @@
+"""ctypes binding of libceg_cuda.so (include/ceg_cuda.h) — the only way the host layer computes.
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is usable,
+every compute entry point raises.  (The CPU oracle under oracle/ is test infrastructure and is
+never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libceg_cuda.so")
+
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+c_double_p = C.POINTER(C.c_double)
+c_float_p = C.POINTER(C.c_float)
+c_uint8_p = C.POINTER(C.c_uint8)
+
+
+class CegError(RuntimeError):
+    pass
+
+
+class ceg_cell_t(C.Structure):
+    _fields_ = [("mat", C.c_double * 9), ("invmat", C.c_double * 9), ("ortho", C.c_int32), ("_pad", C.c_int32),
+                ("safemin2", C.c_double)]
+
+
+class ceg_gridspec_t(C.Structure):
+    _fields_ = [("dims", C.c_int32 * 3), ("_pad", C.c_int32), ("size", C.c_double * 3), ("shift", C.c_double * 3),
+                ("delta", C.c_double * 3)]
+
+
+EXPORTS = [
+    "ceg_last_error", "ceg_abi_version", "ceg_device_count", "ceg_device_info", "ceg_host_register",
+    "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
+    "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
+    "ceg_interpolate", "ceg_interpolate_dev", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
+    "ceg_ewald_reciprocal_dev", "ceg_block_upload", "ceg_block_free", "ceg_energy_points",
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libceg_cuda.so (once).  Raises CegError with build instructions if it is absent."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise CegError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.ceg_last_error.restype = C.c_char_p
+        for name in EXPORTS:
+            if not hasattr(lib, name):
+                raise CegError(f"libceg_cuda.so does not export {name}")
+            if name != "ceg_last_error":
+                getattr(lib, name).restype = C.c_int
+        _lib = lib
+        return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = load().ceg_last_error()
+        raise CegError(msg.decode("utf-8", "replace") if msg else f"libceg_cuda error {rc}")
+
+
+def _p(a: np.ndarray, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _f64(a, shape=None) -> np.ndarray:
+    out = np.ascontiguousarray(a, dtype=np.float64)
+    return out if shape is None else out.reshape(shape)
+
+
+def make_cell(mat9, invmat9, ortho: bool, safemin2: float) -> ceg_cell_t:
+    c = ceg_cell_t()
+    c.mat[:] = [float(x) for x in mat9]
+    c.invmat[:] = [float(x) for x in invmat9]
+    c.ortho = int(bool(ortho))
+    c.safemin2 = float(safemin2)
+    return c
+
+
+def make_gridspec(csetup) -> ceg_gridspec_t:
+    g = ceg_gridspec_t()
+    g.dims[:] = [int(x) for x in csetup.dims]
+    g.size[:] = [float(x) for x in csetup.size]
+    g.shift[:] = [float(x) for x in csetup.shift]
+    g.delta[:] = [float(x) for x in csetup.delta]
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+def device_count() -> int:
+    n = C.c_int32(0)
+    _check(load().ceg_device_count(C.byref(n)))
+    return n.value
+
+
+def device_info(device: int = 0) -> dict:
+    name = C.create_string_buffer(256)
+    sm, mem, clk = C.c_int32(0), C.c_int64(0), C.c_int32(0)
+    _check(load().ceg_device_info(C.c_int32(device), name, C.byref(sm), C.byref(mem), C.byref(clk)))
+    return {"name": name.value.decode(), "sm_count": sm.value, "mem_bytes": mem.value, "clock_khz": clk.value}
+
+
+def host_register(arr: np.ndarray):
+    _check(load().ceg_host_register(C.c_void_p(arr.ctypes.data), C.c_int64(arr.nbytes)))
+
+
+def host_unregister(arr: np.ndarray):
+    _check(load().ceg_host_unregister(C.c_void_p(arr.ctypes.data)))
+
+
+# ---- probes / grid construction --------------------------------------------------------------
+def probe_create(device: int, cell: ceg_cell_t, xyz, types, charges, n_types: int, table: np.ndarray, cutoff2: float,
+                 want_coulomb: bool, alpha: float):
+    xyz = _f64(xyz, (-1, 3))
+    types = np.ascontiguousarray(types, dtype=np.int32)
+    n = xyz.shape[0]
+    assert types.shape == (n,)
+    q = None
+    if charges is not None:
+        q = _f64(charges, (n,))
+    table = np.ascontiguousarray(table)
+    assert table.dtype.itemsize == 72
+    n_probes = table.shape[0] if table.size else 0
+    h = C.c_void_p()
+    _check(load().ceg_probe_create(C.c_int32(device), C.byref(cell), C.c_int64(n), _p(xyz, C.c_double),
+                                   _p(types, C.c_int32), _p(q, C.c_double) if q is not None else None,
+                                   C.c_int32(n_types), C.c_int32(n_probes), C.c_void_p(table.ctypes.data if table.size else 0),
+                                   C.c_double(cutoff2), C.c_int32(int(want_coulomb)), C.c_double(alpha), C.byref(h)))
+    return h
+
+
+def probe_free(h):
+    _check(load().ceg_probe_free(h))
+
+
+def probe_num_grids(h) -> int:
+    n = C.c_int32(0)
+    _check(load().ceg_probe_num_grids(h, C.byref(n)))
+    return n.value
+
+
+def compute_derivatives(h, xyz) -> np.ndarray:
+    xyz = _f64(xyz, (-1, 3))
+    ng = probe_num_grids(h)
+    out = np.empty((ng, xyz.shape[0], 8), dtype=np.float64)
+    _check(load().ceg_compute_derivatives(h, C.c_int64(xyz.shape[0]), _p(xyz, C.c_double), _p(out, C.c_double)))
+    return out
+
+
+def grid_build(h, gs: ceg_gridspec_t, i0: int, i1: int, lam_vdw, thr_vdw, lam_coul, thr_coul, outs, raw=None):
+    """outs: list of n_grids float32 arrays [8][nx][ny][nz] (or None)."""
+    ng = probe_num_grids(h)
+    assert len(outs) == ng
+    ptrs = (c_float_p * ng)()
+    for g, o in enumerate(outs):
+        if o is not None:
+            assert o.dtype == np.float32 and o.flags.c_contiguous
+            ptrs[g] = _p(o, C.c_float)
+    rawp = None
+    if raw is not None:
+        assert raw.dtype == np.float64 and raw.flags.c_contiguous
+        rawp = _p(raw, C.c_double)
+    _check(load().ceg_grid_build(h, C.byref(gs), C.c_int32(i0), C.c_int32(i1), C.c_double(lam_vdw), C.c_double(thr_vdw),
+                                 C.c_double(lam_coul), C.c_double(thr_coul), ptrs, rawp))
+
+
+def grid_build_dev(h, gs: ceg_gridspec_t, i0: int, i1: int, lam_vdw, thr_vdw, lam_coul, thr_coul, dev_ptrs, stream=0):
+    ng = probe_num_grids(h)
+    assert len(dev_ptrs) == ng
+    ptrs = (C.c_void_p * ng)(*[C.c_void_p(int(p)) for p in dev_ptrs])
+    _check(load().ceg_grid_build_dev(h, C.byref(gs), C.c_int32(i0), C.c_int32(i1), C.c_double(lam_vdw),
+                                     C.c_double(thr_vdw), C.c_double(lam_coul), C.c_double(thr_coul), ptrs,
+                                     C.c_void_p(int(stream))))
+
+
+def probe_last_stats(h) -> dict:
+    a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    _check(load().ceg_probe_last_stats(h, C.byref(a), C.byref(b), C.byref(c)))
+    return {"n_points": a.value, "pairs_tested": b.value, "pairs_in_cutoff": c.value}
+
+
+# ---- interpolation -----------------------------------------------------------------------------
+def grid_upload(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, grid: np.ndarray, is_vdw: bool):
+    assert grid.dtype == np.float32 and grid.flags.c_contiguous
+    h = C.c_void_p()
+    _check(load().ceg_grid_upload(C.c_int32(device), C.byref(cell), C.byref(gs), _p(grid, C.c_float),
+                                  C.c_int32(int(is_vdw)), C.byref(h)))
+    return h
+
+
+def grid_free(h):
+    _check(load().ceg_grid_free(h))
+
+
+def interpolate(h, xyz) -> np.ndarray:
+    xyz = _f64(xyz, (-1, 3))
+    out = np.empty(xyz.shape[0], dtype=np.float64)
+    _check(load().ceg_interpolate(h, C.c_int64(xyz.shape[0]), _p(xyz, C.c_double), _p(out, C.c_double)))
+    return out
+
+
+def interpolate_dev(h, n: int, d_xyz: int, d_out: int, stream: int = 0):
+    _check(load().ceg_interpolate_dev(h, C.c_int64(n), C.c_void_p(int(d_xyz)), C.c_void_p(int(d_out)),
+                                      C.c_void_p(int(stream))))
+
+
+# ---- Ewald -------------------------------------------------------------------------------------
+def ewald_create(device: int, invmat9, kmax, kvec, kfactor, frac, charge):
+    invmat9 = _f64(invmat9, (9,))
+    kmax = np.ascontiguousarray(kmax, dtype=np.int32)
+    kvec = np.ascontiguousarray(kvec, dtype=np.int32).reshape(-1, 3)
+    kfactor = _f64(kfactor, (-1,))
+    frac = _f64(frac, (-1, 3))
+    charge = _f64(charge, (-1,))
+    n_k = kvec.shape[0]
+    assert kfactor.shape[0] == n_k and charge.shape[0] == frac.shape[0]
+    S = np.zeros((n_k, 2), dtype=np.float64)
+    h = C.c_void_p()
+    _check(load().ceg_ewald_create(C.c_int32(device), _p(invmat9, C.c_double), _p(kmax, C.c_int32), C.c_int64(n_k),
+                                   _p(kvec, C.c_int32), _p(kfactor, C.c_double), C.c_int64(frac.shape[0]),
+                                   _p(frac, C.c_double), _p(charge, C.c_double), C.byref(h), _p(S, C.c_double)))
+    return h, S[:, 0] + 1j * S[:, 1]
+
+
+def ewald_free(h):
+    _check(load().ceg_ewald_free(h))
+
+
+def ewald_reciprocal(h, xyz, q, energy_net_charges: float, static_contribution: float) -> np.ndarray:
+    q = _f64(q, (-1,))
+    xyz = _f64(xyz, (-1, q.shape[0], 3))
+    out = np.empty(xyz.shape[0], dtype=np.float64)
+    _check(load().ceg_ewald_reciprocal(h, C.c_int64(xyz.shape[0]), C.c_int32(q.shape[0]), _p(xyz, C.c_double),
+                                       _p(q, C.c_double), C.c_double(energy_net_charges),
+                                       C.c_double(static_contribution), _p(out, C.c_double)))
+    return out
+
+
+def ewald_reciprocal_dev(h, n_pos: int, q, d_xyz: int, energy_net_charges, static_contribution, d_out: int, stream=0):
+    q = _f64(q, (-1,))
+    _check(load().ceg_ewald_reciprocal_dev(h, C.c_int64(n_pos), C.c_int32(q.shape[0]), C.c_void_p(int(d_xyz)),
+                                           _p(q, C.c_double), C.c_double(energy_net_charges),
+                                           C.c_double(static_contribution), C.c_void_p(int(d_out)),
+                                           C.c_void_p(int(stream))))
+
+
+# ---- block mask + fused evaluation -----------------------------------------------------------------
+def block_upload(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, mask: np.ndarray):
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    h = C.c_void_p()
+    _check(load().ceg_block_upload(C.c_int32(device), C.byref(cell), C.byref(gs), _p(m, C.c_uint8), C.byref(h)))
+    return h
+
+
+def block_free(h):
+    _check(load().ceg_block_free(h))
+
+
+def energy_points(vdw_handles, coulomb, ewald, block, atomsidx, charges, xyz, energy_net_charges, static_contribution):
+    atomsidx = np.ascontiguousarray(atomsidx, dtype=np.int32)
+    na = atomsidx.shape[0]
+    charges = _f64(charges, (na,))
+    xyz = _f64(xyz, (-1, na, 3))
+    n = xyz.shape[0]
+    nv = len(vdw_handles)
+    arr = (C.c_void_p * max(nv, 1))(*[h if h is not None else C.c_void_p(0) for h in vdw_handles])
+    out_v = np.empty(n, dtype=np.float64)
+    out_c = np.empty(n, dtype=np.float64)
+    _check(load().ceg_energy_points(C.c_int32(nv), arr, coulomb if coulomb is not None else C.c_void_p(0),
+                                    ewald if ewald is not None else C.c_void_p(0),
+                                    block if block is not None else C.c_void_p(0), C.c_int64(n), C.c_int32(na),
+                                    _p(atomsidx, C.c_int32), _p(charges, C.c_double), _p(xyz, C.c_double),
+                                    C.c_double(energy_net_charges), C.c_double(static_contribution),
+                                    _p(out_v, C.c_double), _p(out_c, C.c_double)))
+    return out_v, out_c

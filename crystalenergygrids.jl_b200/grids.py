@@ -1,0 +1,337 @@
+"""Energy grids: construction, RASPA `.grid` I/O, tricubic interpolation, batched evaluation.
+
+Mirrors /root/reference/src/grids.jl (same names, argument meaning and error behaviour):
+  EnergyGrid                          grids.jl:10-19
+  parse_grid                          grids.jl:61-94
+  _create_grid_common (header)        grids.jl:108-116
+  create_grid_vdw / create_grid_coulomb   grids.jl:137-185   -> ceg_grid_build
+  BlockFile(g)                        grids.jl:188-204
+  interpolate_grid                    grids.jl:212-273       -> ceg_interpolate
+  CrystalEnergySetup                  grids.jl:284-294
+  energy_point / energy_grid          grids.jl:311-424       -> ceg_energy_points
+
+In-memory layout of ``EnergyGrid.grid``: float32 array of shape (8, nx, ny, nz), C order, which is
+byte-for-byte the reference's `Array{Cfloat,4}(nz, ny, nx, 8)` (z fastest, channel slowest).
+"""
+from __future__ import annotations
+
+import math
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .cell import CellMatrix, find_supercell, flat, prepare_periodic_distance_computations
+from .constants import (BLOCKED_ENERGY, COULOMBIC_CONVERSION_FACTOR, CUTOFF_COULOMB, GRID_TO_KELVIN)
+from .coordinates import BlockFile, GridCoordinatesSetup
+from .forcefields import ForceField
+from .probes import ProbeSystem
+
+
+def unitcell_struct(cell: CellMatrix):
+    ortho, safemin = prepare_periodic_distance_computations(cell.mat)
+    return _lib.make_cell(flat(cell.mat), flat(cell.invmat), ortho, safemin * safemin)
+
+
+@dataclass
+class EnergyGrid:
+    """grids.jl:10-16.  ewald_precision: -inf zero grid, +inf VdW grid, nan invalid grid."""
+    csetup: GridCoordinatesSetup | None
+    num_unitcell: tuple
+    ewald_precision: float
+    higherorder: bool
+    grid: np.ndarray
+    device: int = 0
+    _handle: object = None
+
+    @staticmethod
+    def zero() -> "EnergyGrid":
+        return EnergyGrid(None, (0, 0, 0), -math.inf, False, np.zeros((0, 0, 0, 0), dtype=np.float32))
+
+    @staticmethod
+    def invalid() -> "EnergyGrid":
+        return EnergyGrid(None, (0, 0, 0), math.nan, False, np.zeros((0, 0, 0, 0), dtype=np.float32))
+
+    @property
+    def is_zero(self) -> bool:
+        return self.ewald_precision == -math.inf
+
+    @property
+    def is_vdw(self) -> bool:
+        return self.ewald_precision == math.inf
+
+    @property
+    def handle(self):
+        """Device-resident copy (node-major re-layout), uploaded on first use."""
+        if self._handle is None:
+            if self.is_zero or math.isnan(self.ewald_precision):
+                return None
+            self._handle = _lib.grid_upload(self.device, unitcell_struct(self.csetup.cell), _lib.make_gridspec(self.csetup),
+                                            self.grid, self.is_vdw)
+        return self._handle
+
+    def close(self):
+        h, self._handle = self._handle, None
+        if h is not None:
+            _lib.grid_free(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- .grid files -------------------------------------------------------------------------------
+def _write_header(f, cset: GridCoordinatesSetup, num_unitcell):
+    """grids.jl:108-116."""
+    f.write(struct.pack("<d", cset.spacing))
+    f.write(struct.pack("<3i", *(int(x) for x in cset.dims)))
+    for v in (cset.size, cset.shift, cset.delta, cset.unitcell):
+        f.write(struct.pack("<3d", *(float(x) for x in v)))
+    f.write(struct.pack("<3i", *(int(x) for x in num_unitcell)))
+
+
+def write_grid(file, cset: GridCoordinatesSetup, num_unitcell, grid: np.ndarray, ewald_precision: float | None = None):
+    """grids.jl:151-155, 178-183 — header, [precision], grid, cell matrix (column-major)."""
+    with open(file, "wb") as f:
+        _write_header(f, cset, num_unitcell)
+        if ewald_precision is not None:
+            f.write(struct.pack("<d", ewald_precision))
+        f.write(np.ascontiguousarray(grid, dtype="<f4").tobytes())
+        f.write(flat(cset.cell.mat).astype("<f8").tobytes())
+
+
+def parse_grid(file, iscoulomb: bool, mat=None, device: int = 0) -> EnergyGrid:
+    """grids.jl:61-94."""
+    with open(file, "rb") as f:
+        spacing, = struct.unpack("<d", f.read(8))
+        dims = np.array(struct.unpack("<3i", f.read(12)), dtype=np.int32)
+        size = np.array(struct.unpack("<3d", f.read(24)))
+        shift = np.array(struct.unpack("<3d", f.read(24)))
+        delta = np.array(struct.unpack("<3d", f.read(24)))
+        unitcell = np.array(struct.unpack("<3d", f.read(24)))
+        num_unitcell = struct.unpack("<3i", f.read(12))
+        ewald_precision = struct.unpack("<d", f.read(8))[0] if iscoulomb else math.inf
+        n = 8 * int(dims[0] + 1) * int(dims[1] + 1) * int(dims[2] + 1)
+        raw = np.fromfile(f, dtype="<f4", count=n)
+        if raw.size != n:
+            raise EOFError(f"{file}: truncated grid")
+        grid = (raw.astype(np.float64) * GRID_TO_KELVIN).astype(np.float32)   # grids.jl:78
+        grid = grid.reshape(8, int(dims[0]) + 1, int(dims[1]) + 1, int(dims[2]) + 1)
+        if mat is None:
+            tail = f.read(72)
+            if len(tail) != 72:
+                raise ValueError("Missing `mat` argument to `parse_grid` not provided by the grid.")
+            mat = np.frombuffer(tail, dtype="<f8").reshape(3, 3).T.copy()
+        cell = mat if isinstance(mat, CellMatrix) else CellMatrix.from_mat(mat)
+    cs = GridCoordinatesSetup(cell, spacing, dims, size, shift, unitcell, delta)
+    return EnergyGrid(cs, tuple(int(x) for x in num_unitcell), float(ewald_precision), True, grid, device)
+
+
+# ---- construction ------------------------------------------------------------------------------
+def vdw_scaling():
+    """grids.jl:142-143,148 — (lambda, threshold)."""
+    lam_inv = GRID_TO_KELVIN
+    return 1.0 / lam_inv, lam_inv * 1e7
+
+
+def coulomb_scaling():
+    """grids.jl:169-170."""
+    lam = COULOMBIC_CONVERSION_FACTOR / GRID_TO_KELVIN
+    return lam, (1.0 / lam) * 1e7
+
+
+def _slabs(n_planes: int, n_parts: int):
+    """Contiguous x-slabs balanced by plane count."""
+    base, rem = divmod(n_planes, n_parts)
+    out, s = [], 0
+    for p in range(n_parts):
+        e = s + base + (1 if p < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def build_grids(framework, forcefield: ForceField, spacing: float, atoms=(), coulomb: bool = False, alpha: float = 0.0,
+                devices=None, xrange=None, want_raw: bool = False, outs=None):
+    """Fused construction of the VdW grids of `atoms` and (optionally) the Coulomb real-space
+    grid in one pass over the framework atoms.  Returns (csetup, [grids...], raw) with grids in
+    the un-scaled `.grid` units, exactly what create_grid_* return (grids.jl:156,184).
+
+    devices: list of CUDA device ordinals; the x index range is split into contiguous slabs, one
+    per device, driven from one host thread each.  xrange=(i0,i1) restricts the build to a slab
+    (used by one-process-per-GPU drivers and by the parity tests).
+    """
+    import threading
+    if isinstance(atoms, str):
+        atoms = (atoms,)
+    cset = GridCoordinatesSetup.from_cell(framework.mat, spacing)
+    nx, ny, nz = cset.nodes
+    n_grids = len(atoms) + int(coulomb)
+    if outs is None:
+        outs = [np.empty((8, nx, ny, nz), dtype=np.float32) for _ in range(n_grids)]
+    i0, i1 = (0, nx) if xrange is None else xrange
+    raw = np.empty((n_grids, 8, i1 - i0, ny, nz), dtype=np.float64) if want_raw else None
+    devices = [0] if devices is None else list(devices)
+    lam_v, thr_v = vdw_scaling()
+    lam_c, thr_c = coulomb_scaling()
+    gs = _lib.make_gridspec(cset)
+    from .probes import probe_inputs
+    inputs = probe_inputs(framework, forcefield, atoms, coulomb, alpha)
+    slabs = [(i0 + a, i0 + b) for a, b in _slabs(i1 - i0, len(devices))]
+    errors = []
+
+    def work(dev, a, b):
+        try:
+            if b <= a:
+                return
+            ps = ProbeSystem(None, None, inputs=inputs, device=dev)
+            try:
+                r = None
+                if raw is not None:
+                    r = np.empty((n_grids, 8, b - a, ny, nz), dtype=np.float64)
+                _lib.grid_build(ps.handle, gs, a, b, lam_v, thr_v, lam_c, thr_c, outs, r)
+                if raw is not None:
+                    raw[:, :, a - i0:b - i0] = r
+            finally:
+                ps.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    if len(devices) == 1:
+        work(devices[0], *slabs[0])
+    else:
+        ths = [threading.Thread(target=work, args=(d, a, b)) for d, (a, b) in zip(devices, slabs)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+    if errors:
+        raise errors[0]
+    return cset, outs, raw
+
+
+def create_grid_vdw(file, framework, forcefield: ForceField, spacing: float, atom: str, devices=None) -> np.ndarray:
+    """grids.jl:137-157."""
+    cset, (grid,), _ = build_grids(framework, forcefield, spacing, atoms=(atom,), devices=devices)
+    num_unitcell = find_supercell(framework.mat, forcefield.cutoff)
+    write_grid(file, cset, num_unitcell, grid)
+    return grid
+
+
+def create_grid_coulomb(file, framework, forcefield: ForceField, spacing: float, _ewald=None, devices=None) -> np.ndarray:
+    """grids.jl:159-185."""
+    from .ewald import EwaldFramework, initialize_ewald
+    num_unitcell = find_supercell(framework.mat, CUTOFF_COULOMB)
+    ewald = _ewald if isinstance(_ewald, EwaldFramework) else initialize_ewald(framework, num_unitcell)
+    cset, (grid,), _ = build_grids(framework, forcefield, spacing, coulomb=True, alpha=ewald.alpha, devices=devices)
+    write_grid(file, cset, num_unitcell, grid, ewald_precision=ewald.precision)
+    return grid
+
+
+# ---- interpolation -----------------------------------------------------------------------------
+def interpolate_grid(g: EnergyGrid, point):
+    """grids.jl:212-273.  `point`: one Cartesian triplet (returns a float) or an (n,3) array
+    (batched method, returns an array).  1e100 marks a blocked VdW position."""
+    if g.ewald_precision == -math.inf:
+        p = np.asarray(point, dtype=np.float64)
+        return 0.0 if p.ndim == 1 else np.zeros(p.reshape(-1, 3).shape[0])
+    if math.isnan(g.ewald_precision):
+        raise ValueError("Invalid grid cannot be interpolated!")
+    p = np.asarray(point, dtype=np.float64)
+    out = _lib.interpolate(g.handle, p.reshape(-1, 3))
+    return float(out[0]) if p.ndim == 1 else out
+
+
+# ---- batched evaluation ------------------------------------------------------------------------
+@dataclass
+class CrystalEnergySetup:
+    """grids.jl:284-294."""
+    framework: object
+    molecule: object
+    coulomb: EnergyGrid
+    charges: np.ndarray
+    grids: list
+    atomsidx: list
+    ewald: object
+    forcefield: ForceField
+    block: BlockFile
+    _block_handle: object = None
+    _ctx: object = None
+
+    def block_handle(self, device=0):
+        if self.block.empty:
+            return None
+        if self._block_handle is None:
+            cs = self.block.csetup
+            self._block_handle = _lib.block_upload(device, unitcell_struct(cs.cell), _lib.make_gridspec(cs), self.block.block)
+        return self._block_handle
+
+    def ewald_ctx(self):
+        if self._ctx is None:
+            from .ewald import ewald_context
+            self._ctx = ewald_context(self.ewald, ((self.molecule,),))
+        return self._ctx
+
+    def __del__(self):
+        h, self._block_handle = self._block_handle, None
+        if h is not None:
+            try:
+                _lib.block_free(h)
+            except Exception:
+                pass
+
+
+def energy_points(setup: CrystalEnergySetup, positions):
+    """Batched energy_point: positions (n_pos, n_atoms, 3) -> (vdw[n_pos], coulomb[n_pos])."""
+    na = len(setup.atomsidx)
+    pos = np.asarray(positions, dtype=np.float64).reshape(-1, na, 3)
+    for g in setup.grids:
+        if math.isnan(g.ewald_precision):
+            raise ValueError("Invalid grid cannot be interpolated!")
+    vdw_handles = [g.handle for g in setup.grids]
+    has_coulomb = setup.coulomb.ewald_precision != -math.inf
+    coul = setup.coulomb.handle if has_coulomb else None
+    ew, enc, static = None, 0.0, 0.0
+    if has_coulomb and setup.ewald.alpha != 0:
+        ctx = setup.ewald_ctx()
+        ew, enc, static = setup.ewald.handle, ctx.energy_net_charges, ctx.static_contribution
+    return _lib.energy_points(vdw_handles, coul, ew, setup.block_handle(), setup.atomsidx, setup.charges, pos, enc, static)
+
+
+def energy_point(setup: CrystalEnergySetup, positions, ctx=None):
+    """grids.jl:311-327 — (vdw, coulomb) in K; (1e100, 0) if an atom sits on a blocking sphere."""
+    v, c = energy_points(setup, np.asarray(positions, dtype=np.float64)[None])
+    return float(v[0]), float(c[0])
+
+
+def energy_grid(setup: CrystalEnergySetup, step: float, num_rotate: int = 40, rotations=None, chunk: int = 1 << 20):
+    """grids.jl:346-424 — energies on a numA x numB x numC lattice along the CELL axes.
+
+    Returns float64 array (n_rot, numA, numB, numC) with vdw+coulomb in K.  The reference draws
+    its rotation set from a Lebedev artifact (lebedev.jl, out of scope): here the
+    rotation matrices are an input (`rotations`, list of 3x3); monoatomic probes or
+    num_rotate == 0 use the identity, exactly as grids.jl:385-390.
+    """
+    mol_pos = np.asarray(setup.molecule.position, dtype=np.float64).reshape(-1, 3)
+    mat = np.asarray(setup.framework.mat, dtype=np.float64)
+    axes = [mat[:, 0], mat[:, 1], mat[:, 2]]
+    nums = [int(math.floor(math.sqrt(float(a @ a)) / step)) + 1 for a in axes]
+    steps = [a / n for a, n in zip(axes, nums)]
+    if num_rotate == 0 or len(mol_pos) == 1 or rotations is None:
+        rotpos = [mol_pos]
+    else:
+        rotpos = [mol_pos @ np.asarray(r, dtype=np.float64).T for r in rotations]
+    numA, numB, numC = nums
+    iA, iB, iC = np.meshgrid(np.arange(numA), np.arange(numB), np.arange(numC), indexing="ij")
+    # thisofs = (iA-1)*stepA + (iB-1)*stepB + (iC-1)*stepC, summed left to right (grids.jl:396)
+    ofs = (iA[..., None] * steps[0] + iB[..., None] * steps[1]) + iC[..., None] * steps[2]
+    ofs = ofs.reshape(-1, 3)
+    allvals = np.empty((len(rotpos), numA * numB * numC), dtype=np.float64)
+    for k, pos in enumerate(rotpos):
+        for s in range(0, ofs.shape[0], chunk):
+            o = ofs[s:s + chunk]
+            buf = o[:, None, :] + pos[None, :, :]
+            v, c = energy_points(setup, buf)
+            allvals[k, s:s + chunk] = v + c
+    return allvals.reshape(len(rotpos), numA, numB, numC)

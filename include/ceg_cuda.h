@@ -1,0 +1,184 @@
+/*
+ * libceg_cuda — C ABI of the B200 (sm_100a) energy-grid hot path.
+ *
+ * The reference (CrystalEnergyGrids.jl) is pure Julia and has no FFI of its own; the drop-in
+ * boundary is its Julia function surface.  Each entry point below replaces the
+ * inner loops of the reference function cited next to it; the Julia-side `ccall` stubs a
+ * maintainer would add are in INTEGRATION.md and julia/CEGCuda.jl, and the Python host mirror
+ * (crystalenergygrids.jl_b200/) binds the same symbols through ctypes.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every function returns 0 on success, non-zero on error, and
+ *    ceg_last_error() then returns a thread-local message (the host shim raises it, like the
+ *    reference's `error(...)`).
+ *  - units are stripped by the caller: Å, K, e.  Every physical constant (GRID_TO_KELVIN,
+ *    COULOMBIC_CONVERSION_FACTOR, thresholds) is an ARGUMENT; the device code carries none.
+ *  - 3x3 matrices are 9 doubles in column-major order (m[3*c+r] = component r of cell vector c),
+ *    i.e. the memory layout of Julia's SMatrix{3,3,Float64,9}.
+ *  - host buffers are owned by the caller (Julia Arrays under GC.@preserve); device memory is
+ *    owned by the library behind opaque handles.  Entry points are blocking and re-entrant
+ *    (one mutex + one stream set per handle), because the reference calls interpolate_grid and
+ *    compute_ewald from concurrent tasks (montecarlo.jl:573-578).
+ *  - functions suffixed `_dev` take DEVICE pointers (on the handle's device) and a cudaStream_t
+ *    passed as void*; they are asynchronous on that stream and exist so that a caller which keeps
+ *    trial positions resident in HBM avoids the PCIe round trip.
+ *  - there is no CPU fallback anywhere: without a usable CUDA device every call fails.
+ */
+#ifndef CEG_CUDA_H
+#define CEG_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEG_ABI_VERSION 1
+
+/* Periodic cell used for minimum-image distances (utils.jl:146-155, 210-246).
+ * `ortho` and `safemin2` are the outputs of prepare_periodic_distance_computations. */
+typedef struct ceg_cell_t {
+    double mat[9];
+    double invmat[9];
+    int32_t ortho;
+    int32_t _pad;
+    double safemin2;
+} ceg_cell_t;
+
+/* GridCoordinatesSetup (coordinates.jl:15-41): dims = nodes-1 per axis. */
+typedef struct ceg_gridspec_t {
+    int32_t dims[3];
+    int32_t _pad;
+    double size[3];
+    double shift[3];
+    double delta[3];
+} ceg_gridspec_t;
+
+/* One (probe species, framework species) entry of ForceField.interactions as seen by
+ * derivativesGrid (interactions.jl:432-472, 599-610).  Terms are summed in the reference's
+ * kind order: HardSphere, Lennard-Jones, Buckingham. */
+#define CEG_PAIR_HS   1
+#define CEG_PAIR_LJ   2
+#define CEG_PAIR_BUCK 4
+typedef struct ceg_pair_t {
+    int32_t flags;     /* OR of CEG_PAIR_*; 0 = NoInteraction; <0 = UndefinedInteraction */
+    int32_t _pad;
+    double hs_r;       /* R1+R2 (Å): value = Inf where r2 < hs_r^2 */
+    double lj_eps, lj_sigma, lj_shift;
+    double buck_A, buck_B, buck_C, buck_shift;
+} ceg_pair_t;
+
+typedef struct ceg_probe_s* ceg_probe_h;   /* ProbeSystem(s)            probes.jl:12-63   */
+typedef struct ceg_grid_s*  ceg_grid_h;    /* device-resident EnergyGrid grids.jl:10-16   */
+typedef struct ceg_ewald_s* ceg_ewald_h;   /* EwaldFramework            ewald.jl:40-50    */
+typedef struct ceg_block_s* ceg_block_h;   /* BlockFile                 coordinates.jl:83 */
+
+const char* ceg_last_error(void);
+int ceg_abi_version(void);
+int ceg_device_count(int32_t* n);
+/* name (<=255 chars), SM count, memory bytes, SM clock kHz of a device */
+int ceg_device_info(int32_t device, char* name256, int32_t* sm_count, int64_t* mem_bytes, int32_t* clock_khz);
+
+/* Pin / unpin a caller-owned host buffer so that slab write-back and query upload overlap compute. */
+int ceg_host_register(void* ptr, int64_t bytes);
+int ceg_host_unregister(void* ptr);
+
+/* ------------------------------------------------------------------------------------------
+ * Grid construction.  Replaces ProbeSystem (probes.jl:21-63), compute_derivatives_vdw /
+ * compute_derivatives_ewald (probes.jl:71-117), derivativesGrid (interactions.jl:432-472),
+ * derivatives_ewald (ewald.jl:299-312), _set_gridpoint! and the @threads loops of
+ * create_grid_vdw / create_grid_coulomb (grids.jl:118-185).
+ *
+ * One handle fuses n_probes VdW probes (table row p) and, if want_coulomb, the Ewald real-space
+ * grid: n_grids = n_probes + want_coulomb, Coulomb last.  xyz/type/charge describe the
+ * REPLICATED supercell (N_sc atoms) and `supercell` is its cell.
+ * ------------------------------------------------------------------------------------------ */
+int ceg_probe_create(int32_t device, const ceg_cell_t* supercell,
+                     int64_t n_atoms, const double* xyz /* n_atoms x 3 */, const int32_t* type /* n_atoms */,
+                     const double* charge /* n_atoms, may be NULL if !want_coulomb */,
+                     int32_t n_types, int32_t n_probes, const ceg_pair_t* table /* n_probes x n_types */,
+                     double cutoff2, int32_t want_coulomb, double alpha,
+                     ceg_probe_h* out);
+int ceg_probe_free(ceg_probe_h h);
+int ceg_probe_num_grids(ceg_probe_h h, int32_t* n_grids);
+
+/* (value, d1[3], d2[3], d3) at arbitrary positions, before _set_gridpoint!:
+ * out[(g*n_pos + i)*8 + c].  Literal per-pair reference algorithm (A3) on the device. */
+int ceg_compute_derivatives(ceg_probe_h h, int64_t n_pos, const double* xyz /* n_pos x 3 */, double* out);
+
+/* Build the x-slab [i0, i1) of every grid of the handle (i in 0..dims[0], the reference's
+ * @threads axis, grids.jl:144,171).  out_f32[g] points at the FULL host array of grid g in the
+ * reference/.grid order [8][nx][ny][nz] (z fastest); only planes i0..i1-1 are written.
+ * lambda/thr per grid kind as in grids.jl:142-143,169-170.
+ * raw_f64 (optional, may be NULL): pre-quantisation derivatives of the slab,
+ * raw_f64[((g*8 + c)*(i1-i0) + (i-i0))*ny*nz + j*nz + k] — used by the parity tests. */
+int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1,
+                   double lambda_vdw, double thr_vdw, double lambda_coul, double thr_coul,
+                   float* const* out_f32 /* n_grids host pointers, entries may be NULL */, double* raw_f64);
+
+/* Same, leaving the slab on the device: d_out[g] = device buffer [8][i1-i0][ny][nz] floats.
+ * Asynchronous on `stream`.  Returns the kernel's algorithmic pair counts through
+ * ceg_probe_last_stats. */
+int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1,
+                       double lambda_vdw, double thr_vdw, double lambda_coul, double thr_coul,
+                       float* const* d_out, void* stream);
+
+/* Work counters of the last build on this handle (after a sync): number of grid points,
+ * number of (point, atom image) pairs tested, number inside the cutoff. */
+int ceg_probe_last_stats(ceg_probe_h h, int64_t* n_points, int64_t* pairs_tested, int64_t* pairs_in_cutoff);
+
+/* ------------------------------------------------------------------------------------------
+ * Interpolation.  Replaces interpolate_grid (grids.jl:212-273) + offsetpoint
+ * (coordinates.jl:58-66).  `grid` is the host array AFTER parse_grid (values already multiplied
+ * by GRID_TO_KELVIN, grids.jl:78), reference order [8][nx][ny][nz]; it is re-laid out on the
+ * device as node-major records.  is_vdw selects the >5e6 K corner test returning 1e100
+ * (grids.jl:245-248).
+ * ------------------------------------------------------------------------------------------ */
+int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs,
+                    const float* grid, int32_t is_vdw, ceg_grid_h* out);
+int ceg_grid_free(ceg_grid_h h);
+int ceg_interpolate(ceg_grid_h h, int64_t n, const double* xyz /* n x 3 Cartesian Å */, double* out /* n, K */);
+int ceg_interpolate_dev(ceg_grid_h h, int64_t n, const double* d_xyz, double* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ewald reciprocal space.  ceg_ewald_create replaces setup_Eik + ewald_main_loop! for the
+ * framework (ewald.jl:109-185, 264-271): S_f(k) = sum_sites q exp(2 pi i (ix fx + jy fy + jz fz))
+ * over the n_sites supercell sites given in SUPERCELL-fractional coordinates.
+ * kvec[3*m..] = (ix, jy, jz) of k-vector m in kindices order (ewald.jl:213-236); kfactor as
+ * ewald.jl:247-259.  S_f_reim (n_k x 2) is returned to the caller (StoreRigidChargeFramework).
+ * ceg_ewald_reciprocal replaces move_one_system! + compute_ewald(ctx) (ewald.jl:350-364,555-577)
+ * for n_pos independent placements of one rigid set of n_atoms charges:
+ *   out = 2*(sum_k kf Re(S_f conj S_a) + energy_net_charges) + (sum_k kf |S_a|^2 + static_contribution)
+ * ------------------------------------------------------------------------------------------ */
+int ceg_ewald_create(int32_t device, const double* invmat /* supercell inverse, 9 doubles */,
+                     const int32_t kmax[3], int64_t n_k, const int32_t* kvec, const double* kfactor,
+                     int64_t n_sites, const double* frac /* n_sites x 3 */, const double* charge,
+                     ceg_ewald_h* out, double* S_f_reim);
+int ceg_ewald_free(ceg_ewald_h h);
+int ceg_ewald_reciprocal(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms,
+                         const double* xyz /* n_pos x n_atoms x 3 Cartesian Å */, const double* q /* n_atoms */,
+                         double energy_net_charges, double static_contribution, double* out /* n_pos, K */);
+int ceg_ewald_reciprocal_dev(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, const double* d_xyz, const double* q_host,
+                             double energy_net_charges, double static_contribution, double* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Blocking mask (coordinates.jl:83-101) and fused batched evaluation: energy_point over n_pos
+ * placements (grids.jl:311-327), the inner loop of energy_grid (grids.jl:394-419).
+ * mask: nx*ny*nz bytes, index (a*ny + b)*nz + c with (a,b,c) = round(offsetpoint)-1.
+ * For each placement: blocked -> (1e100, 0); else vdw = sum_i interp(vdw[atomsidx[i]], pos_i),
+ * coulomb = sum_i q_i interp(coulomb, pos_i) + reciprocal.
+ * vdw[g] may be NULL (zero grid, ewald_precision == -Inf); coulomb/ewald/block may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int ceg_block_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs,
+                     const uint8_t* mask, ceg_block_h* out);
+int ceg_block_free(ceg_block_h h);
+int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, ceg_ewald_h ewald, ceg_block_h block,
+                      int64_t n_pos, int32_t n_atoms, const int32_t* atomsidx /* n_atoms, 0-based into vdw[] */,
+                      const double* charges /* n_atoms */, const double* xyz /* n_pos x n_atoms x 3 */,
+                      double energy_net_charges, double static_contribution,
+                      double* out_vdw /* n_pos */, double* out_coulomb /* n_pos */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEG_CUDA_H */
