@@ -1,0 +1,805 @@
+// libceg_cuda — C ABI implementation (include/ceg_cuda.h).  sm_100a only; no CPU fallback.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+
+#include "common.cuh"
+#include "ewald.cuh"
+#include "grid_build.cuh"
+#include "interp.cuh"
+
+namespace ceg {
+
+std::string& last_error() {
+    static thread_local std::string e;
+    return e;
+}
+int fail(const std::string& msg) {
+    last_error() = msg;
+    return 1;
+}
+int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[768];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    cudaGetLastError();  // clear sticky-less error state
+    return fail(buf);
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int use_device(int dev) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(std::string("no usable CUDA device (libceg_cuda has no CPU fallback): ") + cudaGetErrorString(e));
+    if (dev < 0 || dev >= n) return fail("device ordinal out of range");
+    CEG_CK(cudaSetDevice(dev));
+    return 0;
+}
+
+}  // namespace ceg
+
+using namespace ceg;
+
+// ================================================================================================
+// handles
+// ================================================================================================
+struct ceg_probe_s {
+    int device = 0;
+    std::mutex mu;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    CellDev cell;
+    double cutoff2 = 0, alpha = 0;
+    int n_probes = 0, want_coulomb = 0, n_types = 0;
+    int64_t n_atoms = 0;
+    std::vector<double> h_xyz, h_q;
+    std::vector<int> h_type;
+    double max_hs_r2 = 0;
+    double min_perp_width = 0;
+    DevBuf d_xyz, d_type, d_q, d_table, d_stats;
+    // cached expanded image list
+    DevBuf d_ext, d_ext_meta;
+    int n_ext = 0;
+    double ext_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool ext_valid = false;
+    // scratch for host-facing builds
+    DevBuf d_out, d_raw, d_pos, d_der;
+    int64_t last_points = 0;
+};
+
+struct ceg_grid_s {
+    int device = 0;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    GridDev g;
+    DevBuf d_nodes, d_xyz, d_out;
+};
+
+struct ceg_ewald_s {
+    int device = 0;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    double invmat[9];
+    int kmax[3];
+    int64_t n_k = 0;
+    DevBuf d_kv, d_xyz, d_out, d_q;
+};
+
+struct ceg_block_s {
+    int device = 0;
+    BlockDev b;
+    DevBuf d_mask;
+};
+
+// ================================================================================================
+// misc
+// ================================================================================================
+extern "C" const char* ceg_last_error(void) { return last_error().c_str(); }
+extern "C" int ceg_abi_version(void) { return CEG_ABI_VERSION; }
+
+extern "C" int ceg_device_count(int32_t* n) {
+    if (!n) return fail("null argument");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *n = c;
+    return 0;
+}
+
+extern "C" int ceg_device_info(int32_t device, char* name256, int32_t* sm_count, int64_t* mem_bytes, int32_t* clock_khz) {
+    if (use_device(device)) return 1;
+    cudaDeviceProp p;
+    CEG_CK(cudaGetDeviceProperties(&p, device));
+    if (name256) { strncpy(name256, p.name, 255); name256[255] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (mem_bytes) *mem_bytes = (int64_t)p.totalGlobalMem;
+    if (clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        *clock_khz = khz;
+    }
+    return 0;
+}
+
+extern "C" int ceg_kernel_launch_count(int64_t* n) {
+    if (!n) return fail("null argument");
+    *n = (int64_t)g_launches.load();
+    return 0;
+}
+
+namespace ceg {
+// 8 independent FMA chains per thread; the result is stored so the chains cannot be removed.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace ceg
+
+extern "C" int ceg_measure_fp64_peak(int32_t device, double* tflops) {
+    if (!tflops) return fail("null argument");
+    if (use_device(device)) return 1;
+    cudaDeviceProp p;
+    CEG_CK(cudaGetDeviceProperties(&p, device));
+    const int blocks = p.multiProcessorCount * 8, threads = 256, iters = 4096;
+    DevBuf buf;
+    CEG_CK(buf.reserve(sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CEG_CK(cudaEventCreate(&e0));
+    CEG_CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CEG_CK(cudaEventRecord(e0, 0));
+        fp64_peak_kernel<<<blocks, threads>>>(buf.as<double>(), iters, 0.999999, 1e-9);
+        count_launch();
+        CEG_CK(cudaGetLastError());
+        CEG_CK(cudaEventRecord(e1, 0));
+        CEG_CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CEG_CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 64.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return 0;
+}
+
+extern "C" int ceg_host_register(void* ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail("ceg_host_register: bad argument");
+    CEG_CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+}
+extern "C" int ceg_host_unregister(void* ptr) {
+    CEG_CK(cudaHostUnregister(ptr));
+    return 0;
+}
+
+// ================================================================================================
+// probes / grid construction
+// ================================================================================================
+static double perp_width_min(const double* m) {
+    auto cross = [](const double* u, const double* v, double* o) {
+        o[0] = u[1] * v[2] - u[2] * v[1]; o[1] = u[2] * v[0] - u[0] * v[2]; o[2] = u[0] * v[1] - u[1] * v[0];
+    };
+    const double *a = m, *b = m + 3, *c = m + 6;
+    double bxc[3], cxa[3], axb[3];
+    cross(b, c, bxc); cross(c, a, cxa); cross(a, b, axb);
+    double vol = std::fabs(a[0] * bxc[0] + a[1] * bxc[1] + a[2] * bxc[2]);
+    auto nrm = [](const double* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    return std::min(vol / nrm(bxc), std::min(vol / nrm(cxa), vol / nrm(axb)));
+}
+
+extern "C" int ceg_probe_create(int32_t device, const ceg_cell_t* supercell, int64_t n_atoms, const double* xyz,
+                                const int32_t* type, const double* charge, int32_t n_types, int32_t n_probes,
+                                const ceg_pair_t* table, double cutoff2, int32_t want_coulomb, double alpha,
+                                ceg_probe_h* out) {
+    if (!supercell || !out || n_atoms < 0 || (n_atoms > 0 && (!xyz || !type))) return fail("ceg_probe_create: null argument");
+    if (n_probes < 0 || n_probes > MAX_GRIDS - 1) return fail("ceg_probe_create: at most 4 fused VdW probes per handle");
+    if (n_probes + (want_coulomb ? 1 : 0) == 0) return fail("ceg_probe_create: nothing to compute");
+    if (want_coulomb && !charge && n_atoms > 0) return fail("ceg_probe_create: charges required for the Coulomb grid");
+    if (n_probes > 0 && (!table || n_types <= 0)) return fail("ceg_probe_create: pair table required");
+    if (!(cutoff2 > 0) || !std::isfinite(cutoff2)) return fail("ceg_probe_create: cutoff must be finite and positive");
+    for (int64_t i = 0; i < n_atoms; i++)
+        if (n_probes > 0 && (type[i] < 0 || type[i] >= n_types)) return fail("ceg_probe_create: atom type out of range");
+    for (int p = 0; p < n_probes; p++)
+        for (int64_t i = 0; i < n_atoms; i++)
+            if (table[(size_t)p * n_types + type[i]].flags < 0) return fail("Undefined interaction");
+    if (use_device(device)) return 1;
+    std::unique_ptr<ceg_probe_s> h(new ceg_probe_s);
+    h->device = device;
+    h->cell = to_dev(*supercell);
+    h->cutoff2 = cutoff2;
+    h->alpha = alpha;
+    h->n_probes = n_probes;
+    h->want_coulomb = want_coulomb ? 1 : 0;
+    h->n_types = n_types;
+    h->n_atoms = n_atoms;
+    h->h_xyz.assign(xyz, xyz + 3 * n_atoms);
+    h->h_type.assign(type, type + n_atoms);
+    if (want_coulomb) h->h_q.assign(charge, charge + n_atoms); else h->h_q.assign(n_atoms, 0.0);
+    h->min_perp_width = perp_width_min(supercell->mat);
+    std::vector<PairDev> tab((size_t)std::max(1, n_probes * n_types));
+    for (int i = 0; i < n_probes * n_types; i++) {
+        const ceg_pair_t& s = table[i];
+        PairDev& d = tab[i];
+        d.flags = s.flags; d._pad = 0;
+        d.hs_r2 = s.hs_r * s.hs_r;
+        d.lj_eps = s.lj_eps; d.lj_sig2 = s.lj_sigma * s.lj_sigma; d.lj_shift = s.lj_shift;
+        d.bA = s.buck_A; d.bB = s.buck_B; d.bC = s.buck_C; d.b_shift = s.buck_shift;
+        if (s.flags & CEG_PAIR_HS) h->max_hs_r2 = std::max(h->max_hs_r2, d.hs_r2);
+    }
+    CEG_CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CEG_CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * std::max<int64_t>(1, n_atoms)));
+    CEG_CK(h->d_type.reserve(sizeof(int) * std::max<int64_t>(1, n_atoms)));
+    CEG_CK(h->d_q.reserve(sizeof(double) * std::max<int64_t>(1, n_atoms)));
+    CEG_CK(h->d_table.reserve(sizeof(PairDev) * tab.size()));
+    CEG_CK(h->d_stats.reserve(2 * sizeof(unsigned long long)));
+    if (n_atoms > 0) {
+        CEG_CK(cudaMemcpy(h->d_xyz.p, h->h_xyz.data(), sizeof(double) * 3 * n_atoms, cudaMemcpyHostToDevice));
+        CEG_CK(cudaMemcpy(h->d_type.p, h->h_type.data(), sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
+        CEG_CK(cudaMemcpy(h->d_q.p, h->h_q.data(), sizeof(double) * n_atoms, cudaMemcpyHostToDevice));
+    }
+    CEG_CK(cudaMemcpy(h->d_table.p, tab.data(), sizeof(PairDev) * tab.size(), cudaMemcpyHostToDevice));
+    CEG_CK(cudaMemset(h->d_stats.p, 0, 2 * sizeof(unsigned long long)));
+    *out = h.release();
+    return 0;
+}
+
+extern "C" int ceg_probe_free(ceg_probe_h h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    delete h;
+    return 0;
+}
+
+extern "C" int ceg_probe_num_grids(ceg_probe_h h, int32_t* n) {
+    if (!h || !n) return fail("null argument");
+    *n = h->n_probes + h->want_coulomb;
+    return 0;
+}
+
+extern "C" int ceg_compute_derivatives(ceg_probe_h h, int64_t n_pos, const double* xyz, double* out) {
+    if (!h || (n_pos > 0 && (!xyz || !out)) || n_pos < 0) return fail("ceg_compute_derivatives: bad argument");
+    if (n_pos == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    const int ng = h->n_probes + h->want_coulomb;
+    CEG_CK(h->d_pos.reserve(sizeof(double) * 3 * n_pos));
+    CEG_CK(h->d_der.reserve(sizeof(double) * 8 * n_pos * ng));
+    CEG_CK(cudaMemcpyAsync(h->d_pos.p, xyz, sizeof(double) * 3 * n_pos, cudaMemcpyHostToDevice, h->s_compute));
+    LiteralParams P;
+    P.cell = h->cell; P.cutoff2 = h->cutoff2; P.alpha = h->alpha;
+    P.n_atoms = h->n_atoms; P.n_pos = n_pos;
+    P.xyz = h->d_xyz.as<double>(); P.type = h->d_type.as<int>(); P.q = h->d_q.as<double>();
+    P.table = h->d_table.as<PairDev>();
+    P.n_types = h->n_types; P.n_probes = h->n_probes; P.want_coulomb = h->want_coulomb;
+    P.pos = h->d_pos.as<double>(); P.out = h->d_der.as<double>();
+    const int blocks = (int)std::min<int64_t>((n_pos + 127) / 128, 148 * 16);
+    derivatives_literal_kernel<<<blocks, 128, 0, h->s_compute>>>(P);
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    CEG_CK(cudaMemcpyAsync(out, h->d_der.p, sizeof(double) * 8 * n_pos * ng, cudaMemcpyDeviceToHost, h->s_compute));
+    CEG_CK(cudaStreamSynchronize(h->s_compute));
+    return 0;
+}
+
+// ---- expanded image list ----------------------------------------------------------------------------
+// All periodic images a + n1*A + n2*B + n3*C (A,B,C = supercell vectors) lying inside the box
+// [lo - reach, hi + reach], emitted atom by atom (the reference's summation order, probes.jl:80).
+static void build_ext_list(const ceg_probe_s* h, const double lo[3], const double hi[3], double reach,
+                           std::vector<ExtAtom>& ext, std::vector<ExtMeta>& meta) {
+    const double* m = h->cell.mat;
+    const double* im = h->cell.invmat;
+    double blo[3], bhi[3];
+    for (int d = 0; d < 3; d++) { blo[d] = lo[d] - reach; bhi[d] = hi[d] + reach; }
+    // fractional bounding range of the box
+    double fmin[3] = {1e300, 1e300, 1e300}, fmax[3] = {-1e300, -1e300, -1e300};
+    for (int c = 0; c < 8; c++) {
+        double p[3] = {(c & 1) ? bhi[0] : blo[0], (c & 2) ? bhi[1] : blo[1], (c & 4) ? bhi[2] : blo[2]};
+        for (int r = 0; r < 3; r++) {
+            double f = im[r] * p[0] + im[3 + r] * p[1] + im[6 + r] * p[2];
+            fmin[r] = std::min(fmin[r], f);
+            fmax[r] = std::max(fmax[r], f);
+        }
+    }
+    ext.clear();
+    meta.clear();
+    for (int64_t a = 0; a < h->n_atoms; a++) {
+        const double* p = &h->h_xyz[3 * a];
+        double f[3];
+        for (int r = 0; r < 3; r++) f[r] = im[r] * p[0] + im[3 + r] * p[1] + im[6 + r] * p[2];
+        int n0[3], n1[3];
+        for (int r = 0; r < 3; r++) {
+            n0[r] = (int)std::floor(fmin[r] - f[r] - 1e-9);
+            n1[r] = (int)std::ceil(fmax[r] - f[r] + 1e-9);
+        }
+        for (int i1 = n0[0]; i1 <= n1[0]; i1++)
+            for (int i2 = n0[1]; i2 <= n1[1]; i2++)
+                for (int i3 = n0[2]; i3 <= n1[2]; i3++) {
+                    double q[3];
+                    for (int r = 0; r < 3; r++) q[r] = p[r] + ((double)i1 * m[r] + (double)i2 * m[3 + r] + (double)i3 * m[6 + r]);
+                    if (q[0] < blo[0] || q[0] > bhi[0] || q[1] < blo[1] || q[1] > bhi[1] || q[2] < blo[2] || q[2] > bhi[2])
+                        continue;
+                    ext.push_back(ExtAtom{q[0], q[1], q[2], h->h_q[a]});
+                    meta.push_back(ExtMeta{h->h_type[a], (int)a});
+                }
+    }
+}
+
+template <int TX, int TY, int TZ, int NP, bool COUL>
+static cudaError_t launch_tiled(const BuildParams& P, int n_tiles, cudaStream_t s) {
+    grid_build_tiled_kernel<TX, TY, TZ, NP, COUL><<<n_tiles, TX * TY * TZ, 0, s>>>(P);
+    count_launch();
+    return cudaGetLastError();
+}
+
+struct TileShape { int tx, ty, tz; };
+static TileShape tile_shape(int n_probes) { return n_probes <= 2 ? TileShape{8, 8, 8} : TileShape{4, 8, 8}; }
+
+static cudaError_t dispatch_tiled(int np, bool coul, const BuildParams& P, int n_tiles, cudaStream_t s) {
+#define CASE(NP_, C_)                                                                   \
+    if (np == NP_ && coul == C_) {                                                      \
+        if (NP_ <= 2) return launch_tiled<8, 8, 8, NP_, C_>(P, n_tiles, s);             \
+        return launch_tiled<4, 8, 8, NP_, C_>(P, n_tiles, s);                           \
+    }
+    CASE(0, true) CASE(1, false) CASE(1, true) CASE(2, false) CASE(2, true)
+    CASE(3, false) CASE(3, true) CASE(4, false) CASE(4, true)
+#undef CASE
+    return cudaErrorInvalidValue;
+}
+
+// Fill BuildParams and make sure the image list for slab [i0,i1) is resident.
+static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i1, double lam_v, double thr_v,
+                         double lam_c, double thr_c, BuildParams& P) {
+    if (!gs) return fail("null gridspec");
+    for (int d = 0; d < 3; d++)
+        if (gs->dims[d] < 1 || !(gs->size[d] > 0)) return fail("bad grid spec");
+    if (i0 < 0 || i1 > gs->dims[0] + 1 || i0 >= i1) return fail("bad x-slab range");
+    const double cutoff = std::sqrt(h->cutoff2);
+    if (!(2.0 * cutoff <= h->min_perp_width * (1.0 + 1e-12)))
+        return fail("cutoff exceeds half the perpendicular width of the probe supercell: the tiled kernel requires "
+                    "the supercell of probes.jl:24 (use ceg_compute_derivatives for the literal algorithm)");
+    P.cell = h->cell;
+    P.gs = to_dev(*gs);
+    P.cutoff2 = h->cutoff2;
+    P.alpha = h->alpha;
+    P.cut_hi = h->cutoff2 + GUARD_BAND;
+    P.cut_lo = h->cutoff2 - GUARD_BAND;
+    double small = h->max_hs_r2;
+    if (h->want_coulomb) small = std::max(small, 1.0);
+    P.small_hi = small > 0 ? small + GUARD_BAND : -1.0;
+    P.stale_lo = (h->cell.ortho || h->cell.safemin2 >= h->cutoff2) ? std::numeric_limits<double>::infinity()
+                                                                    : h->cell.safemin2 - GUARD_BAND;
+    const TileShape ts = tile_shape(h->n_probes);
+    const double hx = 0.5 * (ts.tx - 1) * gs->delta[0], hy = 0.5 * (ts.ty - 1) * gs->delta[1], hz = 0.5 * (ts.tz - 1) * gs->delta[2];
+    const double reach = cutoff + std::sqrt(hx * hx + hy * hy + hz * hz) + 1e-6;
+    P.reach2 = reach * reach;
+    P.lam_v = lam_v; P.thr_v = thr_v; P.lam_c = lam_c; P.thr_c = thr_c;
+    P.i0 = i0; P.i1 = i1; P.a0 = i0; P.a1 = i1;
+    P.tiles_y = (gs->dims[1] + 1 + ts.ty - 1) / ts.ty;
+    P.tiles_z = (gs->dims[2] + 1 + ts.tz - 1) / ts.tz;
+    P.tiles_x = (i1 - i0 + ts.tx - 1) / ts.tx;
+    P.atoms_xyz = h->d_xyz.as<double>();
+    P.table = h->d_table.as<PairDev>();
+    P.n_types = h->n_types;
+    for (int g = 0; g < MAX_GRIDS; g++) P.out[g] = nullptr;
+    P.raw = nullptr;
+    P.stats = h->d_stats.as<unsigned long long>();
+    // image list for the slab's bounding box
+    double lo[3], hi[3];
+    lo[0] = i0 * gs->size[0] / gs->dims[0] + gs->shift[0];
+    hi[0] = (i1 - 1) * gs->size[0] / gs->dims[0] + gs->shift[0];
+    for (int d = 1; d < 3; d++) { lo[d] = gs->shift[d]; hi[d] = gs->shift[d] + gs->size[d]; }
+    double key[8] = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], cutoff, reach};
+    if (!h->ext_valid || memcmp(key, h->ext_key, sizeof key) != 0) {
+        std::vector<ExtAtom> ext;
+        std::vector<ExtMeta> meta;
+        build_ext_list(h, lo, hi, reach + 1e-6, ext, meta);
+        h->n_ext = (int)ext.size();
+        CEG_CK(h->d_ext.reserve(sizeof(ExtAtom) * std::max<size_t>(1, ext.size())));
+        CEG_CK(h->d_ext_meta.reserve(sizeof(ExtMeta) * std::max<size_t>(1, meta.size())));
+        if (!ext.empty()) {
+            CEG_CK(cudaMemcpy(h->d_ext.p, ext.data(), sizeof(ExtAtom) * ext.size(), cudaMemcpyHostToDevice));
+            CEG_CK(cudaMemcpy(h->d_ext_meta.p, meta.data(), sizeof(ExtMeta) * meta.size(), cudaMemcpyHostToDevice));
+        }
+        memcpy(h->ext_key, key, sizeof key);
+        h->ext_valid = true;
+    }
+    P.ext = h->d_ext.as<ExtAtom>();
+    P.ext_meta = h->d_ext_meta.as<ExtMeta>();
+    P.n_ext = h->n_ext;
+    return 0;
+}
+
+extern "C" int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
+                                  double thr_vdw, double lambda_coul, double thr_coul, float* const* d_out, void* stream) {
+    if (!h || !d_out) return fail("ceg_grid_build_dev: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    BuildParams P;
+    if (prepare_build(h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, P)) return 1;
+    const int ng = h->n_probes + h->want_coulomb;
+    for (int g = 0; g < ng; g++) P.out[g] = d_out[g];
+    cudaStream_t s = (cudaStream_t)stream;
+    CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), s));
+    const int n_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
+    CEG_CK(dispatch_tiled(h->n_probes, h->want_coulomb != 0, P, n_tiles, s));
+    h->last_points = (int64_t)(i1 - i0) * (gs->dims[1] + 1) * (gs->dims[2] + 1);
+    return 0;
+}
+
+extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
+                              double thr_vdw, double lambda_coul, double thr_coul, float* const* out_f32, double* raw_f64) {
+    if (!h) return fail("ceg_grid_build: null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    BuildParams P;
+    if (prepare_build(h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, P)) return 1;
+    const int ng = h->n_probes + h->want_coulomb;
+    const int64_t ny = gs->dims[1] + 1, nz = gs->dims[2] + 1, nx = gs->dims[0] + 1;
+    const int64_t plane = ny * nz, slab = (int64_t)(i1 - i0) * plane, npts = nx * plane;
+    bool any_out = false;
+    for (int g = 0; g < ng; g++) any_out |= (out_f32 && out_f32[g]);
+    if (any_out) CEG_CK(h->d_out.reserve(sizeof(float) * 8 * slab * ng));
+    if (raw_f64) CEG_CK(h->d_raw.reserve(sizeof(double) * 8 * slab * ng));
+    for (int g = 0; g < ng; g++) P.out[g] = (out_f32 && out_f32[g]) ? h->d_out.as<float>() + (int64_t)g * 8 * slab : nullptr;
+    P.raw = raw_f64 ? h->d_raw.as<double>() : nullptr;
+    CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), h->s_compute));
+    // x-chunks: compute chunk c on s_compute while chunk c-1 drains to the host on s_copy
+    const TileShape ts = tile_shape(h->n_probes);
+    const int chunk = std::max(ts.tx, ((int)((48ll << 20) / (plane * 8 * 4 * ng)) / ts.tx) * ts.tx);
+    std::vector<cudaEvent_t> evs;
+    int rc = 0;
+    for (int a = i0; a < i1 && !rc; a += chunk) {
+        const int b = std::min(i1, a + chunk);
+        P.a0 = a; P.a1 = b;
+        P.tiles_x = (b - a + ts.tx - 1) / ts.tx;
+        const int n_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
+        cudaError_t e = dispatch_tiled(h->n_probes, h->want_coulomb != 0, P, n_tiles, h->s_compute);
+        if (e != cudaSuccess) { rc = fail_cuda(e, "grid_build_tiled_kernel", __FILE__, __LINE__); break; }
+        if (any_out) {
+            cudaEvent_t ev;
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            cudaEventRecord(ev, h->s_compute);
+            cudaStreamWaitEvent(h->s_copy, ev, 0);
+            evs.push_back(ev);
+            for (int g = 0; g < ng && !rc; g++) {
+                if (!P.out[g]) continue;
+                for (int c = 0; c < 8; c++) {
+                    const float* src = P.out[g] + (int64_t)c * slab + (int64_t)(a - i0) * plane;
+                    float* dst = out_f32[g] + (int64_t)c * npts + (int64_t)a * plane;
+                    e = cudaMemcpyAsync(dst, src, sizeof(float) * (int64_t)(b - a) * plane, cudaMemcpyDeviceToHost, h->s_copy);
+                    if (e != cudaSuccess) { rc = fail_cuda(e, "cudaMemcpyAsync(D2H slab)", __FILE__, __LINE__); break; }
+                }
+            }
+        }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->s_compute);
+    cudaError_t e2 = cudaStreamSynchronize(h->s_copy);
+    for (auto ev : evs) cudaEventDestroy(ev);
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return fail_cuda(e1, "grid build (compute stream)", __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return fail_cuda(e2, "grid build (copy stream)", __FILE__, __LINE__);
+    if (raw_f64) CEG_CK(cudaMemcpy(raw_f64, h->d_raw.p, sizeof(double) * 8 * slab * ng, cudaMemcpyDeviceToHost));
+    h->last_points = slab;
+    return 0;
+}
+
+extern "C" int ceg_probe_last_stats(ceg_probe_h h, int64_t* n_points, int64_t* pairs_tested, int64_t* pairs_in_cutoff) {
+    if (!h) return fail("null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    unsigned long long st[2];
+    CEG_CK(cudaMemcpy(st, h->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
+    if (n_points) *n_points = h->last_points;
+    if (pairs_tested) *pairs_tested = (int64_t)st[0];
+    if (pairs_in_cutoff) *pairs_in_cutoff = (int64_t)st[1];
+    return 0;
+}
+
+// ================================================================================================
+// interpolation
+// ================================================================================================
+extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* grid,
+                               int32_t is_vdw, ceg_grid_h* out) {
+    if (!unitcell || !gs || !grid || !out) return fail("ceg_grid_upload: null argument");
+    for (int d = 0; d < 3; d++)
+        if (gs->dims[d] < 1) return fail("ceg_grid_upload: bad dims");
+    if (use_device(device)) return 1;
+    std::unique_ptr<ceg_grid_s> h(new ceg_grid_s);
+    h->device = device;
+    h->g.uc = to_dev(*unitcell);
+    h->g.gs = to_dev(*gs);
+    h->g.is_vdw = is_vdw ? 1 : 0;
+    const int64_t npts = (int64_t)(gs->dims[0] + 1) * (gs->dims[1] + 1) * (gs->dims[2] + 1);
+    CEG_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CEG_CK(h->d_nodes.reserve(sizeof(float) * 8 * npts));
+    {
+        DevBuf tmp;
+        CEG_CK(tmp.reserve(sizeof(float) * 8 * npts));
+        CEG_CK(cudaMemcpyAsync(tmp.p, grid, sizeof(float) * 8 * npts, cudaMemcpyHostToDevice, h->stream));
+        const int blocks = (int)std::min<int64_t>((npts + 255) / 256, 148 * 32);
+        relayout_nodes_kernel<<<blocks, 256, 0, h->stream>>>(tmp.as<float>(), h->d_nodes.as<float4>(), npts);
+        count_launch();
+        CEG_CK(cudaGetLastError());
+        CEG_CK(cudaStreamSynchronize(h->stream));
+    }
+    h->g.nodes = h->d_nodes.as<float4>();
+    *out = h.release();
+    return 0;
+}
+
+extern "C" int ceg_grid_free(ceg_grid_h h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+static int interp_blocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 64)); }
+
+extern "C" int ceg_interpolate_dev(ceg_grid_h h, int64_t n, const double* d_xyz, double* d_out, void* stream) {
+    if (!h || n < 0 || (n > 0 && (!d_xyz || !d_out))) return fail("ceg_interpolate_dev: bad argument");
+    if (n == 0) return 0;
+    if (use_device(h->device)) return 1;
+    interpolate_kernel<<<interp_blocks(n), 256, 0, (cudaStream_t)stream>>>(h->g, n, d_xyz, d_out);
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ceg_interpolate(ceg_grid_h h, int64_t n, const double* xyz, double* out) {
+    if (!h || n < 0 || (n > 0 && (!xyz || !out))) return fail("ceg_interpolate: bad argument");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * n));
+    CEG_CK(h->d_out.reserve(sizeof(double) * n));
+    CEG_CK(cudaMemcpyAsync(h->d_xyz.p, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    interpolate_kernel<<<interp_blocks(n), 256, 0, h->stream>>>(h->g, n, h->d_xyz.as<double>(), h->d_out.as<double>());
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    CEG_CK(cudaMemcpyAsync(out, h->d_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CEG_CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ================================================================================================
+// Ewald
+// ================================================================================================
+extern "C" int ceg_ewald_create(int32_t device, const double* invmat, const int32_t kmax[3], int64_t n_k,
+                                const int32_t* kvec, const double* kfactor, int64_t n_sites, const double* frac,
+                                const double* charge, ceg_ewald_h* out, double* S_f_reim) {
+    if (!invmat || !kmax || !out || n_k < 0 || n_sites < 0) return fail("ceg_ewald_create: bad argument");
+    if (n_k > 0 && (!kvec || !kfactor)) return fail("ceg_ewald_create: null k-list");
+    if (n_sites > 0 && (!frac || !charge)) return fail("ceg_ewald_create: null sites");
+    for (int64_t k = 0; k < n_k; k++)
+        if (kvec[3 * k] < 0 || kvec[3 * k] > kmax[0] || std::abs(kvec[3 * k + 1]) > kmax[1] || std::abs(kvec[3 * k + 2]) > kmax[2])
+            return fail("ceg_ewald_create: k-vector outside kmax");
+    if (use_device(device)) return 1;
+    std::unique_ptr<ceg_ewald_s> h(new ceg_ewald_s);
+    h->device = device;
+    memcpy(h->invmat, invmat, sizeof h->invmat);
+    for (int d = 0; d < 3; d++) h->kmax[d] = kmax[d];
+    h->n_k = n_k;
+    CEG_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CEG_CK(h->d_kv.reserve(sizeof(KVecDev) * std::max<int64_t>(1, n_k)));
+    if (n_k > 0) {
+        DevBuf d_kvec, d_kf, d_frac, d_q, d_part, d_S;
+        const int n_blocks = (int)std::max<int64_t>(1, (n_sites + SF_SITES_PER_BLOCK - 1) / SF_SITES_PER_BLOCK);
+        CEG_CK(d_kvec.reserve(sizeof(int) * 3 * n_k));
+        CEG_CK(d_kf.reserve(sizeof(double) * n_k));
+        CEG_CK(d_frac.reserve(sizeof(double) * 3 * std::max<int64_t>(1, n_sites)));
+        CEG_CK(d_q.reserve(sizeof(double) * std::max<int64_t>(1, n_sites)));
+        CEG_CK(d_part.reserve(sizeof(double2) * n_k * n_blocks));
+        CEG_CK(d_S.reserve(sizeof(double) * 2 * n_k));
+        CEG_CK(cudaMemcpyAsync(d_kvec.p, kvec, sizeof(int) * 3 * n_k, cudaMemcpyHostToDevice, h->stream));
+        CEG_CK(cudaMemcpyAsync(d_kf.p, kfactor, sizeof(double) * n_k, cudaMemcpyHostToDevice, h->stream));
+        if (n_sites > 0) {
+            CEG_CK(cudaMemcpyAsync(d_frac.p, frac, sizeof(double) * 3 * n_sites, cudaMemcpyHostToDevice, h->stream));
+            CEG_CK(cudaMemcpyAsync(d_q.p, charge, sizeof(double) * n_sites, cudaMemcpyHostToDevice, h->stream));
+        }
+        dim3 grid((unsigned)((n_k + SF_THREADS - 1) / SF_THREADS), (unsigned)n_blocks);
+        structure_factor_kernel<<<grid, SF_THREADS, 0, h->stream>>>(n_k, d_kvec.as<int>(), n_sites, d_frac.as<double>(),
+                                                                   d_q.as<double>(), d_part.as<double2>());
+        count_launch();
+        CEG_CK(cudaGetLastError());
+        structure_factor_reduce_kernel<<<(unsigned)((n_k + 127) / 128), 128, 0, h->stream>>>(
+            n_k, n_blocks, d_part.as<double2>(), d_kf.as<double>(), d_kvec.as<int>(), h->d_kv.as<KVecDev>(), d_S.as<double>());
+        count_launch();
+        CEG_CK(cudaGetLastError());
+        if (S_f_reim) CEG_CK(cudaMemcpyAsync(S_f_reim, d_S.p, sizeof(double) * 2 * n_k, cudaMemcpyDeviceToHost, h->stream));
+        CEG_CK(cudaStreamSynchronize(h->stream));
+    }
+    *out = h.release();
+    return 0;
+}
+
+extern "C" int ceg_ewald_free(ceg_ewald_h h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const double* d_xyz, const double* d_q,
+                             double enc, double stat, double* d_out, const uint8_t* d_skip, int accumulate,
+                             cudaStream_t s) {
+    RecipParams P;
+    memcpy(P.invmat, h->invmat, sizeof P.invmat);
+    P.kx = h->kmax[0]; P.ky = h->kmax[1]; P.kz = h->kmax[2];
+    P.n_k = h->n_k;
+    P.kv = h->d_kv.as<KVecDev>();
+    P.n_pos = n_pos; P.n_atoms = n_atoms;
+    P.xyz = d_xyz; P.q = d_q;
+    P.energy_net_charges = enc; P.static_contribution = stat;
+    P.out = d_out; P.skip = d_skip; P.accumulate = accumulate;
+    const size_t per_atom = (size_t)(P.kx + 1) + (2 * P.ky + 1) + (2 * P.kz + 1);
+    const size_t smem = sizeof(double2) * per_atom * n_atoms * RECIP_WARPS;
+    if (smem > 200 * 1024) return fail("ceg_ewald_reciprocal: molecule too large for the shared-memory phase tables");
+    if (smem > 48 * 1024)
+        CEG_CK(cudaFuncSetAttribute(reciprocal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_pos + RECIP_WARPS - 1) / RECIP_WARPS, 148 * 16));
+    reciprocal_kernel<<<blocks, RECIP_WARPS * 32, smem, s>>>(P);
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ceg_ewald_reciprocal_dev(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, const double* d_xyz,
+                                        const double* q_host, double energy_net_charges, double static_contribution,
+                                        double* d_out, void* stream) {
+    if (!h || n_pos < 0 || n_atoms <= 0 || !q_host || (n_pos > 0 && (!d_xyz || !d_out)))
+        return fail("ceg_ewald_reciprocal_dev: bad argument");
+    if (n_pos == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    CEG_CK(h->d_q.reserve(sizeof(double) * n_atoms));
+    CEG_CK(cudaMemcpyAsync(h->d_q.p, q_host, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, s));
+    return launch_reciprocal(h, n_pos, n_atoms, d_xyz, h->d_q.as<double>(), energy_net_charges, static_contribution,
+                             d_out, nullptr, 0, s);
+}
+
+extern "C" int ceg_ewald_reciprocal(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, const double* xyz, const double* q,
+                                    double energy_net_charges, double static_contribution, double* out) {
+    if (!h || n_pos < 0 || n_atoms <= 0 || !q || (n_pos > 0 && (!xyz || !out)))
+        return fail("ceg_ewald_reciprocal: bad argument");
+    if (n_pos == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * n_atoms * n_pos));
+    CEG_CK(h->d_out.reserve(sizeof(double) * n_pos));
+    CEG_CK(h->d_q.reserve(sizeof(double) * n_atoms));
+    CEG_CK(cudaMemcpyAsync(h->d_xyz.p, xyz, sizeof(double) * 3 * n_atoms * n_pos, cudaMemcpyHostToDevice, h->stream));
+    CEG_CK(cudaMemcpyAsync(h->d_q.p, q, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, h->stream));
+    if (launch_reciprocal(h, n_pos, n_atoms, h->d_xyz.as<double>(), h->d_q.as<double>(), energy_net_charges,
+                          static_contribution, h->d_out.as<double>(), nullptr, 0, h->stream))
+        return 1;
+    CEG_CK(cudaMemcpyAsync(out, h->d_out.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, h->stream));
+    CEG_CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ================================================================================================
+// block mask + fused energy_point
+// ================================================================================================
+extern "C" int ceg_block_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs,
+                                const uint8_t* mask, ceg_block_h* out) {
+    if (!unitcell || !gs || !mask || !out) return fail("ceg_block_upload: null argument");
+    if (use_device(device)) return 1;
+    std::unique_ptr<ceg_block_s> h(new ceg_block_s);
+    h->device = device;
+    h->b.uc = to_dev(*unitcell);
+    h->b.gs = to_dev(*gs);
+    const int64_t npts = (int64_t)(gs->dims[0] + 1) * (gs->dims[1] + 1) * (gs->dims[2] + 1);
+    CEG_CK(h->d_mask.reserve(npts));
+    CEG_CK(cudaMemcpy(h->d_mask.p, mask, npts, cudaMemcpyHostToDevice));
+    h->b.mask = h->d_mask.as<uint8_t>();
+    *out = h.release();
+    return 0;
+}
+
+extern "C" int ceg_block_free(ceg_block_h h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    delete h;
+    return 0;
+}
+
+extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, ceg_ewald_h ewald,
+                                 ceg_block_h block, int64_t n_pos, int32_t n_atoms, const int32_t* atomsidx,
+                                 const double* charges, const double* xyz, double energy_net_charges,
+                                 double static_contribution, double* out_vdw, double* out_coulomb) {
+    if (n_pos < 0 || n_atoms <= 0 || !atomsidx || !charges || (n_pos > 0 && (!xyz || !out_vdw || !out_coulomb)))
+        return fail("ceg_energy_points: bad argument");
+    if (n_vdw < 0 || n_vdw > EP_MAX_VDW) return fail("ceg_energy_points: too many distinct VdW grids");
+    if (n_pos == 0) return 0;
+    int device = -1;
+    for (int g = 0; g < n_vdw; g++)
+        if (vdw && vdw[g]) device = vdw[g]->device;
+    if (coulomb) device = coulomb->device;
+    if (ewald) device = ewald->device;
+    if (block) device = block->device;
+    if (device < 0) {   // nothing resident: all grids are zero grids
+        for (int64_t i = 0; i < n_pos; i++) { out_vdw[i] = 0.0; out_coulomb[i] = 0.0; }
+        return 0;
+    }
+    for (int a = 0; a < n_atoms; a++)
+        if (atomsidx[a] < 0 || atomsidx[a] >= std::max(1, n_vdw)) return fail("ceg_energy_points: atomsidx out of range");
+    if (use_device(device)) return 1;
+    EnergyPointsParams P;
+    memset(&P, 0, sizeof P);
+    P.n_vdw = n_vdw;
+    for (int g = 0; g < n_vdw; g++) {
+        P.vdw_present[g] = (vdw && vdw[g]) ? 1 : 0;
+        if (P.vdw_present[g]) {
+            if (vdw[g]->device != device) return fail("ceg_energy_points: handles live on different devices");
+            P.vdw[g] = vdw[g]->g;
+        }
+    }
+    P.has_coulomb = coulomb ? 1 : 0;
+    if (coulomb) P.coulomb = coulomb->g;
+    P.has_block = block ? 1 : 0;
+    if (block) P.block = block->b;
+    P.n_atoms = n_atoms;
+    P.n_pos = n_pos;
+    cudaStream_t s;
+    CEG_CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    DevBuf d_idx, d_q, d_xyz, d_v, d_c, d_blk;
+    int rc = 0;
+    do {
+#define CK2(call) { cudaError_t _e = (call); if (_e != cudaSuccess) { rc = fail_cuda(_e, #call, __FILE__, __LINE__); break; } }
+        CK2(d_idx.reserve(sizeof(int) * n_atoms));
+        CK2(d_q.reserve(sizeof(double) * n_atoms));
+        CK2(d_xyz.reserve(sizeof(double) * 3 * n_atoms * n_pos));
+        CK2(d_v.reserve(sizeof(double) * n_pos));
+        CK2(d_c.reserve(sizeof(double) * n_pos));
+        CK2(d_blk.reserve(n_pos));
+        CK2(cudaMemcpyAsync(d_idx.p, atomsidx, sizeof(int) * n_atoms, cudaMemcpyHostToDevice, s));
+        CK2(cudaMemcpyAsync(d_q.p, charges, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, s));
+        CK2(cudaMemcpyAsync(d_xyz.p, xyz, sizeof(double) * 3 * n_atoms * n_pos, cudaMemcpyHostToDevice, s));
+        P.atomsidx = d_idx.as<int>();
+        P.charges = d_q.as<double>();
+        P.xyz = d_xyz.as<double>();
+        P.out_vdw = d_v.as<double>();
+        P.out_coulomb = d_c.as<double>();
+        P.blocked = d_blk.as<uint8_t>();
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_pos + 127) / 128, 148 * 32));
+        energy_points_kernel<<<blocks, 128, 0, s>>>(P);
+        count_launch();
+        CK2(cudaGetLastError());
+        if (coulomb && ewald && ewald->n_k > 0) {
+            std::lock_guard<std::mutex> lk(ewald->mu);
+            if (launch_reciprocal(ewald, n_pos, n_atoms, P.xyz, P.charges, energy_net_charges, static_contribution,
+                                  P.out_coulomb, P.blocked, 1, s)) { rc = 1; break; }
+        }
+        CK2(cudaMemcpyAsync(out_vdw, d_v.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, s));
+        CK2(cudaMemcpyAsync(out_coulomb, d_c.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, s));
+        CK2(cudaStreamSynchronize(s));
+#undef CK2
+    } while (0);
+    cudaStreamDestroy(s);
+    return rc;
+}

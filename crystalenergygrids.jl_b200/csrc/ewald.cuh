@@ -1,0 +1,171 @@
+// Ewald reciprocal-space kernels (FP64, sm_100a).
+//
+// Replaces setup_Eik + ewald_main_loop! (ewald.jl:109-185), move_one_system! (ewald.jl:350-364)
+// and compute_ewald(ctx) (ewald.jl:555-577).
+//
+//  * structure_factor_kernel: S_f(k) = sum_sites q exp(2 pi i (ix fx + jy fy + jz fz)).  One thread
+//    per k-vector and per block of sites; sites are staged through shared memory, the phase factor
+//    comes from sincospi of the exactly-reduced phase; block partials are written out and reduced
+//    in a fixed order by structure_factor_reduce_kernel (deterministic, no atomics).
+//  * reciprocal_kernel: one warp per placement of the probe molecule.  The per-atom power tables
+//    Eikx[0..kx], Eiky[-ky..ky], Eikz[-kz..kz] (the reference builds them by recurrence from one
+//    cispi per axis) are evaluated directly with sincospi by the lanes into shared memory, the lanes
+//    then stride over the k-list accumulating kf*Re(S_f conj S_a) and kf*|S_a|^2, and a warp-shuffle
+//    reduction yields the energy of the placement.
+#pragma once
+#include "common.cuh"
+
+namespace ceg {
+
+struct KVecDev {       // one k-vector
+    double kf;         // kfactor (ewald.jl:247-259)
+    double sf_re, sf_im;
+    int ix, jy, jz, _pad;
+};
+
+// (m * f) mod 1 with the rounding error of the product carried along (m integer, f in [0,1))
+__device__ __forceinline__ double red_prod(double m, double f) {
+    const double hi = m * f;
+    const double lo = fma(m, f, -hi);
+    double r = (hi - floor(hi)) + lo;
+    return r - floor(r);
+}
+
+constexpr int SF_SITES_PER_BLOCK = 256;
+constexpr int SF_THREADS = 128;
+
+// partial[blockIdx.y][k] over a block of sites
+__global__ void __launch_bounds__(SF_THREADS) structure_factor_kernel(int64_t n_k, const int* __restrict__ kvec,
+                                                                      int64_t n_sites, const double* __restrict__ frac,
+                                                                      const double* __restrict__ charge,
+                                                                      double2* __restrict__ partial) {
+    __shared__ double s_f[SF_SITES_PER_BLOCK][3];
+    __shared__ double s_q[SF_SITES_PER_BLOCK];
+    const int64_t s0 = (int64_t)blockIdx.y * SF_SITES_PER_BLOCK;
+    const int ns = (int)min((int64_t)SF_SITES_PER_BLOCK, n_sites - s0);
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double f = frac[3 * (s0 + s) + d];
+            s_f[s][d] = f - floor(f);          // exp(2 pi i m f) is periodic in f for integer m
+        }
+        s_q[s] = charge[s0 + s];
+    }
+    __syncthreads();
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_k) return;
+    const double ix = kvec[3 * k], jy = kvec[3 * k + 1], jz = kvec[3 * k + 2];
+    double re = 0.0, im = 0.0;
+    for (int s = 0; s < ns; s++) {
+        // each product is exact-ish (|m| <= ~60, f in [0,1)); reduce the phase before sincospi
+        double ph = red_prod(ix, s_f[s][0]) + red_prod(jy, s_f[s][1]) + red_prod(jz, s_f[s][2]);
+        ph -= floor(ph);
+        double sn, cs;
+        sincospi(2.0 * ph, &sn, &cs);
+        re += s_q[s] * cs;
+        im += s_q[s] * sn;
+    }
+    partial[(int64_t)blockIdx.y * n_k + k] = make_double2(re, im);
+}
+
+__global__ void __launch_bounds__(128) structure_factor_reduce_kernel(int64_t n_k, int n_blocks,
+                                                                      const double2* __restrict__ partial,
+                                                                      const double* __restrict__ kfactor,
+                                                                      const int* __restrict__ kvec,
+                                                                      KVecDev* __restrict__ kv, double* __restrict__ S_out) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n_k) return;
+    double re = 0.0, im = 0.0;
+    for (int b = 0; b < n_blocks; b++) {
+        const double2 p = partial[(int64_t)b * n_k + k];
+        re += p.x;
+        im += p.y;
+    }
+    KVecDev o;
+    o.kf = kfactor[k];
+    o.sf_re = re;
+    o.sf_im = im;
+    o.ix = kvec[3 * k]; o.jy = kvec[3 * k + 1]; o.jz = kvec[3 * k + 2]; o._pad = 0;
+    kv[k] = o;
+    S_out[2 * k] = re;
+    S_out[2 * k + 1] = im;
+}
+
+struct RecipParams {
+    double invmat[9];      // supercell inverse, column-major
+    int kx, ky, kz;
+    int64_t n_k;
+    const KVecDev* kv;
+    int64_t n_pos;
+    int n_atoms;
+    const double* xyz;     // n_pos x n_atoms x 3
+    const double* q;       // n_atoms (device)
+    double energy_net_charges, static_contribution;
+    double* out;
+    const uint8_t* skip;   // optional: placements flagged here are left untouched
+    int accumulate;        // 1: out[i] += E (fused energy_point), 0: out[i] = E
+};
+
+constexpr int RECIP_WARPS = 4;
+
+// dynamic shared memory: per warp n_atoms * (kx+1 + 2ky+1 + 2kz+1) double2 + n_atoms doubles
+__global__ void __launch_bounds__(RECIP_WARPS * 32) reciprocal_kernel(const RecipParams P) {
+    extern __shared__ double2 s_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nx = P.kx + 1, ny = 2 * P.ky + 1, nz = 2 * P.kz + 1;
+    const int per_atom = nx + ny + nz;
+    double2* tab = s_dyn + (size_t)warp * per_atom * P.n_atoms;
+    const int64_t wid = (int64_t)blockIdx.x * RECIP_WARPS + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * RECIP_WARPS;
+    for (int64_t i = wid; i < P.n_pos; i += nwarps) {
+        if (P.skip && P.skip[i]) continue;
+        const double* mol = P.xyz + (int64_t)3 * P.n_atoms * i;
+        __syncwarp();
+        // power tables, one entry per lane-iteration: entry t of atom a
+        for (int t = lane; t < per_atom * P.n_atoms; t += 32) {
+            const int a = t / per_atom, u = t - a * per_atom;
+            const double x = mol[3 * a], y = mol[3 * a + 1], z = mol[3 * a + 2];
+            int axis, m;
+            if (u < nx) { axis = 0; m = u; }
+            else if (u < nx + ny) { axis = 1; m = u - nx - P.ky; }
+            else { axis = 2; m = u - nx - ny - P.kz; }
+            // fractional coordinate along this axis: row `axis` of invmat * pos (ewald.jl:358)
+            double f = P.invmat[axis] * x + P.invmat[3 + axis] * y + P.invmat[6 + axis] * z;
+            f -= floor(f);
+            double ph = red_prod((double)m, f);
+            double sn, cs;
+            sincospi(2.0 * ph, &sn, &cs);
+            tab[t] = make_double2(cs, sn);
+        }
+        __syncwarp();
+        double fa = 0.0, aa = 0.0;
+        for (int64_t k = lane; k < P.n_k; k += 32) {
+            const KVecDev kv = P.kv[k];
+            double sre = 0.0, sim = 0.0;
+            for (int a = 0; a < P.n_atoms; a++) {
+                const double2* ta = tab + a * per_atom;
+                const double2 ex = ta[kv.ix], ey = ta[nx + P.ky + kv.jy], ez = ta[nx + ny + P.kz + kv.jz];
+                const double yzr = ey.x * ez.x - ey.y * ez.y, yzi = ey.x * ez.y + ey.y * ez.x;
+                const double qa = P.q[a];
+                sre += qa * (ex.x * yzr - ex.y * yzi);
+                sim += qa * (ex.x * yzi + ex.y * yzr);
+            }
+            fa += kv.kf * (kv.sf_re * sre + kv.sf_im * sim);
+            aa += kv.kf * (sre * sre + sim * sim);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fa += __shfl_xor_sync(0xffffffffu, fa, o);
+            aa += __shfl_xor_sync(0xffffffffu, aa, o);
+        }
+        if (lane == 0) {
+            // ewald.jl:572-576
+            const double host = 2.0 * (fa + P.energy_net_charges);
+            const double ads = aa + P.static_contribution;
+            const double E = host + ads;
+            if (P.accumulate) P.out[i] += E; else P.out[i] = E;
+        }
+    }
+}
+
+}  // namespace ceg

@@ -1,0 +1,376 @@
+// Energy-grid construction kernels (FP64, sm_100a).
+//
+// Replaces the per-point loops of the reference:
+//   compute_derivatives_vdw / compute_derivatives_ewald      probes.jl:71-117
+//   derivativesGrid (LJ / Buckingham / HardSphere, sums)     interactions.jl:432-472, 599-610
+//   derivatives_ewald                                        ewald.jl:299-312
+//   _set_gridpoint! and the create_grid_* loops              grids.jl:118-185
+//
+// Two kernels:
+//  * derivatives_literal_kernel — arbitrary positions, the reference's per-pair algorithm verbatim
+//    (min-image search of utils.jl:210-246 for every supercell atom).  Backs
+//    ceg_compute_derivatives and is the in-kernel "exact" path of the tiled kernel.
+//  * grid_build_tiled_kernel — the production kernel.  One CTA owns a TXxTYxTZ tile of grid
+//    nodes; it scans the pre-expanded list of periodic atom IMAGES (atom-major order, built on the
+//    host for the slab's bounding region), keeps those within cutoff + tile radius of the tile
+//    centre with an ORDERED compaction into shared memory, and every thread (one node each) walks
+//    that list, broadcast from shared memory.  All VdW probes and the Coulomb grid share the one
+//    distance computation.  Because the probe supercell has perpendicular widths >= 2*cutoff
+//    (probes.jl:24), the in-cutoff image of an atom is unique and equals the reference's wrapped
+//    image, so the in-cutoff set is identical; pairs whose d^2 lands within a guard band of a mask
+//    threshold (cutoff^2, 1 Å^2, hard-sphere radius^2) or that would enter the reference's
+//    non-orthogonal image search are re-evaluated with the literal algorithm, which makes every
+//    mask decision bit-identical to the oracle's.
+#pragma once
+#include "common.cuh"
+
+namespace ceg {
+
+struct PairDev {
+    int flags;
+    int _pad;
+    double hs_r2;
+    double lj_eps, lj_sig2, lj_shift;
+    double bA, bB, bC, b_shift;
+};
+
+constexpr int MAX_GRIDS = 5;       // up to 4 fused VdW probes + Coulomb per pass
+constexpr int LIST_CAP = 1024;     // shared-memory image list capacity per round
+constexpr int TABLE_SMEM_TYPES = 24;
+constexpr double GUARD_BAND = 1e-9;  // Å^2; fast-vs-literal d^2 differ by ~1e-13
+
+// ---- pair kernels ------------------------------------------------------------------------------
+// D = (1/r) d/dr.  Reciprocal powers are formed from one rsqrt instead of the reference's chain of
+// divisions; differences are a few ulp, far inside the 1e-9 parity tolerance.
+struct PairGeom {
+    double r2, ir, ir2, r;
+};
+__device__ __forceinline__ PairGeom make_geom(double r2) {
+    PairGeom g;
+    g.r2 = r2;
+    g.ir = rsqrt(r2);
+    g.ir2 = g.ir * g.ir;
+    g.r = r2 * g.ir;
+    return g;
+}
+
+__device__ __forceinline__ void vdw_pair(const PairDev& p, const PairGeom& g, double& v, double& p1, double& p2,
+                                         double& p3) {
+    v = 0.0; p1 = 0.0; p2 = 0.0; p3 = 0.0;
+    const int fl = p.flags;
+    if (fl & CEG_PAIR_HS) v += (g.r2 < p.hs_r2) ? CUDART_INF : 0.0;
+    if (fl & CEG_PAIR_LJ) {                       // interactions.jl:434-441
+        const double eps = p.lj_eps;
+        const double t = p.lj_sig2 * g.ir2;
+        const double x6 = t * t * t;
+        const double ir4 = g.ir2 * g.ir2;
+        v += 4.0 * eps * x6 * (x6 - 1.0) - p.lj_shift;
+        p1 += 24.0 * eps * (x6 * (1.0 - 2.0 * x6)) * g.ir2;
+        p2 += 96.0 * eps * (x6 * (7.0 * x6 - 2.0)) * ir4;
+        p3 += 384.0 * eps * (x6 * (5.0 - 28.0 * x6)) * (ir4 * ir4);
+    }
+    if (fl & CEG_PAIR_BUCK) {                     // interactions.jl:447-457
+        const double A = p.bA, B = p.bB, C = p.bC;
+        const double ir4 = g.ir2 * g.ir2;
+        const double ir6 = ir4 * g.ir2;
+        const double x6 = C * ir6;
+        const double xe = A * exp(-B * g.r);
+        const double Br = B * g.r;
+        v += (xe - x6) - p.b_shift;
+        p1 += -B * xe * g.ir + 6.0 * x6 * g.ir2;
+        p2 += -48.0 * x6 * ir4 + B * xe * (1.0 + Br) * (g.ir2 * g.ir);
+        p3 += -(3.0 * Br + Br * Br + 3.0) * B * xe * (g.r * ir6) + 480.0 * C * (ir6 * ir6);
+    }
+}
+
+// ewald.jl:299-312 with erfc(x) = exp(-x^2) * erfcx(x): one exp serves both terms.
+__device__ __forceinline__ void ewald_pair(double alpha, double two_alpha_over_sqrtpi, double q, const PairGeom& g,
+                                           double& v, double& p1, double& p2, double& p3) {
+    const double ar = alpha * g.r;
+    const double a2 = ar * ar;                    // r2 * alpha^2
+    const double E = exp(-a2);
+    const double e2 = two_alpha_over_sqrtpi * g.r * E;
+    const double c = E * erfcx(ar);
+    const double ir3 = g.ir2 * g.ir, ir5 = ir3 * g.ir2, ir7 = ir5 * g.ir2;
+    v = q * c * g.ir;
+    p1 = -q * (e2 + c) * ir3;
+    p2 = q * (e2 * (3.0 + 2.0 * a2) + 3.0 * c) * ir5;
+    p3 = q * (-e2 * (15.0 + 10.0 * a2 + 4.0 * (a2 * a2)) - 15.0 * c) * ir7;
+}
+
+__device__ __forceinline__ void accumulate(double* acc, double v, double p1, double p2, double p3, double dx,
+                                           double dy, double dz, double dxy, double dxz, double dyz) {
+    acc[0] += v;
+    acc[1] += p1 * dx;
+    acc[2] += p1 * dy;
+    acc[3] += p1 * dz;
+    acc[4] += p2 * dxy;
+    acc[5] += p2 * dxz;
+    acc[6] += p2 * dyz;
+    acc[7] += p3 * (dxz * dy);
+}
+
+__device__ __forceinline__ double clamp_ref(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
+
+// grids.jl:118-135 _set_gridpoint!
+__device__ __forceinline__ void set_gridpoint(const double* acc, const double* delta, double lam, double thr,
+                                              float* o) {
+    double v = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3], b1 = acc[4], b2 = acc[5], b3 = acc[6], c = acc[7];
+    if (v > thr) {
+        v = xmul(2.0, thr);
+        a1 = clamp_ref(a1, -thr, thr); a2 = clamp_ref(a2, -thr, thr); a3 = clamp_ref(a3, -thr, thr);
+        b1 = b2 = b3 = 0.0;
+        c = 0.0;
+    }
+    o[0] = (float)xmul(v, lam);
+    o[1] = (float)xmul(xmul(a1, delta[0]), lam);
+    o[2] = (float)xmul(xmul(a2, delta[1]), lam);
+    o[3] = (float)xmul(xmul(a3, delta[2]), lam);
+    o[4] = (float)xmul(xmul(b1, xmul(delta[0], delta[1])), lam);
+    o[5] = (float)xmul(xmul(b2, xmul(delta[0], delta[2])), lam);
+    o[6] = (float)xmul(xmul(b3, xmul(delta[1], delta[2])), lam);
+    o[7] = (float)xmul(xmul(c, xmul(xmul(delta[0], delta[1]), delta[2])), lam);
+}
+
+// ---- literal kernel (arbitrary positions) ---------------------------------------------------------
+struct LiteralParams {
+    CellDev cell;
+    double cutoff2, alpha;
+    int64_t n_atoms, n_pos;
+    const double* xyz;      // n_atoms x 3
+    const int* type;
+    const double* q;
+    const PairDev* table;   // n_probes x n_types
+    int n_types, n_probes, want_coulomb;
+    const double* pos;      // n_pos x 3
+    double* out;            // [(g*n_pos + i)*8 + c]
+};
+
+__global__ void __launch_bounds__(128) derivatives_literal_kernel(const LiteralParams P) {
+    __shared__ CellDev s_cell;
+    if (threadIdx.x == 0) s_cell = P.cell;
+    __syncthreads();
+    const int n_grids = P.n_probes + P.want_coulomb;
+    const double taosp = 2.0 * P.alpha / sqrt(CUDART_PI);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.n_pos; i += (int64_t)gridDim.x * blockDim.x) {
+        const double px = P.pos[3 * i], py = P.pos[3 * i + 1], pz = P.pos[3 * i + 2];
+        for (int g = 0; g < n_grids; g++) {
+            const bool coul = (g == P.n_probes);
+            double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            double smallest = CUDART_INF;
+            for (int64_t a = 0; a < P.n_atoms; a++) {
+                double b[3] = {xsub(px, P.xyz[3 * a]), xsub(py, P.xyz[3 * a + 1]), xsub(pz, P.xyz[3 * a + 2])};
+                const double d2 = periodic_distance2_ref(b, s_cell);
+                if (d2 >= P.cutoff2) continue;
+                double v, p1, p2, p3;
+                const PairGeom geo = make_geom(d2);
+                if (coul) {
+                    smallest = fmin(smallest, d2);
+                    ewald_pair(P.alpha, taosp, P.q[a], geo, v, p1, p2, p3);
+                } else {
+                    const PairDev pr = P.table[g * P.n_types + P.type[a]];
+                    if (pr.flags == 0) continue;
+                    vdw_pair(pr, geo, v, p1, p2, p3);
+                }
+                accumulate(acc, v, p1, p2, p3, b[0], b[1], b[2], b[0] * b[1], b[0] * b[2], b[1] * b[2]);
+            }
+            if (coul && smallest < 1.0) acc[0] = CUDART_INF;
+            double* o = P.out + ((int64_t)g * P.n_pos + i) * 8;
+#pragma unroll
+            for (int c = 0; c < 8; c++) o[c] = acc[c];
+        }
+    }
+}
+
+// ---- tiled production kernel ----------------------------------------------------------------------
+struct ExtAtom {          // one periodic image of one supercell atom
+    double x, y, z, q;
+};
+struct ExtMeta {
+    int type;
+    int orig;             // index of the supercell atom (for the literal re-evaluation)
+};
+
+struct BuildParams {
+    CellDev cell;
+    GridSpecDev gs;
+    double cutoff2, alpha;
+    double cut_hi, cut_lo;     // cutoff2 +- GUARD_BAND
+    double small_hi;           // max(1 Å^2, max hard-sphere r^2) + band: below it, take the literal path
+    double stale_lo;           // non-ortho cells: safemin2 - band (pairs above enter the image search); +inf if unused
+    double reach2;             // (cutoff + tile radius + slack)^2
+    double lam_v, thr_v, lam_c, thr_c;
+    int i0, i1;                // slab of x planes held by the output buffers
+    int a0, a1;                // planes computed by this launch (i0 <= a0 < a1 <= i1)
+    int tiles_x, tiles_y, tiles_z;
+    const ExtAtom* ext;
+    const ExtMeta* ext_meta;
+    int n_ext;
+    const double* atoms_xyz;   // original supercell atoms
+    const PairDev* table;
+    int n_types;
+    float* out[MAX_GRIDS];     // each [8][i1-i0][ny][nz]
+    double* raw;               // optional [g][8][i1-i0][ny][nz]
+    unsigned long long* stats; // [0] pairs tested, [1] pairs in cutoff
+};
+
+template <int TX, int TY, int TZ, int NP, bool COUL>
+__global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const BuildParams P) {
+    constexpr int NT = TX * TY * TZ;
+    constexpr int NW = NT / 32;
+    constexpr int NG = NP + (COUL ? 1 : 0);
+    __shared__ ExtAtom s_atom[LIST_CAP];
+    __shared__ ExtMeta s_meta[LIST_CAP];
+    __shared__ PairDev s_table[NP > 0 ? NP * TABLE_SMEM_TYPES : 1];   // small tables staged; larger read from global
+    __shared__ CellDev s_cell;
+    __shared__ int s_wcount[NW];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool table_in_smem = (P.n_types <= TABLE_SMEM_TYPES);
+    if (tid == 0) s_cell = P.cell;
+    if (NP > 0 && table_in_smem)
+        for (int i = tid; i < NP * P.n_types; i += NT) s_table[i] = P.table[i];
+
+    // tile -> node indices
+    int t = blockIdx.x;
+    const int tz = t % P.tiles_z; t /= P.tiles_z;
+    const int ty = t % P.tiles_y; t /= P.tiles_y;
+    const int tx = t;
+    const int lz = tid % TZ, ly = (tid / TZ) % TY, lx = tid / (TZ * TY);
+    const int i = P.a0 + tx * TX + lx, j = ty * TY + ly, k = tz * TZ + lz;
+    const bool valid = (i < P.a1) && (j < P.gs.n[1]) && (k < P.gs.n[2]);
+    // abc_to_xyz (coordinates.jl:72-76): multiply, divide, add — bit-identical to the oracle
+    const double px = xadd(xdiv(xmul((double)i, P.gs.size[0]), (double)P.gs.dims[0]), P.gs.shift[0]);
+    const double py = xadd(xdiv(xmul((double)j, P.gs.size[1]), (double)P.gs.dims[1]), P.gs.shift[1]);
+    const double pz = xadd(xdiv(xmul((double)k, P.gs.size[2]), (double)P.gs.dims[2]), P.gs.shift[2]);
+    // tile centre (nominal full tile)
+    const double cx = ((double)(P.a0 + tx * TX) + 0.5 * (TX - 1)) * P.gs.delta[0] + P.gs.shift[0];
+    const double cy = ((double)(ty * TY) + 0.5 * (TY - 1)) * P.gs.delta[1] + P.gs.shift[1];
+    const double cz = ((double)(tz * TZ) + 0.5 * (TZ - 1)) * P.gs.delta[2] + P.gs.shift[2];
+
+    double acc[NG > 0 ? NG : 1][8];
+#pragma unroll
+    for (int g = 0; g < NG; g++)
+#pragma unroll
+        for (int c = 0; c < 8; c++) acc[g][c] = 0.0;
+    double smallest = CUDART_INF;
+    const double taosp = 2.0 * P.alpha / sqrt(CUDART_PI);
+    unsigned long long n_tested = 0, n_in = 0;
+    int count = 0;
+    __syncthreads();
+
+    auto process = [&](int cnt) {
+        if (!valid) return;
+        n_tested += cnt;
+        for (int e = 0; e < cnt; e++) {
+            const ExtAtom a = s_atom[e];
+            double dx = px - a.x, dy = py - a.y, dz = pz - a.z;
+            double d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < P.cut_hi) {
+                if (d2 > P.cut_lo || d2 < P.small_hi || d2 > P.stale_lo) {
+                    // literal re-evaluation from the original atom (mask thresholds, image search)
+                    const int o = s_meta[e].orig;
+                    double b[3] = {xsub(px, P.atoms_xyz[3 * o]), xsub(py, P.atoms_xyz[3 * o + 1]),
+                                   xsub(pz, P.atoms_xyz[3 * o + 2])};
+                    const double d2x = periodic_distance2_ref(b, s_cell);
+                    // this list entry must be the image the reference measured d2 on
+                    if (fabs(d2x - d2) > 1e-6) continue;
+                    if (d2x >= P.cutoff2) continue;
+                    d2 = d2x; dx = b[0]; dy = b[1]; dz = b[2];
+                }
+                n_in++;
+                const PairGeom geo = make_geom(d2);
+                const double dxy = dx * dy, dxz = dx * dz, dyz = dy * dz;
+                const int ty_ = s_meta[e].type;
+#pragma unroll
+                for (int g = 0; g < NP; g++) {
+                    const PairDev& pr = table_in_smem ? s_table[g * P.n_types + ty_] : P.table[g * P.n_types + ty_];
+                    if (pr.flags != 0) {
+                        double v, p1, p2, p3;
+                        vdw_pair(pr, geo, v, p1, p2, p3);
+                        accumulate(acc[g], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                    }
+                }
+                if (COUL) {
+                    smallest = fmin(smallest, d2);
+                    double v, p1, p2, p3;
+                    ewald_pair(P.alpha, taosp, a.q, geo, v, p1, p2, p3);
+                    accumulate(acc[NG - 1], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                }
+            }
+        }
+    };
+
+    for (int base = 0; base < P.n_ext; base += NT) {
+        const int e = base + tid;
+        bool keep = false;
+        ExtAtom a;
+        ExtMeta m;
+        if (e < P.n_ext) {
+            a = P.ext[e];
+            const double ddx = cx - a.x, ddy = cy - a.y, ddz = cz - a.z;
+            keep = (ddx * ddx + ddy * ddy + ddz * ddz) < P.reach2;
+            if (keep) m = P.ext_meta[e];
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        int off = count, total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            const int cw = s_wcount[w];
+            if (w < warp) off += cw;
+            total += cw;
+        }
+        if (keep) {
+            const int slot = off + __popc(bal & ((1u << lane) - 1u));
+            s_atom[slot] = a;
+            s_meta[slot] = m;
+        }
+        count += total;
+        __syncthreads();
+        if (count + NT > LIST_CAP) {   // flush: the next chunk might not fit
+            process(count);
+            count = 0;
+            __syncthreads();
+        }
+    }
+    process(count);
+
+    // stats: one atomic per warp
+    if (P.stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_tested += __shfl_down_sync(0xffffffffu, n_tested, o);
+            n_in += __shfl_down_sync(0xffffffffu, n_in, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&P.stats[0], n_tested);
+            atomicAdd(&P.stats[1], n_in);
+        }
+    }
+    if (!valid) return;
+    if (COUL && smallest < 1.0) acc[NG - 1][0] = CUDART_INF;   // probes.jl:116
+
+    const int64_t ny = P.gs.n[1], nz = P.gs.n[2];
+    const int64_t plane = ny * nz;
+    const int64_t slab = (int64_t)(P.i1 - P.i0) * plane;
+    const int64_t node = (int64_t)(i - P.i0) * plane + (int64_t)j * nz + k;
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+        const bool coul = COUL && (g == NG - 1);
+        if (P.raw) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) P.raw[((int64_t)g * 8 + c) * slab + node] = acc[g][c];
+        }
+        if (P.out[g]) {
+            float o[8];
+            set_gridpoint(acc[g], P.gs.delta, coul ? P.lam_c : P.lam_v, coul ? P.thr_c : P.thr_v, o);
+#pragma unroll
+            for (int c = 0; c < 8; c++) P.out[g][(int64_t)c * slab + node] = o[c];
+        }
+    }
+}
+
+}  // namespace ceg

@@ -1,0 +1,209 @@
+// Batched tricubic interpolation (sm_100a).
+//
+// Replaces interpolate_grid (grids.jl:212-273) + offsetpoint (coordinates.jl:58-66), and the
+// BlockFile lookup (coordinates.jl:97-101).
+//
+// Device layout: the host/.grid order is [channel][x][y][z] (a random query touches 32 different
+// 32-byte sectors for 256 useful bytes).  On upload the grid is transposed ONCE to node-major
+// records [x][y][z][8 x f32]: one node = one 32-byte sector, so a query reads exactly its 8 corner
+// sectors (the 2 z-neighbours are adjacent: four 64-byte runs).
+//
+// Arithmetic: the reference forms a = COEFF * X (64x64 Lekien–Marsden matrix) and sums
+// a[i,j,k] rx^i ry^j rz^k.  That polynomial is the tensor-product cubic Hermite interpolant of the
+// 8 corner records, evaluated here directly: 12 basis values + 8 x 14 flops, FP64 throughout.
+// The cell index (floor of the grid coordinate) is computed with the reference's operation order
+// and no FMA contraction, so the stencil and the blocked mask are bit-identical to the oracle's.
+#pragma once
+#include "common.cuh"
+
+namespace ceg {
+
+struct GridDev {
+    CellDev uc;
+    GridSpecDev gs;
+    const float4* nodes;   // [x][y][z][2 x float4]
+    int is_vdw;
+};
+
+struct BlockDev {
+    CellDev uc;
+    GridSpecDev gs;
+    const uint8_t* mask;   // [x][y][z]
+};
+
+// [8][npts] -> [npts][8]
+__global__ void __launch_bounds__(256) relayout_nodes_kernel(const float* __restrict__ src, float4* __restrict__ dst,
+                                                             int64_t npts) {
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < npts; n += (int64_t)gridDim.x * blockDim.x) {
+        float4 lo, hi;
+        lo.x = src[n]; lo.y = src[npts + n]; lo.z = src[2 * npts + n]; lo.w = src[3 * npts + n];
+        hi.x = src[4 * npts + n]; hi.y = src[5 * npts + n]; hi.z = src[6 * npts + n]; hi.w = src[7 * npts + n];
+        dst[2 * n] = lo;
+        dst[2 * n + 1] = hi;
+    }
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+struct Stencil {
+    int64_t base[2][2];   // node index of (x_ix, y_iy, z0)
+    int zstep;            // 0 or 1 node to z1
+    double r[3];
+};
+
+// grids.jl:215-219: p0 = floor(s), p1 = p0 + (p0 != n), r = s - p0
+__device__ __forceinline__ void make_stencil(const CellDev& uc, const GridSpecDev& gs, const double* p, Stencil& st) {
+    double s[3];
+    offsetpoint_x(uc, gs, p, s);
+    int p0[3], p1[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double fl = floor(s[i]);
+        st.r[i] = xsub(s[i], fl);
+        int q = (int)fl;
+        q = q < 1 ? 1 : (q > gs.n[i] ? gs.n[i] : q);   // memory safety only; in-range for finite input
+        p0[i] = q - 1;
+        p1[i] = p0[i] + (q != gs.n[i]);
+    }
+    const int64_t ny = gs.n[1], nz = gs.n[2];
+    st.base[0][0] = ((int64_t)p0[0] * ny + p0[1]) * nz + p0[2];
+    st.base[1][0] = ((int64_t)p1[0] * ny + p0[1]) * nz + p0[2];
+    st.base[0][1] = ((int64_t)p0[0] * ny + p1[1]) * nz + p0[2];
+    st.base[1][1] = ((int64_t)p1[0] * ny + p1[1]) * nz + p0[2];
+    st.zstep = p1[2] - p0[2];
+}
+
+// cubic Hermite basis on [0,1]: h[0]=value@0, h[1]=value@1, h[2]=slope@0, h[3]=slope@1
+__device__ __forceinline__ void hermite(double t, double* h) {
+    const double t2 = t * t, t3 = t2 * t;
+    h[0] = 2.0 * t3 - 3.0 * t2 + 1.0;
+    h[1] = -2.0 * t3 + 3.0 * t2;
+    h[2] = t3 - 2.0 * t2 + t;
+    h[3] = t3 - t2;
+}
+
+// Interpolate one grid at one prepared stencil.  Returns 1e100 if a VdW corner value exceeds 5e6 K
+// (grids.jl:245-248).
+__device__ __forceinline__ double interp_one(const GridDev& g, const Stencil& st) {
+    float4 lo[8], hi[8];
+#pragma unroll
+    for (int ix = 0; ix < 2; ix++)
+#pragma unroll
+        for (int iy = 0; iy < 2; iy++)
+#pragma unroll
+            for (int iz = 0; iz < 2; iz++) {
+                const float4* p = g.nodes + 2 * (st.base[ix][iy] + (iz ? st.zstep : 0));
+                const int n = (ix * 2 + iy) * 2 + iz;
+                lo[n] = ldg_stream(p);
+                hi[n] = ldg_stream(p + 1);
+            }
+    if (g.is_vdw) {
+        bool blocked = false;
+#pragma unroll
+        for (int n = 0; n < 8; n++) blocked |= (lo[n].x > 5e6f);
+        if (blocked) return 1e100;
+    }
+    double hx[4], hy[4], hz[4];
+    hermite(st.r[0], hx);
+    hermite(st.r[1], hy);
+    hermite(st.r[2], hz);
+    double ret = 0.0;
+#pragma unroll
+    for (int ix = 0; ix < 2; ix++)
+#pragma unroll
+        for (int iy = 0; iy < 2; iy++)
+#pragma unroll
+            for (int iz = 0; iz < 2; iz++) {
+                const int n = (ix * 2 + iy) * 2 + iz;
+                const double x0 = hx[ix], x1 = hx[2 + ix], y0 = hy[iy], y1 = hy[2 + iy], z0 = hz[iz], z1 = hz[2 + iz];
+                // channels: f, fx, fy, fz | fxy, fxz, fyz, fxyz
+                const double a = x0 * (double)lo[n].x + x1 * (double)lo[n].y;   // f , fx
+                const double b = x0 * (double)lo[n].z + x1 * (double)hi[n].x;   // fy, fxy
+                const double c = x0 * (double)lo[n].w + x1 * (double)hi[n].y;   // fz, fxz
+                const double d = x0 * (double)hi[n].z + x1 * (double)hi[n].w;   // fyz, fxyz
+                ret += z0 * (y0 * a + y1 * b) + z1 * (y0 * c + y1 * d);
+            }
+    return ret;
+}
+
+__global__ void __launch_bounds__(256) interpolate_kernel(const GridDev g, int64_t n, const double* __restrict__ xyz,
+                                                          double* __restrict__ out) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const double p[3] = {xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2]};
+        Stencil st;
+        make_stencil(g.uc, g.gs, p, st);
+        out[q] = interp_one(g, st);
+    }
+}
+
+// ---- fused energy_point (grids.jl:311-318): block test + VdW and Coulomb interpolation ------------
+constexpr int EP_MAX_VDW = 8;
+struct EnergyPointsParams {
+    int n_vdw;                       // number of distinct VdW grids
+    GridDev vdw[EP_MAX_VDW];
+    int vdw_present[EP_MAX_VDW];     // 0 = zero grid
+    GridDev coulomb;
+    int has_coulomb;
+    BlockDev block;
+    int has_block;
+    int n_atoms;
+    const int* atomsidx;             // device
+    const double* charges;           // device
+    const double* xyz;               // n_pos x n_atoms x 3
+    int64_t n_pos;
+    double* out_vdw;
+    double* out_coulomb;             // direct part only here; reciprocal added by ewald kernel
+    uint8_t* blocked;                // n_pos flags for the reciprocal kernel
+};
+
+__global__ void __launch_bounds__(128) energy_points_kernel(const EnergyPointsParams P) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.n_pos; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* mol = P.xyz + (int64_t)3 * P.n_atoms * i;
+        bool blocked = false;
+        if (P.has_block) {
+            for (int a = 0; a < P.n_atoms && !blocked; a++) {
+                double s[3];
+                const double p[3] = {mol[3 * a], mol[3 * a + 1], mol[3 * a + 2]};
+                offsetpoint_x(P.block.uc, P.block.gs, p, s);
+                // round(Int, x): half to even
+                int64_t ia = (int64_t)rint(s[0]) - 1, ib = (int64_t)rint(s[1]) - 1, ic = (int64_t)rint(s[2]) - 1;
+                ia = ia < 0 ? 0 : (ia >= P.block.gs.n[0] ? P.block.gs.n[0] - 1 : ia);
+                ib = ib < 0 ? 0 : (ib >= P.block.gs.n[1] ? P.block.gs.n[1] - 1 : ib);
+                ic = ic < 0 ? 0 : (ic >= P.block.gs.n[2] ? P.block.gs.n[2] - 1 : ic);
+                blocked = P.block.mask[(ia * P.block.gs.n[1] + ib) * P.block.gs.n[2] + ic] != 0;
+            }
+        }
+        if (blocked) {
+            P.out_vdw[i] = 1e100;
+            P.out_coulomb[i] = 0.0;
+            P.blocked[i] = 1;
+            continue;
+        }
+        double vdw = 0.0, coul = 0.0;
+        for (int a = 0; a < P.n_atoms; a++) {
+            const double p[3] = {mol[3 * a], mol[3 * a + 1], mol[3 * a + 2]};
+            const int gi = P.atomsidx[a];
+            if (P.vdw_present[gi]) {
+                Stencil st;
+                make_stencil(P.vdw[gi].uc, P.vdw[gi].gs, p, st);
+                vdw += interp_one(P.vdw[gi], st);
+            }
+            if (P.has_coulomb) {
+                Stencil st;
+                make_stencil(P.coulomb.uc, P.coulomb.gs, p, st);
+                coul += P.charges[a] * interp_one(P.coulomb, st);
+            }
+        }
+        P.out_vdw[i] = vdw;
+        P.out_coulomb[i] = coul;
+        P.blocked[i] = 0;
+    }
+}
+
+}  // namespace ceg

@@ -79,6 +79,12 @@ int ceg_device_count(int32_t* n);
 /* name (<=255 chars), SM count, memory bytes, SM clock kHz of a device */
 int ceg_device_info(int32_t device, char* name256, int32_t* sm_count, int64_t* mem_bytes, int32_t* clock_khz);
 
+/* Number of kernels this library has launched in this process (all handles, all threads). */
+int ceg_kernel_launch_count(int64_t* n);
+/* FP64 FMA-chain microbenchmark: sustained DFMA throughput of the device in TFLOP/s (2 flop per FMA).
+ * The roofline denominator of the construction kernels (MEASURED_PEAKS.json has no FP64 entry). */
+int ceg_measure_fp64_peak(int32_t device, double* tflops);
+
 /* Pin / unpin a caller-owned host buffer so that slab write-back and query upload overlap compute. */
 int ceg_host_register(void* ptr, int64_t bytes);
 int ceg_host_unregister(void* ptr);

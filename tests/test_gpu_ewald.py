@@ -1,0 +1,106 @@
+"""GPU parity of the reciprocal-space Ewald term and the fused energy_point (A12)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import ceg_b200 as ceg
+from ceg_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def _framework_from_fixture(ex):
+    """Rebuild the unit-cell framework (positions, charges) of a fixture for the host API."""
+    n_unit = len(ex["site_charge"]) // int(np.prod(ex["supercell"]))
+    return ceg.RASPASystem(ex["unit_mat"], ex["positions"][:n_unit], ["X"] * n_unit, np.ones(n_unit),
+                           ex["charges"][:n_unit], False)
+
+
+def test_structure_factor_and_reciprocal_vs_oracle(cuda_lib, orc):
+    inp, cset, ex = wl.load_fixture("cha_na")
+    fw = _framework_from_fixture(ex)
+    ef = ceg.initialize_ewald(fw, tuple(int(x) for x in ex["supercell"]))
+    oe = orc.OracleEwald(fw, tuple(int(x) for x in ex["supercell"]))
+    assert ef.kspace.ks == (8, 8, 8) and ef.kspace.num_kvecs == 1368
+    assert np.array_equal(ef.kfactors, oe.kfactors)
+    S_gold = ex["S_re"] + 1j * ex["S_im"]
+    scale = np.abs(S_gold).max()
+    assert np.abs(ef.StoreRigidChargeFramework - oe.S).max() <= 1e-11 * scale
+    assert np.abs(ef.StoreRigidChargeFramework - S_gold).max() <= 1e-11 * scale
+    # batched placements of a 3-site molecule (CO2 geometry) and of a single ion
+    rng = np.random.default_rng(3)
+    centers = wl.random_positions(fw.mat, 500, 31) * 3.0 - 20.0
+    for q, offs in [(np.array([-0.3256, 0.6512, -0.3256]), np.array([[0, 0, 1.149], [0, 0, 0], [0, 0, -1.149]])),
+                    (np.array([0.9094]), np.zeros((1, 3)))]:
+        pos = centers[:, None, :] + offs[None, :, :]
+        enc, stat = 12.5, -3.25
+        got = ceg._lib.ewald_reciprocal(ef.handle, pos, q, enc, stat)
+        want = oe.reciprocal(pos, q, enc, stat)
+        assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max(), np.abs(got - want).max()
+
+
+def test_two_co2_golden(cuda_lib):
+    """test/runtests.jl:53-56: compute_ewald of two CO2 molecules in CHA."""
+    gold = json.load(open(os.path.join(wl.GOLDEN_DIR, "goldens.json")))["reference_values"]
+    inp, cset, ex = wl.load_fixture("cha_na")
+    fw = _framework_from_fixture(ex)
+    ef = ceg.initialize_ewald(fw)
+    q = np.array([-0.3256, 0.6512, -0.3256])
+    co2 = ceg.RASPASystem(np.diag([np.inf] * 3), np.array([[0, 0, 1.149], [0, 0, 0.0], [0, 0, -1.149]]),
+                          ["O_co2", "C_co2", "O_co2"], np.ones(3), q, True)
+    m1 = co2.with_positions([[1.3, 2.9, 1.149], [1.3, 2.9, 0.0], [1.3, 2.9, -1.149]])
+    m2 = co2.with_positions([[4.7, 10.1, 1.149], [4.7, 10.1, 0.0], [4.7, 10.1, -1.149]])
+    e = ceg.compute_ewald(ef, ([m1, m2],))
+    assert abs(e - gold["two_co2_reciprocal"]) <= 1e-9 * abs(gold["two_co2_reciprocal"]), e
+
+
+def test_energy_points_fused_na_cha(cuda_lib, orc):
+    """energy_point / energy_grid path (grids.jl:311-327): VdW + q*Coulomb interpolation + reciprocal
+    Ewald, with a blocking mask, vs the same composition of oracle pieces; plus the reference's
+    Na+ origin golden (runtests.jl:44-45) on a coarse sub-lattice of energy_grid."""
+    gold = json.load(open(os.path.join(wl.GOLDEN_DIR, "goldens.json")))["reference_values"]
+    inp, cset, ex = wl.load_fixture("cha_na")
+    fw = _framework_from_fixture(ex)
+    nx, ny, nz = cset.nodes
+    ps = ceg.ProbeSystem(None, None, inputs=inp)
+    outs = [np.empty((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
+    lam_v, thr_v = ceg.vdw_scaling()
+    lam_c, thr_c = ceg.coulomb_scaling()
+    ceg._lib.grid_build(ps.handle, ceg._lib.make_gridspec(cset), 0, nx, lam_v, thr_v, lam_c, thr_c, outs, None)
+    ps.close()
+    gv = ceg.EnergyGrid(cset, inp.supercell, np.inf, True, orc.scale_to_kelvin(outs[0]))
+    gc = ceg.EnergyGrid(cset, inp.supercell, 1e-6, True, orc.scale_to_kelvin(outs[1]))
+    ef = ceg.initialize_ewald(fw)
+    qna = float(ex["probe_charge"])
+    na = ceg.RASPASystem(np.diag([np.inf] * 3), np.zeros((1, 3)), ["Na"], np.ones(1), np.array([qna]), True)
+    # a blocking mask: one sphere, via the BlockFile derived from the VdW grid (grids.jl:188-204)
+    block = ceg.blockfile_from_grid(gv)
+    assert not block.empty
+    setup = ceg.CrystalEnergySetup(fw, na, gc, np.array([qna]), [gv], [0], ef, None, block)
+    # golden at the origin, without the mask
+    setup_nb = ceg.CrystalEnergySetup(fw, na, gc, np.array([qna]), [gv], [0], ef, None, ceg.BlockFile(cset))
+    v, c = ceg.energy_point(setup_nb, np.zeros((1, 3)))
+    assert abs(v - gold["na_cha_origin_vdw"]) <= 1e-9 * abs(gold["na_cha_origin_vdw"])
+    assert abs(c - gold["na_cha_origin_coulomb"]) <= 1e-9 * abs(gold["na_cha_origin_coulomb"])
+    # random placements vs oracle composition
+    pos = wl.random_positions(fw.mat, 20000, 41)
+    v, c = ceg.energy_points(setup, pos[:, None, :])
+    ctx = setup.ewald_ctx()
+    oe = orc.OracleEwald(fw)
+    blocked = orc.block_lookup(cset, block.block, pos)
+    wv = orc.interpolate(cset, gv.grid, True, pos)
+    wc = qna * orc.interpolate(cset, gc.grid, False, pos) + oe.reciprocal(pos[:, None, :], np.array([qna]),
+                                                                         ctx.energy_net_charges, ctx.static_contribution)
+    wv[blocked] = 1e100
+    wc[blocked] = 0.0
+    assert np.array_equal(v == 1e100, wv == 1e100)
+    ok = wv != 1e100
+    assert (np.abs(v[ok] - wv[ok]) <= 1e-9 * np.abs(wv[ok]) + 1e-6).all()
+    assert (np.abs(c - wc) <= 1e-9 * np.abs(wc) + 1e-6).all()
+    # energy_grid on a coarse lattice: [1,1,1] entry equals energy_point at the origin (runtests.jl:46)
+    eg = ceg.energy_grid(setup_nb, 3.0)
+    v0, c0 = ceg.energy_point(setup_nb, np.zeros((1, 3)))
+    assert eg.shape[0] == 1 and eg[0, 0, 0, 0] == v0 + c0
+    gv.close(); gc.close()

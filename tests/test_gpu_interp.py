@@ -1,0 +1,123 @@
+"""GPU parity of tricubic interpolation against the CPU oracle (64x64 matrix form)."""
+import numpy as np
+import pytest
+
+import ceg_b200 as ceg
+from ceg_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9   # north_star: interpolated energies within 1e-9 relative
+
+
+def _random_grid(cset, seed, hot_fraction=0.0):
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = cset.nodes
+    g = rng.standard_normal((8, nx, ny, nz)).astype(np.float32)
+    g[0] *= 1000.0
+    if hot_fraction:
+        hot = rng.random((nx, ny, nz)) < hot_fraction
+        g[0][hot] = np.float32(2.4e7)
+    return g
+
+
+def _check(orc, cset, grid, is_vdw, pos, what):
+    eg = ceg.EnergyGrid(cset, (1, 1, 1), np.inf if is_vdw else 1e-6, True, grid)
+    got = ceg.interpolate_grid(eg, pos)
+    want = orc.interpolate(cset, grid, is_vdw, pos)
+    blocked = want == 1e100
+    assert np.array_equal(got == 1e100, blocked), f"{what}: blocked masks differ"
+    ok = ~blocked
+    scale = np.maximum(np.abs(want[ok]), 1e-3 * np.abs(grid[0]).mean() if not is_vdw else 1.0)
+    err = np.abs(got[ok] - want[ok]) / scale
+    assert err.max() <= RTOL, f"{what}: worst rel err {err.max():.3e}"
+    eg.close()
+    return blocked.mean()
+
+
+@pytest.mark.parametrize("shape", ["triclinic", "ortho", "rhombo"])
+def test_random_grids(cuda_lib, orc, shape):
+    mats = {"triclinic": ceg.mat_from_parameters((13.0187, 11.2063, 9.3758), (92.82, 107.2, 103.26)),
+            "ortho": np.diag([7.3, 9.1, 5.2]),
+            "rhombo": ceg.mat_from_parameters((9.0, 9.0, 9.0), (94.07, 94.07, 94.07))}
+    cset = ceg.GridCoordinatesSetup.from_cell(mats[shape], 0.41)
+    grid = _random_grid(cset, 5, hot_fraction=0.02)
+    # positions inside, outside (wrapped) and far outside the cell
+    pos = np.concatenate([wl.random_positions(cset.cell.mat, 20000, 21),
+                          wl.random_positions(cset.cell.mat, 2000, 22) * 7.0 - 30.0])
+    frac_blocked = _check(orc, cset, grid, True, pos, shape + " vdw")
+    assert 0.02 < frac_blocked < 0.5
+    _check(orc, cset, grid, False, pos, shape + " coulomb")
+
+
+def test_nodes_edges_and_empty(cuda_lib, orc):
+    """Exact nodes (r = 0), the far faces of the bounding box (p1 clamps, grids.jl:218) and n = 0."""
+    cset = ceg.GridCoordinatesSetup.from_cell(np.diag([6.0, 5.0, 4.0]), 0.5)
+    grid = _random_grid(cset, 9)
+    eg = ceg.EnergyGrid(cset, (1, 1, 1), 1e-6, True, grid)
+    nx, ny, nz = cset.nodes
+    idx = np.array([(i, j, k) for i in (0, 3, nx - 2) for j in (0, 5, ny - 2) for k in (0, 2, nz - 2)])
+    pos = np.array([ceg.abc_to_xyz(cset, *t) for t in idx]) + 1e-9   # just inside the cell of node t
+    got = ceg.interpolate_grid(eg, pos)
+    want = grid[0][idx[:, 0], idx[:, 1], idx[:, 2]].astype(np.float64)
+    assert np.allclose(got, want, rtol=0, atol=2e-5)
+    assert np.allclose(got, orc.interpolate(cset, grid, False, pos), rtol=1e-9, atol=1e-9)
+    # points on the cell faces: wrap to 0 / stay at the top face
+    face = np.array([[6.0, 2.0, 1.0], [0.0, 0.0, 0.0], [5.999999999, 4.999999999, 3.999999999], [-1e-12, 2.0, 3.0]])
+    assert np.allclose(ceg.interpolate_grid(eg, face), orc.interpolate(cset, grid, False, face), rtol=1e-9, atol=1e-9)
+    assert ceg.interpolate_grid(eg, np.zeros((0, 3))).shape == (0,)
+    assert isinstance(ceg.interpolate_grid(eg, np.array([1.0, 2.0, 3.0])), float)
+    eg.close()
+    assert ceg.interpolate_grid(ceg.EnergyGrid.zero(), np.array([1.0, 2.0, 3.0])) == 0.0
+    with pytest.raises(ValueError):
+        ceg.interpolate_grid(ceg.EnergyGrid.invalid(), np.array([1.0, 2.0, 3.0]))
+
+
+def test_c2_on_built_grids_and_goldens(cuda_lib, orc, tmp_path):
+    """C1 -> C2 end to end on the device path: build the Ar grid of CHA+Na and the Na+/Coulomb grids of
+    CHA at 0.15 Å, write/parse the .grid files, interpolate; check the reference's own known
+    answers (test/runtests.jl:38,44) and 2e5 random positions against the oracle on the same
+    Float32 grids."""
+    import json, os
+    gold = json.load(open(os.path.join(wl.GOLDEN_DIR, "goldens.json")))["reference_values"]
+    # --- Ar in CHA+Na: minimum of energy_grid(0.3 Å) at lattice index (52,50,91)
+    inp, cset, ex = wl.load_fixture("chana_ar")
+    ps = ceg.ProbeSystem(None, None, inputs=inp)
+    nx, ny, nz = cset.nodes
+    out = [np.empty((8, nx, ny, nz), dtype=np.float32)]
+    lam_v, thr_v = ceg.vdw_scaling()
+    lam_c, thr_c = ceg.coulomb_scaling()
+    ceg._lib.grid_build(ps.handle, ceg._lib.make_gridspec(cset), 0, nx, lam_v, thr_v, lam_c, thr_c, out, None)
+    ps.close()
+    path = str(tmp_path / "ar.grid")
+    ceg.write_grid(path, cset, inp.supercell, out[0])
+    eg = ceg.parse_grid(path, False)            # cell matrix read back from the file tail
+    assert np.array_equal(eg.csetup.dims, cset.dims) and np.allclose(eg.csetup.cell.mat, cset.cell.mat, rtol=0, atol=0)
+    mat = cset.cell.mat
+    nums = [int(np.floor(np.linalg.norm(mat[:, c]) / 0.3)) + 1 for c in range(3)]
+    p = (51 * mat[:, 0] / nums[0] + 49 * mat[:, 1] / nums[1]) + 90 * mat[:, 2] / nums[2]
+    e = ceg.interpolate_grid(eg, p)
+    assert abs(e - gold["ar_chana_min"]) <= 1e-9 * abs(gold["ar_chana_min"]), (e, gold["ar_chana_min"])
+    pos = wl.random_positions(mat, 200000, 1)
+    got = ceg.interpolate_grid(eg, pos)
+    want = orc.interpolate(eg.csetup, eg.grid, True, pos)
+    assert np.array_equal(got == 1e100, want == 1e100)
+    ok = want != 1e100
+    assert (np.abs(got[ok] - want[ok]) <= 1e-9 * np.abs(want[ok]) + 1e-6).all()
+    eg.close()
+    # --- Na+ in CHA at the origin: vdw golden (runtests.jl:44)
+    inp, cset, ex = wl.load_fixture("cha_na")
+    ps = ceg.ProbeSystem(None, None, inputs=inp)
+    nx, ny, nz = cset.nodes
+    outs = [np.empty((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
+    ceg._lib.grid_build(ps.handle, ceg._lib.make_gridspec(cset), 0, nx, lam_v, thr_v, lam_c, thr_c, outs, None)
+    ps.close()
+    pv, pc = str(tmp_path / "na.grid"), str(tmp_path / "coul.grid")
+    ceg.write_grid(pv, cset, inp.supercell, outs[0])
+    ceg.write_grid(pc, cset, inp.supercell, outs[1], ewald_precision=1e-6)
+    gv = ceg.parse_grid(pv, False, cset.cell.mat)
+    gc = ceg.parse_grid(pc, True, cset.cell.mat)
+    assert gc.ewald_precision == 1e-6 and gv.ewald_precision == np.inf
+    v0 = ceg.interpolate_grid(gv, np.zeros(3))
+    assert abs(v0 - gold["na_cha_origin_vdw"]) <= 1e-9 * abs(gold["na_cha_origin_vdw"])
+    gv.close(); gc.close()
