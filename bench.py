@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""Benchmark of the energy-grid hot path (BASELINE.json metric: grid points/sec (LJ+Ewald FP64) at
+1/2/4/8 B200; tricubic interpolations/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # product arm (CUDA, C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+One JSON line on stdout (rank 0).  Under torchrun (N > 1) one rank per GPU; the C4 grid is sharded
+into contiguous x-slabs (no data-path collective) and interpolation queries are
+sharded by index.  Timings are device-side (CUDA events on the launching stream), max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD_BUILD = ("C4: CHA_1.4_3b4eeb96 (972 framework atoms, rhombohedral 28.377 Å cell), Na+ probe: fused "
+                  "VdW (Buckingham+HardSphere) + Ewald real-space grids, value + 7 derivative channels, 0.10 Å spacing "
+                  "(326x306x284 = 28,330,704 points), 12 Å cutoff, x-slab sharded")
+WORKLOAD_INTERP = ("C2: tricubic interpolation of 10^7 random positions (splitmix64 seed 1) on the C1 Na+ VdW and "
+                   "Coulomb grids (0.15 Å, 218x204x190 nodes, 270 MB each)")
+N_QUERIES = 10_000_000
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def slabs(n, parts):
+    base, rem = divmod(n, parts)
+    out, s = [], 0
+    for p in range(parts):
+        e = s + base + (1 if p < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while a timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+        out["samples"] = len(rows)
+        if sm:
+            top = [x for x in sm if x >= 0.5 * max(sm)]   # samples under load
+            out["sm_mhz"] = float(np.median(top))
+            out["sm_max_mhz"] = float(rows[0][2])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, nme in enumerate(names):
+            if any(r[5 + i].strip().lower().startswith("active") for r in rows):
+                out["reasons"].append(nme)
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def flops_per_point(inp, stats):
+    """per in-cutoff pair 8 (distance) + 64 (Ewald real-space) for every atom + 59
+    (Buckingham) / 48 (LJ) for the atoms the probe has a VdW term with."""
+    n_in = stats["pairs_in_cutoff"] / max(1, stats["n_points"])
+    types, counts = np.unique(inp.types, return_counts=True)
+    frac = {int(t): c / len(inp.types) for t, c in zip(types, counts)}
+    per_pair = 8.0 + (64.0 if inp.want_coulomb else 0.0)
+    for p in range(inp.table.shape[0]):
+        for t, f in frac.items():
+            fl = int(inp.table[p, t]["flags"])
+            if fl & 4:
+                per_pair += 59.0 * f
+            elif fl & 2:
+                per_pair += 48.0 * f
+    return n_in * per_pair, n_in
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    import ceg_b200 as ceg
+    from ceg_b200 import workloads as wl
+
+    rank, local_rank, world = env_rank()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    K, W = args.steps, args.warmup
+    stream = torch.cuda.current_stream().cuda_stream
+    inp, cset1, ex = wl.load_fixture("cha_na")
+    cset4 = wl.respace(cset1, 0.10)
+    lam_v, thr_v = ceg.vdw_scaling()
+    lam_c, thr_c = ceg.coulomb_scaling()
+    launches0 = ceg._lib.kernel_launch_count()
+    fp64_peak = ceg._lib.measure_fp64_peak(dev)
+    hbm_peak, hbm_src = measured_peaks()
+
+    # ================= construction: kernel-only, outputs resident in HBM ===========================
+    nx, ny, nz = cset4.nodes
+    a, b = slabs(nx, world)[rank]
+    gs4 = ceg._lib.make_gridspec(cset4)
+    ps = ceg.ProbeSystem(None, None, inputs=inp, device=dev)
+    d_out = [torch.empty((8, b - a, ny, nz), dtype=torch.float32, device="cuda") for _ in range(2)]
+    ptrs = [t.data_ptr() for t in d_out]
+    for _ in range(W):
+        ceg._lib.grid_build_dev(ps.handle, gs4, a, b, lam_v, thr_v, lam_c, thr_c, ptrs, stream)
+    barrier()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ceg._lib.kernel_launch_count()
+    e0.record()
+    for _ in range(K):
+        ceg._lib.grid_build_dev(ps.handle, gs4, a, b, lam_v, thr_v, lam_c, thr_c, ptrs, stream)
+    e1.record()
+    barrier()
+    build_ms = max_over_ranks(e0.elapsed_time(e1)) / K
+    build_launches = ceg._lib.kernel_launch_count() - l0
+    clocks = sampler.stop()
+    stats = ceg._lib.probe_last_stats(ps.handle)
+    fl_pp, n_in_pp = flops_per_point(inp, stats)
+    my_ms = e0.elapsed_time(e1) / K
+    my_tflops = fl_pp * stats["n_points"] / (my_ms * 1e-3) / 1e12
+    total_points = nx * ny * nz
+    build_value = total_points / (build_ms * 1e-3)
+
+    # ================= construction: end to end through the host C ABI ==============================
+    host = [torch.empty((8, nx, ny, nz), dtype=torch.float32).pin_memory() if world == 1 else
+            torch.empty((8, nx, ny, nz), dtype=torch.float32) for _ in range(2)]
+    host_np = [h.numpy() for h in host]
+    if world > 1:   # pin only this rank's slab pages is not expressible; register the whole array once
+        for h in host_np:
+            ceg._lib.host_register(h)
+    h2d_bytes = (inp.positions.nbytes + inp.types.nbytes + inp.charges.nbytes + inp.table.nbytes + 200)
+    d2h_bytes = 2 * 8 * (b - a) * ny * nz * 4
+
+    def e2e_step():
+        p2 = ceg.ProbeSystem(None, None, inputs=inp, device=dev)
+        ceg._lib.grid_build(p2.handle, gs4, a, b, lam_v, thr_v, lam_c, thr_c, host_np, None)
+        p2.close()
+
+    for _ in range(max(1, W // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, K // 2)):
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / max(1, K // 2)
+    e2e_value = total_points / (e2e_ms * 1e-3)
+
+    # ================= C1 (0.15 Å) on this GPU: the "< 1 s" headline, and the grids for C2 ============
+    nx1, ny1, nz1 = cset1.nodes
+    gs1 = ceg._lib.make_gridspec(cset1)
+    c1_host = [np.empty((8, nx1, ny1, nz1), dtype=np.float32) for _ in range(2)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ceg._lib.grid_build(ps.handle, gs1, 0, nx1, lam_v, thr_v, lam_c, thr_c, c1_host, None)
+    c1_e2e_ms = (time.perf_counter() - t0) * 1e3
+    d1 = [torch.empty((8, nx1, ny1, nz1), dtype=torch.float32, device="cuda") for _ in range(2)]
+    p1 = [t.data_ptr() for t in d1]
+    ceg._lib.grid_build_dev(ps.handle, gs1, 0, nx1, lam_v, thr_v, lam_c, thr_c, p1, stream)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        ceg._lib.grid_build_dev(ps.handle, gs1, 0, nx1, lam_v, thr_v, lam_c, thr_c, p1, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    c1_kernel_ms = e0.elapsed_time(e1) / 3
+    del d1, d_out
+    ps.close()
+
+    # ================= interpolation (C2) ============================================================
+    gK = [(g.astype(np.float64) * ceg.GRID_TO_KELVIN).astype(np.float32) for g in c1_host]   # parse_grid scaling
+    del c1_host
+    eg_v = ceg.EnergyGrid(cset1, (1, 1, 1), float("inf"), True, gK[0], dev)
+    eg_c = ceg.EnergyGrid(cset1, (1, 1, 1), 1e-6, True, gK[1], dev)
+    hv, hc = eg_v.handle, eg_c.handle
+    qa, qb = slabs(N_QUERIES, world)[rank]
+    nq = qb - qa
+    pos_host = torch.from_numpy(wl.random_positions(cset1.cell.mat, nq, 1, start=qa)).pin_memory()
+    d_pos = pos_host.cuda()
+    d_e = [torch.empty(nq, dtype=torch.float64, device="cuda") for _ in range(2)]
+
+    def interp_step():
+        ceg._lib.interpolate_dev(hv, nq, d_pos.data_ptr(), d_e[0].data_ptr(), stream)
+        ceg._lib.interpolate_dev(hc, nq, d_pos.data_ptr(), d_e[1].data_ptr(), stream)
+
+    for _ in range(W):
+        interp_step()
+    barrier()
+    sampler2 = ClockSampler(dev)
+    sampler2.start()
+    l0 = ceg._lib.kernel_launch_count()
+    KI = max(K, 20)
+    e0.record()
+    for _ in range(KI):
+        interp_step()
+    e1.record()
+    barrier()
+    interp_ms = max_over_ranks(e0.elapsed_time(e1)) / KI
+    interp_launches = ceg._lib.kernel_launch_count() - l0
+    clocks2 = sampler2.stop()
+    interp_value = 2 * N_QUERIES / (interp_ms * 1e-3)
+    my_interp_ms = e0.elapsed_time(e1) / KI
+    interp_gbs = 2 * nq * 288.0 / (my_interp_ms * 1e-3) / 1e9
+    blocked_fraction = float((d_e[0] == 1e100).double().mean().item())
+    checksum = float(torch.where(d_e[0] == 1e100, torch.zeros_like(d_e[0]), d_e[0]).sum().item())
+    # e2e: pinned host positions in, host energies out, through ceg_interpolate
+    out_host = [torch.empty(nq, dtype=torch.float64).pin_memory() for _ in range(2)]
+    pos_np = pos_host.numpy()
+    out_np = [o.numpy() for o in out_host]
+    import ctypes as C
+
+    def interp_e2e():
+        for h, o in ((hv, out_np[0]), (hc, out_np[1])):
+            rc = ceg._lib.load().ceg_interpolate(h, C.c_int64(nq), pos_np.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 o.ctypes.data_as(C.POINTER(C.c_double)))
+            assert rc == 0
+    interp_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        interp_e2e()
+    barrier()
+    interp_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+    assert np.array_equal(out_np[0], d_e[0].cpu().numpy())
+
+    # ================= CPU baseline (rank 0, N = 1 only): the oracle on the host cores ===============
+    cpu = None
+    cpu_i = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, cpu_i = cpu_baseline(inp, cset4, cset1, gK, budget_s=args.cpu_budget)
+
+    total_launches = ceg._lib.kernel_launch_count() - launches0
+    if rank == 0:
+        line = {
+            "metric": "grid points/sec (LJ+Ewald FP64)",
+            "value": build_value, "unit": "grid points/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": build_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "real CHA_1.4_3b4eeb96 framework fixture (flattened, tests/golden/cha_na.npz); "
+                                     "synthetic query positions",
+            "config": {"workload": WORKLOAD_BUILD, "parallelism": f"x-slab x{world}",
+                       "l2": "no L2 flush: inputs (<1 MB image list) are re-read by every tile by design; each step "
+                             "writes 1.8 GB of output (> 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(sum_over_ranks(d2h_bytes)) if world > 1 else int(d2h_bytes),
+                    "ms_per_step": e2e_ms, "note": "ceg_probe_create + ceg_grid_build into pinned host arrays + free"},
+            "roofline": {"bound": "fp64", "achieved": my_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": my_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "ceg_measure_fp64_peak (DFMA chain, this run); nominal 37-40",
+                         "algorithmic_flop_per_point": fl_pp, "pairs_in_cutoff_per_point": n_in_pp,
+                         "pairs_tested_per_point": stats["pairs_tested"] / max(1, stats["n_points"]),
+                         "kernel": "grid_build_tiled_kernel<8,8,8,1,true>", "kernel_ms": my_ms},
+            "gpu_launches": int(build_launches),
+            "clocks": clocks,
+            "c1": {"workload": "C1: same framework, 0.15 Å (218x204x190 = 8,449,680 points), VdW + Coulomb grids, 1 GPU",
+                   "kernel_ms": c1_kernel_ms, "e2e_ms_pageable_host": c1_e2e_ms,
+                   "points_per_s_kernel": 8449680 / (c1_kernel_ms * 1e-3)},
+            "interp": {"metric": "tricubic interpolations/sec", "value": interp_value, "unit": "interpolations/s",
+                       "ms_per_step": interp_ms, "steps": KI,
+                       "config": {"workload": WORKLOAD_INTERP, "parallelism": f"queries x{world}",
+                                  "l2": "grids 2 x 270 MB + 240 MB of positions exceed the 126 MB L2; no flush"},
+                       "e2e": {"value": 2 * N_QUERIES / (interp_e2e_ms * 1e-3), "unit": "interpolations/s",
+                               "h2d_bytes_per_step": int(2 * N_QUERIES * 24), "d2h_bytes_per_step": int(2 * N_QUERIES * 8),
+                               "ms_per_step": interp_e2e_ms},
+                       "roofline": {"bound": "hbm", "achieved": interp_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": interp_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                                    "algorithmic_bytes_per_query": 288, "kernel": "interpolate_kernel"},
+                       "gpu_launches": int(interp_launches), "clocks": clocks2,
+                       "blocked_fraction": blocked_fraction, "checksum_K": checksum,
+                       "cpu_baseline": cpu_i},
+            "cpu_baseline": cpu,
+            "gpu_launches_total": int(total_launches),
+            "device": ceg._lib.device_info(dev),
+        }
+        print(json.dumps(line))
+    eg_v.close()
+    eg_c.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_baseline(inp, cset4, cset1, gK, budget_s=20.0):
+    """The reference's CPU algorithm (oracle port: brute force over all supercell atoms per point, one
+    pass per grid, probes.jl:71-117) on a bounded sample of the same workload, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    orc.build()
+    nx, ny, nz = cset4.nodes
+    t0 = time.perf_counter()
+    orc.grid_build(inp, cset4, nx // 2, nx // 2 + 1, 1, want_f32=True)
+    t1 = time.perf_counter() - t0
+    n_planes = int(max(1, min(nx, budget_s / max(t1, 1e-3))))
+    stride = max(1, nx // n_planes)
+    t0 = time.perf_counter()
+    orc.grid_build(inp, cset4, 0, nx, stride, want_f32=True)
+    dt = time.perf_counter() - t0
+    planes = len(range(0, nx, stride))
+    cores = orc.num_threads()
+    cpu = {"value": planes * ny * nz / dt, "unit": "grid points/s", "cores": cores, "kind": "port",
+           "sample": f"{planes} of {nx} x planes (every {stride}th) of the same C4 grid, VdW + Coulomb passes, "
+                     f"{dt:.1f} s on {cores} OpenMP threads"}
+    cpu_i = None
+    if gK is not None:
+        from ceg_b200 import workloads as wl
+        pos = wl.random_positions(cset1.cell.mat, 1_000_000, 1)
+        t0 = time.perf_counter()
+        orc.interpolate(cset1, gK[0], True, pos)
+        orc.interpolate(cset1, gK[1], False, pos)
+        dt = time.perf_counter() - t0
+        cpu_i = {"value": 2e6 / dt, "unit": "interpolations/s", "cores": cores, "kind": "port",
+                 "sample": f"first 10^6 of the 10^7 C2 positions on both grids, 64x64 matrix form, {dt:.2f} s"}
+    return cpu, cpu_i
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Julia is not available
+    (SURVEY.md §8c), so this is the oracle port, timed with all host threads on bounded samples of the
+    product arm's workload.  Rank 0 only."""
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    from ceg_b200 import workloads as wl
+    orc.build()
+    inp, cset1, _ = wl.load_fixture("cha_na")
+    cset4 = wl.respace(cset1, 0.10)
+    nx, ny, nz = cset4.nodes
+    K, W = args.steps, args.warmup
+    t0 = time.perf_counter()
+    orc.grid_build(inp, cset4, nx // 2, nx // 2 + 1, 1, want_f32=True)
+    t1 = time.perf_counter() - t0
+    per_step_s = max(1.0, args.cpu_budget * 3.0 / (K + W))
+    n_planes = int(max(1, min(nx, per_step_s / max(t1, 1e-3))))
+    stride = max(1, nx // n_planes)
+    planes = len(range(0, nx, stride))
+    for w in range(W):
+        orc.grid_build(inp, cset4, w % stride, nx, stride, want_f32=True)
+    t0 = time.perf_counter()
+    for k in range(K):
+        orc.grid_build(inp, cset4, k % stride, nx, stride, want_f32=True)
+    dt = time.perf_counter() - t0
+    pts = sum(len(range(k % stride, nx, stride)) for k in range(K)) * ny * nz
+    value = pts / dt
+    cores = orc.num_threads()
+    sample = (f"each step = {planes} of {nx} x planes (every {stride}th) of the C4 grid, VdW + Coulomb passes, "
+              f"{cores} OpenMP threads")
+    line = {"impl": "reference", "metric": "grid points/sec (LJ+Ewald FP64)", "value": value, "unit": "grid points/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "real CHA_1.4_3b4eeb96 framework fixture (flattened, tests/golden/cha_na.npz)",
+            "config": {"workload": WORKLOAD_BUILD, "parallelism": f"OpenMP x{cores}"},
+            "cpu_baseline": {"value": value, "unit": "grid points/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "grid points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = CrystalEnergyGrids.jl CPU algorithm restated in C/OpenMP (oracle/ceg_oracle.c); "
+                    "Julia is not installed in this image"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ceg", choices=["ceg", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ceg" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -113,7 +113,7 @@ def mfi_shaped():
     n_o = n - n_si
     q_si = 2.05
     q_o = -q_si * n_si / n_o
-    species = {"O": (53.0, 3.30, q_o), "Si": (22.0, 2.30, q_si), "CH4": (148.0, 3.73, 0.0),
+    species = {"O": (53.0, 3.30, q_o), "Si": (22.0, 2.30, q_si), "C_ch4": (148.0, 3.73, 0.0),
                "C_co2": (27.0, 2.80, 0.70), "O_co2": (79.0, 3.05, -0.35)}
     ff = _lj_forcefield(species)
     charges = np.array([species[s][2] for s in symbols])
@@ -131,7 +131,7 @@ def mof_shaped(n_atoms: int = 5000, edge: float = 50.0):
     symbols = [kinds[i % 4] for i in range(n)]
     q = {"C": 0.25, "H": 0.15, "O": -0.70, "Zn": 0.30}
     species = {"C": (47.9, 3.47, q["C"]), "H": (7.65, 2.85, q["H"]), "O": (48.2, 3.03, q["O"]), "Zn": (27.7, 4.04, q["Zn"]),
-               "CH4": (148.0, 3.73, 0.0), "Na": (15.1, 2.66, 1.0)}
+               "C_ch4": (148.0, 3.73, 0.0), "Na": (15.1, 2.66, 1.0)}
     charges = np.array([q[s] for s in symbols])
     charges -= charges.mean()
     ff = _lj_forcefield(species)

@@ -86,7 +86,7 @@ def test_tiled_slab_cit7_triclinic_multi_probe(cuda_lib, orc):
 
 def test_tiled_slab_mfi_synthetic(cuda_lib, orc):
     """C3: orthorhombic synthetic framework, CH4 + CO2 sites (LJ) + Coulomb, supercell (2,2,2)."""
-    inp, cset, fw = wl.synthetic_inputs("mfi", 0.3, ("CH4", "C_co2", "O_co2"), True)
+    inp, cset, fw = wl.synthetic_inputs("mfi", 0.3, ("C_ch4", "C_co2", "O_co2"), True)
     assert inp.ortho and inp.supercell == (2, 2, 2)
     _check_slab(orc, inp, cset, 10, 14, "mfi")
 
