@@ -180,6 +180,33 @@ extern "C" int ceg_measure_fp64_peak(int32_t device, double* tflops) {
     return 0;
 }
 
+namespace ceg {
+__global__ void selftest_math_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    out[4 * i] = exp_neg_fast(-v);
+    out[4 * i + 1] = erfcx_fast(v);
+    out[4 * i + 2] = rsqrt_fast(v);
+    out[4 * i + 3] = rcp_fast(v);
+}
+}  // namespace ceg
+
+extern "C" int ceg_selftest_math(int32_t device, int64_t n, const double* x, double* out) {
+    if (n < 0 || (n > 0 && (!x || !out))) return fail("ceg_selftest_math: bad argument");
+    if (n == 0) return 0;
+    if (use_device(device)) return 1;
+    DevBuf dx, dout;
+    CEG_CK(dx.reserve(sizeof(double) * n));
+    CEG_CK(dout.reserve(sizeof(double) * 4 * n));
+    CEG_CK(cudaMemcpy(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, dx.as<double>(), dout.as<double>());
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    CEG_CK(cudaMemcpy(out, dout.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int ceg_host_register(void* ptr, int64_t bytes) {
     if (!ptr || bytes <= 0) return fail("ceg_host_register: bad argument");
     CEG_CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
@@ -383,12 +410,15 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     P.cutoff2 = h->cutoff2;
     P.alpha = h->alpha;
     P.cut_hi = h->cutoff2 + GUARD_BAND;
-    P.cut_lo = h->cutoff2 - GUARD_BAND;
-    double small = h->max_hs_r2;
-    if (h->want_coulomb) small = std::max(small, 1.0);
-    P.small_hi = small > 0 ? small + GUARD_BAND : -1.0;
-    P.stale_lo = (h->cell.ortho || h->cell.safemin2 >= h->cutoff2) ? std::numeric_limits<double>::infinity()
-                                                                    : h->cell.safemin2 - GUARD_BAND;
+    // fast path window: away from every mask threshold (hard spheres, the 1 Å rule, the cutoff, the
+    // entry of the reference's non-orthogonal image search) and from r -> 0
+    double flo = std::max(h->max_hs_r2, NEAR_R2);
+    if (h->want_coulomb) flo = std::max(flo, 1.0);
+    P.fast_lo = flo + GUARD_BAND;
+    double fhi = h->cutoff2 - GUARD_BAND;
+    if (!h->cell.ortho && h->cell.safemin2 < h->cutoff2) fhi = std::min(fhi, h->cell.safemin2 - GUARD_BAND);
+    P.fast_hi = fhi;
+    P.poly_erfcx = (h->alpha * cutoff <= ERFCX_XMAX && h->alpha >= 0) ? 1 : 0;
     const TileShape ts = tile_shape(h->n_probes);
     const double hx = 0.5 * (ts.tx - 1) * gs->delta[0], hy = 0.5 * (ts.ty - 1) * gs->delta[1], hz = 0.5 * (ts.tz - 1) * gs->delta[2];
     const double reach = cutoff + std::sqrt(hx * hx + hy * hy + hz * hz) + 1e-6;

@@ -8,8 +8,9 @@
 //
 // Two kernels:
 //  * derivatives_literal_kernel — arbitrary positions, the reference's per-pair algorithm verbatim
-//    (min-image search of utils.jl:210-246 for every supercell atom).  Backs
-//    ceg_compute_derivatives and is the in-kernel "exact" path of the tiled kernel.
+//    (min-image search of utils.jl:210-246 for every supercell atom, division-based formulas).
+//    Backs ceg_compute_derivatives; its device functions are also the "exact" path of the tiled
+//    kernel.
 //  * grid_build_tiled_kernel — the production kernel.  One CTA owns a TXxTYxTZ tile of grid
 //    nodes; it scans the pre-expanded list of periodic atom IMAGES (atom-major order, built on the
 //    host for the slab's bounding region), keeps those within cutoff + tile radius of the tile
@@ -18,11 +19,12 @@
 //    distance computation.  Because the probe supercell has perpendicular widths >= 2*cutoff
 //    (probes.jl:24), the in-cutoff image of an atom is unique and equals the reference's wrapped
 //    image, so the in-cutoff set is identical; pairs whose d^2 lands within a guard band of a mask
-//    threshold (cutoff^2, 1 Å^2, hard-sphere radius^2) or that would enter the reference's
-//    non-orthogonal image search are re-evaluated with the literal algorithm, which makes every
-//    mask decision bit-identical to the oracle's.
+//    threshold (cutoff^2, 1 Å^2, hard-sphere radius^2), that are closer than 0.1 Å, or that would
+//    enter the reference's non-orthogonal image search are re-evaluated with the literal algorithm
+//    and formulas, which makes every mask decision (and every Inf/NaN) bit-identical to the oracle's.
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace ceg {
 
@@ -38,76 +40,124 @@ constexpr int MAX_GRIDS = 5;       // up to 4 fused VdW probes + Coulomb per pas
 constexpr int LIST_CAP = 1024;     // shared-memory image list capacity per round
 constexpr int TABLE_SMEM_TYPES = 24;
 constexpr double GUARD_BAND = 1e-9;  // Å^2; fast-vs-literal d^2 differ by ~1e-13
+constexpr double NEAR_R2 = 0.01;     // below (0.1 Å)^2 always take the literal formulas (r -> 0 semantics)
 
-// ---- pair kernels ------------------------------------------------------------------------------
-// D = (1/r) d/dr.  Reciprocal powers are formed from one rsqrt instead of the reference's chain of
-// divisions; differences are a few ulp, far inside the 1e-9 parity tolerance.
+// ---- literal pair formulas (reference operation order; used off the hot path) -----------------------
+__device__ __noinline__ void vdw_pair_ref(const PairDev& p, double r2, double& v, double& p1, double& p2, double& p3) {
+    v = 0.0; p1 = 0.0; p2 = 0.0; p3 = 0.0;
+    const int fl = p.flags;
+    if (fl & CEG_PAIR_HS) v += (r2 < p.hs_r2) ? CUDART_INF : 0.0;
+    if (fl & CEG_PAIR_LJ) {                       // interactions.jl:434-441
+        const double eps = p.lj_eps;
+        const double t = p.lj_sig2 / r2;
+        const double x6 = t * t * t;
+        const double r4 = r2 * r2;
+        v += 4.0 * eps * x6 * (x6 - 1.0) - p.lj_shift;
+        p1 += 24.0 * eps * (x6 * (1.0 - 2.0 * x6)) / r2;
+        p2 += 96.0 * eps * (x6 * (7.0 * x6 - 2.0)) / r4;
+        p3 += 384.0 * eps * (x6 * (5.0 - 28.0 * x6)) / (r4 * r4);
+    }
+    if (fl & CEG_PAIR_BUCK) {                     // interactions.jl:447-457
+        const double A = p.bA, B = p.bB, C = p.bC;
+        const double r4 = r2 * r2;
+        const double r = sqrt(r2);
+        const double r6 = r4 * r2;
+        const double x6 = C / r6;
+        const double xe = A * exp(-B * r);
+        v += (xe - x6) - p.b_shift;
+        p1 += -B * xe / r + 6.0 * x6 / r2;
+        p2 += -48.0 * x6 / r4 + B * xe * (1.0 + B * r) / (r2 * r);
+        p3 += -(3.0 * B * r + B * B * r2 + 3.0) * B * xe * r / r6 + 480.0 * C / (r6 * r6);
+    }
+}
+
+__device__ __noinline__ void ewald_pair_ref(double alpha, double q, double r2, double& v, double& p1, double& p2,
+                                            double& p3) {   // ewald.jl:299-312
+    const double r = sqrt(r2);
+    const double r3 = r2 * r, r5 = r3 * r2;
+    const double a2 = r2 * (alpha * alpha);
+    const double e2 = 2.0 * alpha * r * exp(-a2) / sqrt(CUDART_PI);
+    const double c = erfc(alpha * r);
+    v = q * c / r;
+    p1 = -q * (e2 + c) / r3;
+    p2 = q * (e2 * (3.0 + 2.0 * a2) + 3.0 * c) / r5;
+    p3 = q * (-e2 * (15.0 + 10.0 * a2 + 4.0 * (a2 * a2)) - 15.0 * c) / (r5 * r2);
+}
+
+// ---- hot-path pair formulas ---------------------------------------------------------------------------
+// D = (1/r) d/dr.  Reciprocal powers come from one rsqrt, exp/erfcx are the branch-free versions of
+// fastmath.cuh; differences from the literal formulas are ~1e-13 relative.
 struct PairGeom {
     double r2, ir, ir2, r;
 };
 __device__ __forceinline__ PairGeom make_geom(double r2) {
     PairGeom g;
     g.r2 = r2;
-    g.ir = rsqrt(r2);
+    g.ir = rsqrt_fast(r2);
     g.ir2 = g.ir * g.ir;
     g.r = r2 * g.ir;
     return g;
 }
 
-__device__ __forceinline__ void vdw_pair(const PairDev& p, const PairGeom& g, double& v, double& p1, double& p2,
-                                         double& p3) {
+__device__ __forceinline__ void vdw_pair_fast(const PairDev& p, const PairGeom& g, double& v, double& p1, double& p2,
+                                              double& p3) {
     v = 0.0; p1 = 0.0; p2 = 0.0; p3 = 0.0;
     const int fl = p.flags;
-    if (fl & CEG_PAIR_HS) v += (g.r2 < p.hs_r2) ? CUDART_INF : 0.0;
-    if (fl & CEG_PAIR_LJ) {                       // interactions.jl:434-441
+    // hard sphere: the fast path only sees r2 >= fast_lo > every hs_r2, where the term is exactly 0
+    if (fl & CEG_PAIR_LJ) {
         const double eps = p.lj_eps;
         const double t = p.lj_sig2 * g.ir2;
         const double x6 = t * t * t;
         const double ir4 = g.ir2 * g.ir2;
-        v += 4.0 * eps * x6 * (x6 - 1.0) - p.lj_shift;
-        p1 += 24.0 * eps * (x6 * (1.0 - 2.0 * x6)) * g.ir2;
-        p2 += 96.0 * eps * (x6 * (7.0 * x6 - 2.0)) * ir4;
-        p3 += 384.0 * eps * (x6 * (5.0 - 28.0 * x6)) * (ir4 * ir4);
+        const double ex6 = eps * x6;
+        v += fma(4.0 * ex6, x6 - 1.0, -p.lj_shift);
+        p1 += 24.0 * (ex6 * fma(-2.0, x6, 1.0)) * g.ir2;
+        p2 += 96.0 * (ex6 * fma(7.0, x6, -2.0)) * ir4;
+        p3 += 384.0 * (ex6 * fma(-28.0, x6, 5.0)) * (ir4 * ir4);
     }
-    if (fl & CEG_PAIR_BUCK) {                     // interactions.jl:447-457
-        const double A = p.bA, B = p.bB, C = p.bC;
+    if (fl & CEG_PAIR_BUCK) {
+        const double B = p.bB;
         const double ir4 = g.ir2 * g.ir2;
         const double ir6 = ir4 * g.ir2;
-        const double x6 = C * ir6;
-        const double xe = A * exp(-B * g.r);
+        const double x6 = p.bC * ir6;
         const double Br = B * g.r;
+        const double xe = p.bA * exp_neg_fast(-Br);
+        const double Bxe = B * xe;
+        const double ir3 = g.ir2 * g.ir;
+        const double x6ir2 = x6 * g.ir2;
         v += (xe - x6) - p.b_shift;
-        p1 += -B * xe * g.ir + 6.0 * x6 * g.ir2;
-        p2 += -48.0 * x6 * ir4 + B * xe * (1.0 + Br) * (g.ir2 * g.ir);
-        p3 += -(3.0 * Br + Br * Br + 3.0) * B * xe * (g.r * ir6) + 480.0 * C * (ir6 * ir6);
+        p1 += fma(6.0, x6ir2, -(Bxe * g.ir));
+        p2 += fma(fma(Bxe, Br, Bxe), ir3, -48.0 * (x6ir2 * g.ir2));
+        p3 += fma(-(fma(Br, Br + 3.0, 3.0) * Bxe), ir3 * g.ir2, 480.0 * (x6 * ir6));
     }
 }
 
-// ewald.jl:299-312 with erfc(x) = exp(-x^2) * erfcx(x): one exp serves both terms.
-__device__ __forceinline__ void ewald_pair(double alpha, double two_alpha_over_sqrtpi, double q, const PairGeom& g,
-                                           double& v, double& p1, double& p2, double& p3) {
+__device__ __forceinline__ void ewald_pair_fast(double alpha, double two_alpha_over_sqrtpi, double q,
+                                                const PairGeom& g, bool poly_erfcx, double& v, double& p1,
+                                                double& p2, double& p3) {
     const double ar = alpha * g.r;
     const double a2 = ar * ar;                    // r2 * alpha^2
-    const double E = exp(-a2);
-    const double e2 = two_alpha_over_sqrtpi * g.r * E;
-    const double c = E * erfcx(ar);
-    const double ir3 = g.ir2 * g.ir, ir5 = ir3 * g.ir2, ir7 = ir5 * g.ir2;
-    v = q * c * g.ir;
-    p1 = -q * (e2 + c) * ir3;
-    p2 = q * (e2 * (3.0 + 2.0 * a2) + 3.0 * c) * ir5;
-    p3 = q * (-e2 * (15.0 + 10.0 * a2 + 4.0 * (a2 * a2)) - 15.0 * c) * ir7;
+    const double E = exp_neg_fast(-a2);
+    const double e2 = (two_alpha_over_sqrtpi * g.r) * E;
+    const double c = E * (poly_erfcx ? erfcx_fast(ar) : erfcx(ar));
+    const double qir = q * g.ir;
+    const double qir3 = qir * g.ir2, qir5 = qir3 * g.ir2, qir7 = qir5 * g.ir2;
+    v = qir * c;
+    p1 = -(qir3 * (e2 + c));
+    p2 = qir5 * fma(e2, fma(2.0, a2, 3.0), 3.0 * c);
+    p3 = -(qir7 * fma(e2, fma(fma(4.0, a2, 10.0), a2, 15.0), 15.0 * c));
 }
 
 __device__ __forceinline__ void accumulate(double* acc, double v, double p1, double p2, double p3, double dx,
                                            double dy, double dz, double dxy, double dxz, double dyz) {
     acc[0] += v;
-    acc[1] += p1 * dx;
-    acc[2] += p1 * dy;
-    acc[3] += p1 * dz;
-    acc[4] += p2 * dxy;
-    acc[5] += p2 * dxz;
-    acc[6] += p2 * dyz;
-    acc[7] += p3 * (dxz * dy);
+    acc[1] = fma(p1, dx, acc[1]);
+    acc[2] = fma(p1, dy, acc[2]);
+    acc[3] = fma(p1, dz, acc[3]);
+    acc[4] = fma(p2, dxy, acc[4]);
+    acc[5] = fma(p2, dxz, acc[5]);
+    acc[6] = fma(p2, dyz, acc[6]);
+    acc[7] = fma(p3, dxz * dy, acc[7]);
 }
 
 __device__ __forceinline__ double clamp_ref(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
@@ -151,7 +201,6 @@ __global__ void __launch_bounds__(128) derivatives_literal_kernel(const LiteralP
     if (threadIdx.x == 0) s_cell = P.cell;
     __syncthreads();
     const int n_grids = P.n_probes + P.want_coulomb;
-    const double taosp = 2.0 * P.alpha / sqrt(CUDART_PI);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.n_pos; i += (int64_t)gridDim.x * blockDim.x) {
         const double px = P.pos[3 * i], py = P.pos[3 * i + 1], pz = P.pos[3 * i + 2];
         for (int g = 0; g < n_grids; g++) {
@@ -163,14 +212,13 @@ __global__ void __launch_bounds__(128) derivatives_literal_kernel(const LiteralP
                 const double d2 = periodic_distance2_ref(b, s_cell);
                 if (d2 >= P.cutoff2) continue;
                 double v, p1, p2, p3;
-                const PairGeom geo = make_geom(d2);
                 if (coul) {
                     smallest = fmin(smallest, d2);
-                    ewald_pair(P.alpha, taosp, P.q[a], geo, v, p1, p2, p3);
+                    ewald_pair_ref(P.alpha, P.q[a], d2, v, p1, p2, p3);
                 } else {
                     const PairDev pr = P.table[g * P.n_types + P.type[a]];
                     if (pr.flags == 0) continue;
-                    vdw_pair(pr, geo, v, p1, p2, p3);
+                    vdw_pair_ref(pr, d2, v, p1, p2, p3);
                 }
                 accumulate(acc, v, p1, p2, p3, b[0], b[1], b[2], b[0] * b[1], b[0] * b[2], b[1] * b[2]);
             }
@@ -195,14 +243,14 @@ struct BuildParams {
     CellDev cell;
     GridSpecDev gs;
     double cutoff2, alpha;
-    double cut_hi, cut_lo;     // cutoff2 +- GUARD_BAND
-    double small_hi;           // max(1 Å^2, max hard-sphere r^2) + band: below it, take the literal path
-    double stale_lo;           // non-ortho cells: safemin2 - band (pairs above enter the image search); +inf if unused
+    double cut_hi;             // cutoff2 + GUARD_BAND: pairs below enter the pair code
+    double fast_lo, fast_hi;   // d2 in [fast_lo, fast_hi] takes the fast path, anything else the literal one
     double reach2;             // (cutoff + tile radius + slack)^2
     double lam_v, thr_v, lam_c, thr_c;
     int i0, i1;                // slab of x planes held by the output buffers
     int a0, a1;                // planes computed by this launch (i0 <= a0 < a1 <= i1)
     int tiles_x, tiles_y, tiles_z;
+    int poly_erfcx;            // alpha*cutoff within the fitted range of erfcx_fast
     const ExtAtom* ext;
     const ExtMeta* ext_meta;
     int n_ext;
@@ -256,7 +304,8 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
         for (int c = 0; c < 8; c++) acc[g][c] = 0.0;
     double smallest = CUDART_INF;
     const double taosp = 2.0 * P.alpha / sqrt(CUDART_PI);
-    unsigned long long n_tested = 0, n_in = 0;
+    const bool poly_erfcx = P.poly_erfcx != 0;
+    unsigned int n_tested = 0, n_in = 0;
     int count = 0;
     __syncthreads();
 
@@ -266,10 +315,30 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
         for (int e = 0; e < cnt; e++) {
             const ExtAtom a = s_atom[e];
             double dx = px - a.x, dy = py - a.y, dz = pz - a.z;
-            double d2 = dx * dx + dy * dy + dz * dz;
+            double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
             if (d2 < P.cut_hi) {
-                if (d2 > P.cut_lo || d2 < P.small_hi || d2 > P.stale_lo) {
-                    // literal re-evaluation from the original atom (mask thresholds, image search)
+                const int ty_ = s_meta[e].type;
+                if (d2 >= P.fast_lo && d2 <= P.fast_hi) {
+                    // ---- hot path ----
+                    n_in++;
+                    const PairGeom geo = make_geom(d2);
+                    const double dxy = dx * dy, dxz = dx * dz, dyz = dy * dz;
+#pragma unroll
+                    for (int g = 0; g < NP; g++) {
+                        const PairDev& pr = table_in_smem ? s_table[g * P.n_types + ty_] : P.table[g * P.n_types + ty_];
+                        if (pr.flags != 0) {
+                            double v, p1, p2, p3;
+                            vdw_pair_fast(pr, geo, v, p1, p2, p3);
+                            accumulate(acc[g], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                        }
+                    }
+                    if (COUL) {   // d2 >= fast_lo > 1 Å^2 here: `smallest` (probes.jl:108) is tracked on the literal path
+                        double v, p1, p2, p3;
+                        ewald_pair_fast(P.alpha, taosp, a.q, geo, poly_erfcx, v, p1, p2, p3);
+                        accumulate(acc[NG - 1], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                    }
+                } else {
+                    // ---- literal re-evaluation from the original atom (mask thresholds, r -> 0, image search)
                     const int o = s_meta[e].orig;
                     double b[3] = {xsub(px, P.atoms_xyz[3 * o]), xsub(py, P.atoms_xyz[3 * o + 1]),
                                    xsub(pz, P.atoms_xyz[3 * o + 2])};
@@ -277,26 +346,23 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
                     // this list entry must be the image the reference measured d2 on
                     if (fabs(d2x - d2) > 1e-6) continue;
                     if (d2x >= P.cutoff2) continue;
-                    d2 = d2x; dx = b[0]; dy = b[1]; dz = b[2];
-                }
-                n_in++;
-                const PairGeom geo = make_geom(d2);
-                const double dxy = dx * dy, dxz = dx * dz, dyz = dy * dz;
-                const int ty_ = s_meta[e].type;
+                    n_in++;
+                    const double bxy = b[0] * b[1], bxz = b[0] * b[2], byz = b[1] * b[2];
 #pragma unroll
-                for (int g = 0; g < NP; g++) {
-                    const PairDev& pr = table_in_smem ? s_table[g * P.n_types + ty_] : P.table[g * P.n_types + ty_];
-                    if (pr.flags != 0) {
-                        double v, p1, p2, p3;
-                        vdw_pair(pr, geo, v, p1, p2, p3);
-                        accumulate(acc[g], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                    for (int g = 0; g < NP; g++) {
+                        const PairDev& pr = table_in_smem ? s_table[g * P.n_types + ty_] : P.table[g * P.n_types + ty_];
+                        if (pr.flags != 0) {
+                            double v, p1, p2, p3;
+                            vdw_pair_ref(pr, d2x, v, p1, p2, p3);
+                            accumulate(acc[g], v, p1, p2, p3, b[0], b[1], b[2], bxy, bxz, byz);
+                        }
                     }
-                }
-                if (COUL) {
-                    smallest = fmin(smallest, d2);
-                    double v, p1, p2, p3;
-                    ewald_pair(P.alpha, taosp, a.q, geo, v, p1, p2, p3);
-                    accumulate(acc[NG - 1], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                    if (COUL) {
+                        smallest = fmin(smallest, d2x);
+                        double v, p1, p2, p3;
+                        ewald_pair_ref(P.alpha, a.q, d2x, v, p1, p2, p3);
+                        accumulate(acc[NG - 1], v, p1, p2, p3, b[0], b[1], b[2], bxy, bxz, byz);
+                    }
                 }
             }
         }
@@ -340,14 +406,15 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
 
     // stats: one atomic per warp
     if (P.stats) {
+        unsigned long long t64 = n_tested, i64 = n_in;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            n_tested += __shfl_down_sync(0xffffffffu, n_tested, o);
-            n_in += __shfl_down_sync(0xffffffffu, n_in, o);
+            t64 += __shfl_down_sync(0xffffffffu, t64, o);
+            i64 += __shfl_down_sync(0xffffffffu, i64, o);
         }
         if (lane == 0) {
-            atomicAdd(&P.stats[0], n_tested);
-            atomicAdd(&P.stats[1], n_in);
+            atomicAdd(&P.stats[0], t64);
+            atomicAdd(&P.stats[1], i64);
         }
     }
     if (!valid) return;

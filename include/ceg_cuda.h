@@ -85,6 +85,10 @@ int ceg_kernel_launch_count(int64_t* n);
  * The roofline denominator of the construction kernels (MEASURED_PEAKS.json has no FP64 entry). */
 int ceg_measure_fp64_peak(int32_t device, double* tflops);
 
+/* Self-test hook for the branch-free device math of the construction kernels (fastmath.cuh):
+ * out[4*i..] = exp_neg_fast(-x[i]), erfcx_fast(x[i]), rsqrt_fast(x[i]), rcp_fast(x[i]), x[i] > 0. */
+int ceg_selftest_math(int32_t device, int64_t n, const double* x, double* out);
+
 /* Pin / unpin a caller-owned host buffer so that slab write-back and query upload overlap compute. */
 int ceg_host_register(void* ptr, int64_t bytes);
 int ceg_host_unregister(void* ptr);
