@@ -41,7 +41,7 @@ EXPORTS = [
     "ceg_measure_fp64_peak", "ceg_selftest_math", "ceg_host_register",
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
-    "ceg_interpolate", "ceg_interpolate_dev", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
+    "ceg_interpolate", "ceg_interpolate_dev", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
     "ceg_ewald_reciprocal_dev", "ceg_block_upload", "ceg_block_free", "ceg_energy_points",
 ]
 
@@ -221,6 +221,17 @@ def grid_upload(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, grid: np.ndar
     _check(load().ceg_grid_upload(C.c_int32(device), C.byref(cell), C.byref(gs), _p(grid, C.c_float),
                                   C.c_int32(int(is_vdw)), C.byref(h)))
     return h
+
+
+def set_interp_layout(layout: int):
+    """-1 auto, 0 node records, 1 quads, 2 cells (include/ceg_cuda.h)."""
+    _check(load().ceg_set_interp_layout(C.c_int32(layout)))
+
+
+def grid_layout(h) -> int:
+    n = C.c_int32(0)
+    _check(load().ceg_grid_layout(h, C.byref(n)))
+    return n.value
 
 
 def grid_free(h):

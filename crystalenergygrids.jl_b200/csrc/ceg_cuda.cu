@@ -549,6 +549,20 @@ extern "C" int ceg_probe_last_stats(ceg_probe_h h, int64_t* n_points, int64_t* p
 // ================================================================================================
 // interpolation
 // ================================================================================================
+static std::atomic<int> g_interp_layout{-1};   // -1 = automatic
+
+extern "C" int ceg_set_interp_layout(int32_t layout) {
+    if (layout < -1 || layout > LAYOUT_CELL) return fail("ceg_set_interp_layout: layout must be -1 (auto), 0, 1 or 2");
+    g_interp_layout.store(layout);
+    return 0;
+}
+
+extern "C" int ceg_grid_layout(ceg_grid_h h, int32_t* layout) {
+    if (!h || !layout) return fail("null argument");
+    *layout = h->g.layout;
+    return 0;
+}
+
 extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* grid,
                                int32_t is_vdw, ceg_grid_h* out) {
     if (!unitcell || !gs || !grid || !out) return fail("ceg_grid_upload: null argument");
@@ -560,20 +574,40 @@ extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const
     h->g.uc = to_dev(*unitcell);
     h->g.gs = to_dev(*gs);
     h->g.is_vdw = is_vdw ? 1 : 0;
-    const int64_t npts = (int64_t)(gs->dims[0] + 1) * (gs->dims[1] + 1) * (gs->dims[2] + 1);
+    const int nx = gs->dims[0] + 1, ny = gs->dims[1] + 1, nz = gs->dims[2] + 1;
+    const int64_t npts = (int64_t)nx * ny * nz;
+    const size_t node_bytes = sizeof(float) * 8 * (size_t)npts;
     CEG_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CEG_CK(h->d_nodes.reserve(sizeof(float) * 8 * npts));
+    // layout: the widest record whose expansion leaves most of the memory free
+    int layout = g_interp_layout.load();
+    if (layout < 0) {
+        size_t free_b = 0, total_b = 0;
+        CEG_CK(cudaMemGetInfo(&free_b, &total_b));
+        layout = LAYOUT_NODE;
+        if (4 * node_bytes + 2 * node_bytes < free_b / 4) layout = LAYOUT_QUAD;
+        if (8 * node_bytes + 2 * node_bytes < free_b / 4) layout = LAYOUT_CELL;
+    }
     {
-        DevBuf tmp;
-        CEG_CK(tmp.reserve(sizeof(float) * 8 * npts));
-        CEG_CK(cudaMemcpyAsync(tmp.p, grid, sizeof(float) * 8 * npts, cudaMemcpyHostToDevice, h->stream));
+        DevBuf tmp, nodes;
+        DevBuf& node_dst = (layout == LAYOUT_NODE) ? h->d_nodes : nodes;
+        CEG_CK(tmp.reserve(node_bytes));
+        CEG_CK(node_dst.reserve(node_bytes));
+        CEG_CK(cudaMemcpyAsync(tmp.p, grid, node_bytes, cudaMemcpyHostToDevice, h->stream));
         const int blocks = (int)std::min<int64_t>((npts + 255) / 256, 148 * 32);
-        relayout_nodes_kernel<<<blocks, 256, 0, h->stream>>>(tmp.as<float>(), h->d_nodes.as<float4>(), npts);
+        relayout_nodes_kernel<<<blocks, 256, 0, h->stream>>>(tmp.as<float>(), node_dst.as<Rec8>(), npts);
         count_launch();
         CEG_CK(cudaGetLastError());
+        if (layout != LAYOUT_NODE) {
+            const int corners = (layout == LAYOUT_QUAD) ? 4 : 8;
+            CEG_CK(h->d_nodes.reserve(node_bytes * corners));
+            expand_records_kernel<<<148 * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz, corners);
+            count_launch();
+            CEG_CK(cudaGetLastError());
+        }
         CEG_CK(cudaStreamSynchronize(h->stream));
     }
-    h->g.nodes = h->d_nodes.as<float4>();
+    h->g.data = h->d_nodes.as<float>();
+    h->g.layout = layout;
     *out = h.release();
     return 0;
 }
@@ -588,13 +622,22 @@ extern "C" int ceg_grid_free(ceg_grid_h h) {
 
 static int interp_blocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 64)); }
 
+static cudaError_t launch_interpolate(const GridDev& g, int64_t n, const double* d_xyz, double* d_out, cudaStream_t s) {
+    const int blocks = interp_blocks(n);
+    switch (g.layout) {
+        case LAYOUT_CELL: interpolate_kernel<LAYOUT_CELL><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
+        case LAYOUT_QUAD: interpolate_kernel<LAYOUT_QUAD><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
+        default: interpolate_kernel<LAYOUT_NODE><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 extern "C" int ceg_interpolate_dev(ceg_grid_h h, int64_t n, const double* d_xyz, double* d_out, void* stream) {
     if (!h || n < 0 || (n > 0 && (!d_xyz || !d_out))) return fail("ceg_interpolate_dev: bad argument");
     if (n == 0) return 0;
     if (use_device(h->device)) return 1;
-    interpolate_kernel<<<interp_blocks(n), 256, 0, (cudaStream_t)stream>>>(h->g, n, d_xyz, d_out);
-    count_launch();
-    CEG_CK(cudaGetLastError());
+    CEG_CK(launch_interpolate(h->g, n, d_xyz, d_out, (cudaStream_t)stream));
     return 0;
 }
 
@@ -606,9 +649,7 @@ extern "C" int ceg_interpolate(ceg_grid_h h, int64_t n, const double* xyz, doubl
     CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * n));
     CEG_CK(h->d_out.reserve(sizeof(double) * n));
     CEG_CK(cudaMemcpyAsync(h->d_xyz.p, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
-    interpolate_kernel<<<interp_blocks(n), 256, 0, h->stream>>>(h->g, n, h->d_xyz.as<double>(), h->d_out.as<double>());
-    count_launch();
-    CEG_CK(cudaGetLastError());
+    CEG_CK(launch_interpolate(h->g, n, h->d_xyz.as<double>(), h->d_out.as<double>(), h->stream));
     CEG_CK(cudaMemcpyAsync(out, h->d_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
     CEG_CK(cudaStreamSynchronize(h->stream));
     return 0;

@@ -3,10 +3,17 @@
 // Replaces interpolate_grid (grids.jl:212-273) + offsetpoint (coordinates.jl:58-66), and the
 // BlockFile lookup (coordinates.jl:97-101).
 //
-// Device layout: the host/.grid order is [channel][x][y][z] (a random query touches 32 different
-// 32-byte sectors for 256 useful bytes).  On upload the grid is transposed ONCE to node-major
-// records [x][y][z][8 x f32]: one node = one 32-byte sector, so a query reads exactly its 8 corner
-// sectors (the 2 z-neighbours are adjacent: four 64-byte runs).
+// Device layouts.  The host/.grid order is [channel][x][y][z]: a random query touches 32 different
+// 32-byte sectors for 256 useful bytes.  On upload the grid is transposed ONCE to node-major records
+// (8 channels x f32 = 32 B = one sector per node) and, memory permitting, expanded further so that a
+// query's 8 corner records are contiguous and aligned:
+//   NODE  [x][y][z]            32 B records, 1x memory: 8 sectors per query, 4 runs of 64 B;
+//   QUAD  [x][y0][z0]         128 B records = nodes (y0,z0),(y0,z1),(y1,z0),(y1,z1), 4x memory:
+//                              2 aligned 128 B lines per query;
+//   CELL  [x0][y0][z0]        256 B records = all 8 corners, 8x memory: one aligned 256 B block.
+// ncu on the NODE layout (round 1) showed 595 B of DRAM traffic per query for 288 algorithmic bytes:
+// the L2 fetches whole 64/128 B neighbourhoods of every 32 B sector.  QUAD/CELL make every fetched
+// byte useful.  Each record is read with one 256-bit load per corner (LDG.E.256).
 //
 // Arithmetic: the reference forms a = COEFF * X (64x64 Lekien–Marsden matrix) and sums
 // a[i,j,k] rx^i ry^j rz^k.  That polynomial is the tensor-product cubic Hermite interpolant of the
@@ -18,11 +25,14 @@
 
 namespace ceg {
 
+enum { LAYOUT_NODE = 0, LAYOUT_QUAD = 1, LAYOUT_CELL = 2 };
+
 struct GridDev {
     CellDev uc;
     GridSpecDev gs;
-    const float4* nodes;   // [x][y][z][2 x float4]
+    const float* data;     // records of 8 floats per node, arranged per `layout`
     int is_vdw;
+    int layout;
 };
 
 struct BlockDev {
@@ -31,29 +41,47 @@ struct BlockDev {
     const uint8_t* mask;   // [x][y][z]
 };
 
+struct alignas(32) Rec8 {
+    float4 lo, hi;         // f, fx, fy, fz | fxy, fxz, fyz, fxyz
+};
+
 // [8][npts] -> [npts][8]
-__global__ void __launch_bounds__(256) relayout_nodes_kernel(const float* __restrict__ src, float4* __restrict__ dst,
+__global__ void __launch_bounds__(256) relayout_nodes_kernel(const float* __restrict__ src, Rec8* __restrict__ dst,
                                                              int64_t npts) {
     for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < npts; n += (int64_t)gridDim.x * blockDim.x) {
-        float4 lo, hi;
-        lo.x = src[n]; lo.y = src[npts + n]; lo.z = src[2 * npts + n]; lo.w = src[3 * npts + n];
-        hi.x = src[4 * npts + n]; hi.y = src[5 * npts + n]; hi.z = src[6 * npts + n]; hi.w = src[7 * npts + n];
-        dst[2 * n] = lo;
-        dst[2 * n + 1] = hi;
+        Rec8 r;
+        r.lo.x = src[n]; r.lo.y = src[npts + n]; r.lo.z = src[2 * npts + n]; r.lo.w = src[3 * npts + n];
+        r.hi.x = src[4 * npts + n]; r.hi.y = src[5 * npts + n]; r.hi.z = src[6 * npts + n]; r.hi.w = src[7 * npts + n];
+        dst[n] = r;
     }
 }
 
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+// NODE -> QUAD (corners = 4) or CELL (corners = 8); upper neighbours clamp at the last node, which is
+// exactly grids.jl:218 (p1 = p0 when p0 is the last node).
+__global__ void __launch_bounds__(256) expand_records_kernel(const Rec8* __restrict__ nodes, Rec8* __restrict__ dst,
+                                                             int nx, int ny, int nz, int corners) {
+    const int64_t total = (int64_t)nx * ny * nz * corners;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t % corners);
+        int64_t n = t / corners;
+        const int z = (int)(n % nz); n /= nz;
+        const int y = (int)(n % ny);
+        const int x = (int)(n / ny);
+        const int iz = c & 1, iy = (c >> 1) & 1, ix = (c >> 2) & 1;   // QUAD never sets ix
+        const int xx = min(x + ix, nx - 1), yy = min(y + iy, ny - 1), zz = min(z + iz, nz - 1);
+        dst[t] = nodes[((int64_t)xx * ny + yy) * nz + zz];
+    }
+}
+
+__device__ __forceinline__ void ld_rec(const float* p, float4& lo, float4& hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
                  : "l"(p));
-    return v;
 }
 
 struct Stencil {
-    int64_t base[2][2];   // node index of (x_ix, y_iy, z0)
-    int zstep;            // 0 or 1 node to z1
+    int p0[3];            // 0-based node indices of the lower corner
+    int step[3];          // 0 or 1: p1 - p0 per axis
     double r[3];
 };
 
@@ -61,22 +89,15 @@ struct Stencil {
 __device__ __forceinline__ void make_stencil(const CellDev& uc, const GridSpecDev& gs, const double* p, Stencil& st) {
     double s[3];
     offsetpoint_x(uc, gs, p, s);
-    int p0[3], p1[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        double fl = floor(s[i]);
+        const double fl = floor(s[i]);
         st.r[i] = xsub(s[i], fl);
         int q = (int)fl;
-        q = q < 1 ? 1 : (q > gs.n[i] ? gs.n[i] : q);   // memory safety only; in-range for finite input
-        p0[i] = q - 1;
-        p1[i] = p0[i] + (q != gs.n[i]);
+        q = q < 1 ? 1 : (q > gs.n[i] ? gs.n[i] : q);   // memory safety only; in range for finite input
+        st.p0[i] = q - 1;
+        st.step[i] = (q != gs.n[i]);
     }
-    const int64_t ny = gs.n[1], nz = gs.n[2];
-    st.base[0][0] = ((int64_t)p0[0] * ny + p0[1]) * nz + p0[2];
-    st.base[1][0] = ((int64_t)p1[0] * ny + p0[1]) * nz + p0[2];
-    st.base[0][1] = ((int64_t)p0[0] * ny + p1[1]) * nz + p0[2];
-    st.base[1][1] = ((int64_t)p1[0] * ny + p1[1]) * nz + p0[2];
-    st.zstep = p1[2] - p0[2];
 }
 
 // cubic Hermite basis on [0,1]: h[0]=value@0, h[1]=value@1, h[2]=slope@0, h[3]=slope@1
@@ -90,19 +111,36 @@ __device__ __forceinline__ void hermite(double t, double* h) {
 
 // Interpolate one grid at one prepared stencil.  Returns 1e100 if a VdW corner value exceeds 5e6 K
 // (grids.jl:245-248).
+template <int LAYOUT>
 __device__ __forceinline__ double interp_one(const GridDev& g, const Stencil& st) {
     float4 lo[8], hi[8];
+    const int64_t ny = g.gs.n[1], nz = g.gs.n[2];
+    const int64_t base = ((int64_t)st.p0[0] * ny + st.p0[1]) * nz + st.p0[2];
+    if (LAYOUT == LAYOUT_CELL) {
+        const float* rec = g.data + base * 64;
 #pragma unroll
-    for (int ix = 0; ix < 2; ix++)
+        for (int n = 0; n < 8; n++) ld_rec(rec + 8 * n, lo[n], hi[n]);
+    } else if (LAYOUT == LAYOUT_QUAD) {
+        const float* r0 = g.data + base * 32;
+        const float* r1 = r0 + (int64_t)st.step[0] * ny * nz * 32;
 #pragma unroll
-        for (int iy = 0; iy < 2; iy++)
+        for (int n = 0; n < 4; n++) {
+            ld_rec(r0 + 8 * n, lo[n], hi[n]);
+            ld_rec(r1 + 8 * n, lo[4 + n], hi[4 + n]);
+        }
+    } else {
 #pragma unroll
-            for (int iz = 0; iz < 2; iz++) {
-                const float4* p = g.nodes + 2 * (st.base[ix][iy] + (iz ? st.zstep : 0));
-                const int n = (ix * 2 + iy) * 2 + iz;
-                lo[n] = ldg_stream(p);
-                hi[n] = ldg_stream(p + 1);
-            }
+        for (int ix = 0; ix < 2; ix++)
+#pragma unroll
+            for (int iy = 0; iy < 2; iy++)
+#pragma unroll
+                for (int iz = 0; iz < 2; iz++) {
+                    const int64_t node = base + ((int64_t)(ix ? st.step[0] : 0) * ny + (iy ? st.step[1] : 0)) * nz +
+                                         (iz ? st.step[2] : 0);
+                    const int n = (ix * 2 + iy) * 2 + iz;
+                    ld_rec(g.data + node * 8, lo[n], hi[n]);
+                }
+    }
     if (g.is_vdw) {
         bool blocked = false;
 #pragma unroll
@@ -122,7 +160,6 @@ __device__ __forceinline__ double interp_one(const GridDev& g, const Stencil& st
             for (int iz = 0; iz < 2; iz++) {
                 const int n = (ix * 2 + iy) * 2 + iz;
                 const double x0 = hx[ix], x1 = hx[2 + ix], y0 = hy[iy], y1 = hy[2 + iy], z0 = hz[iz], z1 = hz[2 + iz];
-                // channels: f, fx, fy, fz | fxy, fxz, fyz, fxyz
                 const double a = x0 * (double)lo[n].x + x1 * (double)lo[n].y;   // f , fx
                 const double b = x0 * (double)lo[n].z + x1 * (double)hi[n].x;   // fy, fxy
                 const double c = x0 * (double)lo[n].w + x1 * (double)hi[n].y;   // fz, fxz
@@ -132,13 +169,22 @@ __device__ __forceinline__ double interp_one(const GridDev& g, const Stencil& st
     return ret;
 }
 
+__device__ __forceinline__ double interp_any(const GridDev& g, const Stencil& st) {
+    switch (g.layout) {
+        case LAYOUT_CELL: return interp_one<LAYOUT_CELL>(g, st);
+        case LAYOUT_QUAD: return interp_one<LAYOUT_QUAD>(g, st);
+        default: return interp_one<LAYOUT_NODE>(g, st);
+    }
+}
+
+template <int LAYOUT>
 __global__ void __launch_bounds__(256) interpolate_kernel(const GridDev g, int64_t n, const double* __restrict__ xyz,
                                                           double* __restrict__ out) {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
         const double p[3] = {xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2]};
         Stencil st;
         make_stencil(g.uc, g.gs, p, st);
-        out[q] = interp_one(g, st);
+        out[q] = interp_one<LAYOUT>(g, st);
     }
 }
 
@@ -192,12 +238,12 @@ __global__ void __launch_bounds__(128) energy_points_kernel(const EnergyPointsPa
             if (P.vdw_present[gi]) {
                 Stencil st;
                 make_stencil(P.vdw[gi].uc, P.vdw[gi].gs, p, st);
-                vdw += interp_one(P.vdw[gi], st);
+                vdw += interp_any(P.vdw[gi], st);
             }
             if (P.has_coulomb) {
                 Stencil st;
                 make_stencil(P.coulomb.uc, P.coulomb.gs, p, st);
-                coul += P.charges[a] * interp_one(P.coulomb, st);
+                coul += P.charges[a] * interp_any(P.coulomb, st);
             }
         }
         P.out_vdw[i] = vdw;

@@ -147,6 +147,11 @@ int ceg_probe_last_stats(ceg_probe_h h, int64_t* n_points, int64_t* pairs_tested
 int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs,
                     const float* grid, int32_t is_vdw, ceg_grid_h* out);
 int ceg_grid_free(ceg_grid_h h);
+/* Device record layout used by subsequent ceg_grid_upload calls: 0 = node records (1x memory),
+ * 1 = (y,z) quads (4x), 2 = whole 8-corner cells (8x, one aligned 256 B block per query),
+ * -1 = automatic (the widest layout that leaves >= 3/4 of the free device memory untouched). */
+int ceg_set_interp_layout(int32_t layout);
+int ceg_grid_layout(ceg_grid_h h, int32_t* layout);
 int ceg_interpolate(ceg_grid_h h, int64_t n, const double* xyz /* n x 3 Cartesian Å */, double* out /* n, K */);
 int ceg_interpolate_dev(ceg_grid_h h, int64_t n, const double* d_xyz, double* d_out, void* stream);
 

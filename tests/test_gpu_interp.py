@@ -35,8 +35,16 @@ def _check(orc, cset, grid, is_vdw, pos, what):
     return blocked.mean()
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["node", "quad", "cell"])
+def layout(request, cuda_lib):
+    """Every device record layout (include/ceg_cuda.h: ceg_set_interp_layout) must give the same answers."""
+    ceg._lib.set_interp_layout(request.param)
+    yield request.param
+    ceg._lib.set_interp_layout(-1)
+
+
 @pytest.mark.parametrize("shape", ["triclinic", "ortho", "rhombo"])
-def test_random_grids(cuda_lib, orc, shape):
+def test_random_grids(cuda_lib, orc, shape, layout):
     mats = {"triclinic": ceg.mat_from_parameters((13.0187, 11.2063, 9.3758), (92.82, 107.2, 103.26)),
             "ortho": np.diag([7.3, 9.1, 5.2]),
             "rhombo": ceg.mat_from_parameters((9.0, 9.0, 9.0), (94.07, 94.07, 94.07))}
@@ -50,11 +58,12 @@ def test_random_grids(cuda_lib, orc, shape):
     _check(orc, cset, grid, False, pos, shape + " coulomb")
 
 
-def test_nodes_edges_and_empty(cuda_lib, orc):
+def test_nodes_edges_and_empty(cuda_lib, orc, layout):
     """Exact nodes (r = 0), the far faces of the bounding box (p1 clamps, grids.jl:218) and n = 0."""
     cset = ceg.GridCoordinatesSetup.from_cell(np.diag([6.0, 5.0, 4.0]), 0.5)
     grid = _random_grid(cset, 9)
     eg = ceg.EnergyGrid(cset, (1, 1, 1), 1e-6, True, grid)
+    assert ceg._lib.grid_layout(eg.handle) == layout
     nx, ny, nz = cset.nodes
     idx = np.array([(i, j, k) for i in (0, 3, nx - 2) for j in (0, 5, ny - 2) for k in (0, 2, nz - 2)])
     pos = np.array([ceg.abc_to_xyz(cset, *t) for t in idx]) + 1e-9   # just inside the cell of node t
