@@ -578,15 +578,11 @@ extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const
     const int64_t npts = (int64_t)nx * ny * nz;
     const size_t node_bytes = sizeof(float) * 8 * (size_t)npts;
     CEG_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    // layout: the widest record whose expansion leaves most of the memory free
+    // layout: node records unless the caller asked otherwise.  Measured on B200 (10^7 random queries,
+    // 218x204x190 grid): NODE 0.70 ms, QUAD 1.42 ms, CELL 1.57 ms — the 4x/8x footprints (1-2 GB) fall
+    // out of TLB reach and of the L2, which costs more than the over-fetch they remove.
     int layout = g_interp_layout.load();
-    if (layout < 0) {
-        size_t free_b = 0, total_b = 0;
-        CEG_CK(cudaMemGetInfo(&free_b, &total_b));
-        layout = LAYOUT_NODE;
-        if (4 * node_bytes + 2 * node_bytes < free_b / 4) layout = LAYOUT_QUAD;
-        if (8 * node_bytes + 2 * node_bytes < free_b / 4) layout = LAYOUT_CELL;
-    }
+    if (layout < 0) layout = LAYOUT_NODE;
     {
         DevBuf tmp, nodes;
         DevBuf& node_dst = (layout == LAYOUT_NODE) ? h->d_nodes : nodes;
