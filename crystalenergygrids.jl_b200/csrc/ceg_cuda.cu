@@ -372,9 +372,9 @@ static void build_ext_list(const ceg_probe_s* h, const double lo[3], const doubl
     }
 }
 
-template <int TX, int TY, int TZ, int NP, bool COUL>
+template <int TX, int TY, int TZ, int NP, bool COUL, bool POLY>
 static cudaError_t launch_tiled(const BuildParams& P, int n_tiles, cudaStream_t s) {
-    grid_build_tiled_kernel<TX, TY, TZ, NP, COUL><<<n_tiles, TX * TY * TZ, 0, s>>>(P);
+    grid_build_tiled_kernel<TX, TY, TZ, NP, COUL, POLY><<<n_tiles, TX * TY * TZ, 0, s>>>(P);
     count_launch();
     return cudaGetLastError();
 }
@@ -382,16 +382,26 @@ static cudaError_t launch_tiled(const BuildParams& P, int n_tiles, cudaStream_t 
 struct TileShape { int tx, ty, tz; };
 static TileShape tile_shape(int n_probes) { return n_probes <= 2 ? TileShape{8, 8, 8} : TileShape{4, 8, 8}; }
 
+template <int NP, bool COUL>
+static cudaError_t dispatch_np(const BuildParams& P, int n_tiles, cudaStream_t s) {
+    constexpr int TX = NP <= 2 ? 8 : 4;
+    if (COUL && P.poly_erfcx) return launch_tiled<TX, 8, 8, NP, COUL, true>(P, n_tiles, s);
+    return launch_tiled<TX, 8, 8, NP, COUL, false>(P, n_tiles, s);
+}
+
 static cudaError_t dispatch_tiled(int np, bool coul, const BuildParams& P, int n_tiles, cudaStream_t s) {
-#define CASE(NP_, C_)                                                                   \
-    if (np == NP_ && coul == C_) {                                                      \
-        if (NP_ <= 2) return launch_tiled<8, 8, 8, NP_, C_>(P, n_tiles, s);             \
-        return launch_tiled<4, 8, 8, NP_, C_>(P, n_tiles, s);                           \
+    switch (np * 2 + (coul ? 1 : 0)) {
+        case 1: return dispatch_np<0, true>(P, n_tiles, s);
+        case 2: return dispatch_np<1, false>(P, n_tiles, s);
+        case 3: return dispatch_np<1, true>(P, n_tiles, s);
+        case 4: return dispatch_np<2, false>(P, n_tiles, s);
+        case 5: return dispatch_np<2, true>(P, n_tiles, s);
+        case 6: return dispatch_np<3, false>(P, n_tiles, s);
+        case 7: return dispatch_np<3, true>(P, n_tiles, s);
+        case 8: return dispatch_np<4, false>(P, n_tiles, s);
+        case 9: return dispatch_np<4, true>(P, n_tiles, s);
+        default: return cudaErrorInvalidValue;
     }
-    CASE(0, true) CASE(1, false) CASE(1, true) CASE(2, false) CASE(2, true)
-    CASE(3, false) CASE(3, true) CASE(4, false) CASE(4, true)
-#undef CASE
-    return cudaErrorInvalidValue;
 }
 
 // Fill BuildParams and make sure the image list for slab [i0,i1) is resident.

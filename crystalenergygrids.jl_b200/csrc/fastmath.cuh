@@ -28,9 +28,9 @@ __device__ __forceinline__ double rcp_fast(double d) {
     return fma(y, fma(e, e, e), y);                 // y (1 + e + e^2)
 }
 
-// exp(x) for -700 <= x <= 0 (clamped below): 2^n * p(f), n = rint(x log2 e), f = x - n ln2.
+// exp(x) for x <= 0: 2^n * p(f), n = rint(x log2 e), f = x - n ln2.  n is clamped at -1021 on the
+// integer pipe, so arguments below -707 return ~2^-1021 (the true value underflows) instead of wrapping.
 __device__ __forceinline__ double exp_neg_fast(double x) {
-    x = fmax(x, -700.0);
     const double MAGIC = 6755399441055744.0;        // 1.5 * 2^52: low word of (t) holds n
     const double t = fma(x, 1.4426950408889634, MAGIC);
     const double n = t - MAGIC;
@@ -39,8 +39,8 @@ __device__ __forceinline__ double exp_neg_fast(double x) {
     double p = c_exp[EXP_DEG];
 #pragma unroll
     for (int k = EXP_DEG - 1; k >= 0; k--) p = fma(p, f, c_exp[k]);
-    const int hi = __double2hiint(p) + (__double2loint(t) << 20);
-    return __hiloint2double(hi, __double2loint(p));
+    const int ni = max(__double2loint(t), -1021);
+    return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
 }
 
 // erfcx(x) = exp(x^2) erfc(x) for 0 <= x <= ERFCX_XMAX.

@@ -99,47 +99,60 @@ __device__ __forceinline__ PairGeom make_geom(double r2) {
     return g;
 }
 
+// Lennard-Jones terms (interactions.jl:434-441), no branches
+__device__ __forceinline__ void lj_terms(const PairDev& p, const PairGeom& g, double& v, double& p1, double& p2,
+                                         double& p3) {
+    const double t = p.lj_sig2 * g.ir2;
+    const double x6 = t * t * t;
+    const double ir4 = g.ir2 * g.ir2;
+    const double ex6 = p.lj_eps * x6;
+    v = fma(4.0 * ex6, x6 - 1.0, -p.lj_shift);
+    p1 = 24.0 * (ex6 * fma(-2.0, x6, 1.0)) * g.ir2;
+    p2 = 96.0 * (ex6 * fma(7.0, x6, -2.0)) * ir4;
+    p3 = 384.0 * (ex6 * fma(-28.0, x6, 5.0)) * (ir4 * ir4);
+}
+
+// Buckingham terms (interactions.jl:447-457), no branches
+__device__ __forceinline__ void buck_terms(const PairDev& p, const PairGeom& g, double& v, double& p1, double& p2,
+                                           double& p3) {
+    const double B = p.bB;
+    const double ir4 = g.ir2 * g.ir2;
+    const double ir6 = ir4 * g.ir2;
+    const double x6 = p.bC * ir6;
+    const double Br = B * g.r;
+    const double xe = p.bA * exp_neg_fast(-Br);
+    const double Bxe = B * xe;
+    const double ir3 = g.ir2 * g.ir;
+    const double x6ir2 = x6 * g.ir2;
+    v = (xe - x6) - p.b_shift;
+    p1 = fma(6.0, x6ir2, -(Bxe * g.ir));
+    p2 = fma(fma(Bxe, Br, Bxe), ir3, -48.0 * (x6ir2 * g.ir2));
+    p3 = fma(-(fma(Br, Br + 3.0, 3.0) * Bxe), ir3 * g.ir2, 480.0 * (x6 * ir6));
+}
+
 __device__ __forceinline__ void vdw_pair_fast(const PairDev& p, const PairGeom& g, double& v, double& p1, double& p2,
                                               double& p3) {
     v = 0.0; p1 = 0.0; p2 = 0.0; p3 = 0.0;
     const int fl = p.flags;
     // hard sphere: the fast path only sees r2 >= fast_lo > every hs_r2, where the term is exactly 0
-    if (fl & CEG_PAIR_LJ) {
-        const double eps = p.lj_eps;
-        const double t = p.lj_sig2 * g.ir2;
-        const double x6 = t * t * t;
-        const double ir4 = g.ir2 * g.ir2;
-        const double ex6 = eps * x6;
-        v += fma(4.0 * ex6, x6 - 1.0, -p.lj_shift);
-        p1 += 24.0 * (ex6 * fma(-2.0, x6, 1.0)) * g.ir2;
-        p2 += 96.0 * (ex6 * fma(7.0, x6, -2.0)) * ir4;
-        p3 += 384.0 * (ex6 * fma(-28.0, x6, 5.0)) * (ir4 * ir4);
-    }
+    if (fl & CEG_PAIR_LJ) lj_terms(p, g, v, p1, p2, p3);
     if (fl & CEG_PAIR_BUCK) {
-        const double B = p.bB;
-        const double ir4 = g.ir2 * g.ir2;
-        const double ir6 = ir4 * g.ir2;
-        const double x6 = p.bC * ir6;
-        const double Br = B * g.r;
-        const double xe = p.bA * exp_neg_fast(-Br);
-        const double Bxe = B * xe;
-        const double ir3 = g.ir2 * g.ir;
-        const double x6ir2 = x6 * g.ir2;
-        v += (xe - x6) - p.b_shift;
-        p1 += fma(6.0, x6ir2, -(Bxe * g.ir));
-        p2 += fma(fma(Bxe, Br, Bxe), ir3, -48.0 * (x6ir2 * g.ir2));
-        p3 += fma(-(fma(Br, Br + 3.0, 3.0) * Bxe), ir3 * g.ir2, 480.0 * (x6 * ir6));
+        double bv, b1, b2, b3;
+        buck_terms(p, g, bv, b1, b2, b3);
+        v += bv; p1 += b1; p2 += b2; p3 += b3;
     }
 }
 
+// ewald.jl:299-312 with erfc(x) = exp(-x^2) erfcx(x): one exp serves both terms.  POLY: alpha*cutoff lies
+// inside the fitted range of erfcx_fast (the default Ewald precision), else the library erfcx.
+template <bool POLY>
 __device__ __forceinline__ void ewald_pair_fast(double alpha, double two_alpha_over_sqrtpi, double q,
-                                                const PairGeom& g, bool poly_erfcx, double& v, double& p1,
-                                                double& p2, double& p3) {
+                                                const PairGeom& g, double& v, double& p1, double& p2, double& p3) {
     const double ar = alpha * g.r;
     const double a2 = ar * ar;                    // r2 * alpha^2
     const double E = exp_neg_fast(-a2);
     const double e2 = (two_alpha_over_sqrtpi * g.r) * E;
-    const double c = E * (poly_erfcx ? erfcx_fast(ar) : erfcx(ar));
+    const double c = E * (POLY ? erfcx_fast(ar) : erfcx(ar));
     const double qir = q * g.ir;
     const double qir3 = qir * g.ir2, qir5 = qir3 * g.ir2, qir7 = qir5 * g.ir2;
     v = qir * c;
@@ -262,7 +275,7 @@ struct BuildParams {
     unsigned long long* stats; // [0] pairs tested, [1] pairs in cutoff
 };
 
-template <int TX, int TY, int TZ, int NP, bool COUL>
+template <int TX, int TY, int TZ, int NP, bool COUL, bool POLY>
 __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const BuildParams P) {
     constexpr int NT = TX * TY * TZ;
     constexpr int NW = NT / 32;
@@ -304,7 +317,6 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
         for (int c = 0; c < 8; c++) acc[g][c] = 0.0;
     double smallest = CUDART_INF;
     const double taosp = 2.0 * P.alpha / sqrt(CUDART_PI);
-    const bool poly_erfcx = P.poly_erfcx != 0;
     unsigned int n_tested = 0, n_in = 0;
     int count = 0;
     __syncthreads();
@@ -323,19 +335,46 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
                     n_in++;
                     const PairGeom geo = make_geom(d2);
                     const double dxy = dx * dy, dxz = dx * dz, dyz = dy * dz;
-#pragma unroll
-                    for (int g = 0; g < NP; g++) {
-                        const PairDev& pr = table_in_smem ? s_table[g * P.n_types + ty_] : P.table[g * P.n_types + ty_];
-                        if (pr.flags != 0) {
-                            double v, p1, p2, p3;
+                    if (NP == 1 && COUL) {
+                        // one straight-line block per interaction class, so that the independent exp / erfcx /
+                        // algebra chains of the VdW and Ewald terms are scheduled against each other
+                        const PairDev& pr = table_in_smem ? s_table[ty_] : P.table[ty_];
+                        const int fl = pr.flags & ~CEG_PAIR_HS;   // hard spheres contribute exactly 0 here
+                        double v, p1, p2, p3, ev, e1, e2, e3;
+                        if (fl == CEG_PAIR_BUCK) {
+                            buck_terms(pr, geo, v, p1, p2, p3);
+                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, ev, e1, e2, e3);
+                            accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                            accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
+                        } else if (fl == CEG_PAIR_LJ) {
+                            lj_terms(pr, geo, v, p1, p2, p3);
+                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, ev, e1, e2, e3);
+                            accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                            accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
+                        } else if (fl == 0) {
+                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, ev, e1, e2, e3);
+                            accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
+                        } else {
                             vdw_pair_fast(pr, geo, v, p1, p2, p3);
-                            accumulate(acc[g], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, ev, e1, e2, e3);
+                            accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                            accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         }
-                    }
-                    if (COUL) {   // d2 >= fast_lo > 1 Å^2 here: `smallest` (probes.jl:108) is tracked on the literal path
-                        double v, p1, p2, p3;
-                        ewald_pair_fast(P.alpha, taosp, a.q, geo, poly_erfcx, v, p1, p2, p3);
-                        accumulate(acc[NG - 1], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < NP; g++) {
+                            const PairDev& pr = table_in_smem ? s_table[g * P.n_types + ty_] : P.table[g * P.n_types + ty_];
+                            if (pr.flags != 0) {
+                                double v, p1, p2, p3;
+                                vdw_pair_fast(pr, geo, v, p1, p2, p3);
+                                accumulate(acc[g], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                            }
+                        }
+                        if (COUL) {   // d2 >= fast_lo > 1 Å^2 here: `smallest` (probes.jl:108) is tracked on the literal path
+                            double v, p1, p2, p3;
+                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, v, p1, p2, p3);
+                            accumulate(acc[NG - 1], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
+                        }
                     }
                 } else {
                     // ---- literal re-evaluation from the original atom (mask thresholds, r -> 0, image search)
