@@ -37,13 +37,8 @@ def env_rank():
 
 
 def slabs(n, parts):
-    base, rem = divmod(n, parts)
-    out, s = [], 0
-    for p in range(parts):
-        e = s + base + (1 if p < rem else 0)
-        out.append((s, e))
-        s = e
-    return out
+    from ceg_b200.sharding import split_range
+    return split_range(n, parts)
 
 
 class ClockSampler:

@@ -255,22 +255,35 @@ extern "C" int ceg_probe_create(int32_t device, const ceg_cell_t* supercell, int
     h->alpha = alpha;
     h->n_probes = n_probes;
     h->want_coulomb = want_coulomb ? 1 : 0;
-    h->n_types = n_types;
     h->n_atoms = n_atoms;
     h->h_xyz.assign(xyz, xyz + 3 * n_atoms);
-    h->h_type.assign(type, type + n_atoms);
     if (want_coulomb) h->h_q.assign(charge, charge + n_atoms); else h->h_q.assign(n_atoms, 0.0);
     h->min_perp_width = perp_width_min(supercell->mat);
-    std::vector<PairDev> tab((size_t)std::max(1, n_probes * n_types));
-    for (int i = 0; i < n_probes * n_types; i++) {
-        const ceg_pair_t& s = table[i];
-        PairDev& d = tab[i];
-        d.flags = s.flags; d._pad = 0;
-        d.hs_r2 = s.hs_r * s.hs_r;
-        d.lj_eps = s.lj_eps; d.lj_sig2 = s.lj_sigma * s.lj_sigma; d.lj_shift = s.lj_shift;
-        d.bA = s.buck_A; d.bB = s.buck_B; d.bC = s.buck_C; d.b_shift = s.buck_shift;
-        if (s.flags & CEG_PAIR_HS) h->max_hs_r2 = std::max(h->max_hs_r2, d.hs_r2);
+    // dense re-indexing of the species actually present in the framework: the kernels stage the
+    // (probe x present species) pair table in shared memory
+    std::vector<int> dense(std::max(1, n_types), -1), present;
+    h->h_type.assign(n_atoms, 0);
+    for (int64_t i = 0; i < n_atoms; i++) {
+        const int t = n_probes > 0 ? type[i] : 0;
+        if (dense[t] < 0) { dense[t] = (int)present.size(); present.push_back(t); }
+        h->h_type[i] = dense[t];
     }
+    const int n_present = std::max<int>(1, (int)present.size());
+    if (n_probes > 0 && n_present > TABLE_SMEM_TYPES)
+        return fail("ceg_probe_create: more than 24 distinct framework species in one probe system");
+    h->n_types = n_present;
+    std::vector<PairDev> tab((size_t)std::max(1, n_probes * n_present));
+    memset(tab.data(), 0, sizeof(PairDev) * tab.size());
+    for (int p = 0; p < n_probes; p++)
+        for (int j = 0; j < (int)present.size(); j++) {
+            const ceg_pair_t& s = table[(size_t)p * n_types + present[j]];
+            PairDev& d = tab[(size_t)p * n_present + j];
+            d.flags = s.flags; d._pad = 0;
+            d.hs_r2 = s.hs_r * s.hs_r;
+            d.lj_eps = s.lj_eps; d.lj_sig2 = s.lj_sigma * s.lj_sigma; d.lj_shift = s.lj_shift;
+            d.bA = s.buck_A; d.bB = s.buck_B; d.bC = s.buck_C; d.b_shift = s.buck_shift;
+            if (s.flags & CEG_PAIR_HS) h->max_hs_r2 = std::max(h->max_hs_r2, d.hs_r2);
+        }
     CEG_CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     CEG_CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * std::max<int64_t>(1, n_atoms)));

@@ -282,15 +282,14 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
     constexpr int NG = NP + (COUL ? 1 : 0);
     __shared__ ExtAtom s_atom[LIST_CAP];
     __shared__ ExtMeta s_meta[LIST_CAP];
-    __shared__ PairDev s_table[NP > 0 ? NP * TABLE_SMEM_TYPES : 1];   // small tables staged; larger read from global
+    __shared__ PairDev s_table[NP > 0 ? NP * TABLE_SMEM_TYPES : 1];   // (probe x present species), <= 24 species
     __shared__ CellDev s_cell;
     __shared__ int s_wcount[NW];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const bool table_in_smem = (P.n_types <= TABLE_SMEM_TYPES);
     if (tid == 0) s_cell = P.cell;
-    if (NP > 0 && table_in_smem)
+    if (NP > 0)
         for (int i = tid; i < NP * P.n_types; i += NT) s_table[i] = P.table[i];
 
     // tile -> node indices
@@ -338,7 +337,7 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
                     if (NP == 1 && COUL) {
                         // one straight-line block per interaction class, so that the independent exp / erfcx /
                         // algebra chains of the VdW and Ewald terms are scheduled against each other
-                        const PairDev& pr = table_in_smem ? s_table[ty_] : P.table[ty_];
+                        const PairDev& pr = s_table[ty_];
                         const int fl = pr.flags & ~CEG_PAIR_HS;   // hard spheres contribute exactly 0 here
                         double v, p1, p2, p3, ev, e1, e2, e3;
                         if (fl == CEG_PAIR_BUCK) {
@@ -363,7 +362,7 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
                     } else {
 #pragma unroll
                         for (int g = 0; g < NP; g++) {
-                            const PairDev& pr = table_in_smem ? s_table[g * P.n_types + ty_] : P.table[g * P.n_types + ty_];
+                            const PairDev& pr = s_table[g * P.n_types + ty_];
                             if (pr.flags != 0) {
                                 double v, p1, p2, p3;
                                 vdw_pair_fast(pr, geo, v, p1, p2, p3);
@@ -389,7 +388,7 @@ __global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const Buil
                     const double bxy = b[0] * b[1], bxz = b[0] * b[2], byz = b[1] * b[2];
 #pragma unroll
                     for (int g = 0; g < NP; g++) {
-                        const PairDev& pr = table_in_smem ? s_table[g * P.n_types + ty_] : P.table[g * P.n_types + ty_];
+                        const PairDev& pr = s_table[g * P.n_types + ty_];
                         if (pr.flags != 0) {
                             double v, p1, p2, p3;
                             vdw_pair_ref(pr, d2x, v, p1, p2, p3);

@@ -1,0 +1,226 @@
+# CEGCuda.jl — the reference-side binding of libceg_cuda (include/ceg_cuda.h).
+#
+# Drop this file next to CrystalEnergyGrids.jl's src/ and `include("CEGCuda.jl")` at the end of
+# src/CrystalEnergyGrids.jl (after grids.jl, probes.jl and ewald.jl).  It re-defines, with identical
+# signatures, the entry points of the hot path so that their inner loops run on the GPU:
+#
+#   create_grid_vdw        grids.jl:137-157      -> ceg_probe_create + ceg_grid_build
+#   create_grid_coulomb    grids.jl:159-185      -> ceg_probe_create + ceg_grid_build
+#   interpolate_grid       grids.jl:212-273      -> ceg_grid_upload (once per grid) + ceg_interpolate
+#   energy_point/energy_grid  grids.jl:311-424   -> ceg_energy_points
+#   initialize_ewald (S_f) ewald.jl:264-271      -> ceg_ewald_create
+#   compute_ewald(ctx)     ewald.jl:555-577      -> ceg_ewald_reciprocal
+#
+# Everything else (force-field parsing, CIF loading, .grid headers, caches, Monte-Carlo) is
+# untouched Julia.  Units are stripped to Å / K / e before each `ccall`; every physical constant is
+# passed as an argument, so the Unitful version in use keeps deciding GRID_TO_KELVIN and
+# COULOMBIC_CONVERSION_FACTOR.
+#
+# NOTE: Julia is not installed in the build image of this repository, so this file has not been
+# executed there; the same C ABI is exercised through the ctypes mirror
+# (crystalenergygrids.jl_b200/_lib.py) by the GPU test-suite.
+
+module CEGCuda
+
+using ..CrystalEnergyGrids
+using ..CrystalEnergyGrids: ForceField, InteractionRule, InteractionRuleSum, FF, ProbeSystem, EnergyGrid,
+    GridCoordinatesSetup, EwaldFramework, EwaldContext, CellMatrix, BlockFile, CrystalEnergySetup,
+    prepare_periodic_distance_computations, find_supercell, initialize_ewald, _setup_grid_common,
+    _create_grid_common, GRID_TO_KELVIN, COULOMBIC_CONVERSION_FACTOR, TÅ
+using StaticArrays, Unitful, UnitfulAtomic
+
+const libceg = get(ENV, "LIBCEG_CUDA", "libceg_cuda.so")
+
+# ---- C structs (include/ceg_cuda.h) -----------------------------------------------------------------
+struct CegCell
+    mat::NTuple{9,Cdouble}
+    invmat::NTuple{9,Cdouble}
+    ortho::Int32
+    _pad::Int32
+    safemin2::Cdouble
+end
+struct CegGridSpec
+    dims::NTuple{3,Int32}
+    _pad::Int32
+    size::NTuple{3,Cdouble}
+    shift::NTuple{3,Cdouble}
+    delta::NTuple{3,Cdouble}
+end
+struct CegPair
+    flags::Int32
+    _pad::Int32
+    hs_r::Cdouble
+    lj_eps::Cdouble; lj_sigma::Cdouble; lj_shift::Cdouble
+    buck_A::Cdouble; buck_B::Cdouble; buck_C::Cdouble; buck_shift::Cdouble
+end
+
+const PAIR_HS, PAIR_LJ, PAIR_BUCK = Int32(1), Int32(2), Int32(4)
+
+ceg_error() = unsafe_string(ccall((:ceg_last_error, libceg), Cstring, ()))
+check(rc::Cint) = rc == 0 ? nothing : error(ceg_error())   # same failure mode as the reference: `error(...)`
+
+function CegCell(mat::SMatrix{3,3,Float64,9}, invmat::SMatrix{3,3,Float64,9})
+    _, ortho, safemin = prepare_periodic_distance_computations(mat)          # utils.jl:146-155
+    CegCell(Tuple(mat), Tuple(invmat), Int32(ortho), Int32(0), safemin^2)
+end
+function CegGridSpec(cs::GridCoordinatesSetup)
+    å(x) = Tuple(Float64.(ustrip.(u"Å", x)))
+    CegGridSpec(Tuple(Int32.(cs.dims)), Int32(0), å(cs.size), å(cs.shift), å(cs.Δ))
+end
+
+# derivativesGrid's view of one ForceField entry (interactions.jl:432-472, 599-610)
+function CegPair(rule::Union{InteractionRule,InteractionRuleSum})
+    flags = Int32(0); hs = 0.0; lj = (0.0, 0.0, 0.0); bk = (0.0, 0.0, 0.0, 0.0)
+    for r in (rule isa InteractionRule ? (rule,) : rule.rules)
+        k = r.kind
+        if k === FF.NoInteraction || k === FF.CoulombEwaldDirect
+            continue
+        elseif k === FF.HardSphere
+            flags |= PAIR_HS; hs = r.params[1] + r.params[2]
+        elseif k === FF.LennardJones
+            flags |= PAIR_LJ; lj = (r.params[1], r.params[2], r.shift)
+        elseif k === FF.Buckingham
+            flags |= PAIR_BUCK; bk = (r.params[1], r.params[2], r.params[3], r.shift)
+        elseif k === FF.UndefinedInteraction
+            flags = Int32(-1)
+        else
+            error("VdW grid not implemented for $(k)")                        # interactions.jl:442,462-465
+        end
+    end
+    CegPair(flags, 0, hs, lj..., bk...)
+end
+
+# ---- grid construction ---------------------------------------------------------------------------------
+mutable struct ProbeHandle
+    ptr::Ptr{Cvoid}
+    function ProbeHandle(s::ProbeSystem, probes::Vector{Int}, coulomb::Bool, α::Float64; device=0)
+        ff = s.forcefield
+        ntypes = length(ff.sdict)
+        table = [CegPair(ff.interactions[t, p]) for p in probes for t in 1:ntypes]   # row p, column t
+        cell = CegCell(s.mat, s.invmat)
+        xyz = reinterpret(Float64, s.positions)                                      # n x 3, row-major
+        types = Int32.(s.atomkinds .- 1)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve xyz types table begin
+            check(ccall((:ceg_probe_create, libceg), Cint,
+                (Int32, Ref{CegCell}, Int64, Ptr{Cdouble}, Ptr{Int32}, Ptr{Cdouble}, Int32, Int32, Ptr{CegPair},
+                 Cdouble, Int32, Cdouble, Ref{Ptr{Cvoid}}),
+                device, cell, length(s.positions), xyz, types, coulomb ? s.charges : C_NULL, ntypes,
+                length(probes), table, ustrip(u"Å^2", ff.cutoff^2), coulomb, α, out))
+        end
+        h = new(out[])
+        finalizer(x -> ccall((:ceg_probe_free, libceg), Cint, (Ptr{Cvoid},), x.ptr), h)
+    end
+end
+
+function _build!(grids::Vector{Array{Cfloat,4}}, h::ProbeHandle, cset::GridCoordinatesSetup;
+                 xrange=0:Int(cset.dims[1]))
+    λv = inv(GRID_TO_KELVIN); Tv = GRID_TO_KELVIN * 1e7                                # grids.jl:142-148
+    λc = ustrip(u"K*Å/e_au^2", COULOMBIC_CONVERSION_FACTOR) / GRID_TO_KELVIN; Tc = inv(λc) * 1e7   # :169-170
+    ptrs = [pointer(g) for g in grids]
+    GC.@preserve grids begin
+        check(ccall((:ceg_grid_build, libceg), Cint,
+            (Ptr{Cvoid}, Ref{CegGridSpec}, Int32, Int32, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Ptr{Cfloat}}, Ptr{Cdouble}),
+            h.ptr, CegGridSpec(cset), first(xrange), last(xrange) + 1, λv, Tv, λc, Tc, ptrs, C_NULL))
+    end
+    grids
+end
+
+# grids.jl:137-157 — same signature, same file layout, same return value
+function CrystalEnergyGrids.create_grid_vdw(file, framework, forcefield::ForceField, spacing::TÅ, atom::Symbol)
+    cset, num_unitcell = _setup_grid_common(framework, spacing, forcefield.cutoff)
+    grid = Array{Cfloat,4}(undef, cset.dims[3]+1, cset.dims[2]+1, cset.dims[1]+1, 8)
+    probe = ProbeSystem(framework, forcefield, atom)
+    _build!([grid], ProbeHandle(probe, [probe.probe], false, 0.0), cset)
+    open(file, "w") do f
+        _create_grid_common(f, cset, num_unitcell)
+        write(f, grid)
+        write(f, NoUnits.(cset.cell.mat ./ u"Å"))
+    end
+    grid
+end
+
+# grids.jl:159-185
+function CrystalEnergyGrids.create_grid_coulomb(file, framework, forcefield::ForceField, spacing::TÅ, _ewald=nothing)
+    cset, num_unitcell = _setup_grid_common(framework, spacing, 12.0u"Å")
+    ewald = _ewald isa EwaldFramework ? _ewald : initialize_ewald(framework, num_unitcell)
+    grid = Array{Cfloat,4}(undef, cset.dims[3]+1, cset.dims[2]+1, cset.dims[1]+1, 8)
+    probe = ProbeSystem(framework, forcefield)
+    _build!([grid], ProbeHandle(probe, Int[], true, ustrip(u"Å^-1", ewald.α)), cset)
+    open(file, "w") do f
+        _create_grid_common(f, cset, num_unitcell)
+        write(f, ewald.precision)
+        write(f, grid)
+        write(f, NoUnits.(cset.cell.mat ./ u"Å"))
+    end
+    grid
+end
+
+# New: all VdW probes of a molecule and the Coulomb grid in ONE pass over the framework atoms
+# (what retrieve_or_create_grid's callers, raspa.jl:499-516, loop over one grid at a time).
+function create_grids_fused(framework, forcefield::ForceField, spacing::TÅ, atoms::Vector{Symbol}, ewald::Union{Nothing,EwaldFramework})
+    cset, _ = _setup_grid_common(framework, spacing, forcefield.cutoff)
+    probe = ProbeSystem(framework, forcefield)                                   # positions/charges/kinds
+    idx = [forcefield.sdict[Symbol(CrystalEnergyGrids.get_atom_name(a))] for a in atoms]
+    n = length(idx) + !(ewald isa Nothing)
+    grids = [Array{Cfloat,4}(undef, cset.dims[3]+1, cset.dims[2]+1, cset.dims[1]+1, 8) for _ in 1:n]
+    α = ewald isa Nothing ? 0.0 : ustrip(u"Å^-1", ewald.α)
+    _build!(grids, ProbeHandle(probe, idx, !(ewald isa Nothing), α), cset)
+end
+
+# ---- interpolation -----------------------------------------------------------------------------------------
+const GRID_HANDLES = IdDict{Array{Cfloat,4},Ptr{Cvoid}}()      # device copy per EnergyGrid.grid
+const GRID_LOCK = ReentrantLock()
+
+function handle(g::EnergyGrid; device=0)
+    lock(GRID_LOCK) do
+        get!(GRID_HANDLES, g.grid) do
+            cell = CegCell(SMatrix{3,3,Float64,9}(ustrip.(u"Å", g.csetup.cell.mat)),
+                           SMatrix{3,3,Float64,9}(ustrip.(u"Å^-1", g.csetup.cell.invmat)))
+            out = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:ceg_grid_upload, libceg), Cint,
+                (Int32, Ref{CegCell}, Ref{CegGridSpec}, Ptr{Cfloat}, Int32, Ref{Ptr{Cvoid}}),
+                device, cell, CegGridSpec(g.csetup), g.grid, g.ewald_precision == Inf, out))
+            out[]
+        end
+    end
+end
+
+# batched method of interpolate_grid (grids.jl:212-273): points is 3 x n (Å); returns K, 1e100 = blocked
+function CrystalEnergyGrids.interpolate_grid(g::EnergyGrid, points::AbstractMatrix{Float64})
+    g.ewald_precision === -Inf32 && return zeros(size(points, 2))
+    isnan(g.ewald_precision) && error("Invalid grid cannot be interpolated!")
+    out = Vector{Float64}(undef, size(points, 2))
+    check(ccall((:ceg_interpolate, libceg), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
+                handle(g), size(points, 2), points, out))
+    out
+end
+
+# ---- Ewald ---------------------------------------------------------------------------------------------------
+# S_f(k) of initialize_ewald (ewald.jl:264-271): call with the k-list/kfactors computed by the Julia code.
+function structure_factor(invmat::SMatrix{3,3,Float64,9}, ks::NTuple{3,Int}, kindices, kfactors::Vector{Float64},
+                          frac::Matrix{Float64}, charges::Vector{Float64}; device=0)
+    kvec = Int32[]
+    for (jy, jz, jxrange, _) in kindices, ix in jxrange
+        append!(kvec, (ix, jy, jz))
+    end
+    S = Matrix{Float64}(undef, 2, length(kfactors))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ceg_ewald_create, libceg), Cint,
+        (Int32, Ptr{Cdouble}, Ptr{Int32}, Int64, Ptr{Int32}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble},
+         Ref{Ptr{Cvoid}}, Ptr{Cdouble}),
+        device, collect(invmat), Int32[ks...], length(kfactors), kvec, kfactors, length(charges), frac, charges, out, S))
+    out[], reinterpret(ComplexF64, vec(S))
+end
+
+# compute_ewald(ctx) for many placements of the context's molecule (ewald.jl:350-364, 555-577)
+function reciprocal(h::Ptr{Cvoid}, positions::Array{Float64,3}, q::Vector{Float64}, energy_net_charges, static_contribution)
+    n_atoms, n_pos = size(positions, 2), size(positions, 3)
+    out = Vector{Float64}(undef, n_pos)
+    check(ccall((:ceg_ewald_reciprocal, libceg), Cint,
+        (Ptr{Cvoid}, Int64, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}),
+        h, n_pos, n_atoms, positions, q, ustrip(u"K", energy_net_charges), ustrip(u"K", static_contribution), out))
+    out
+end
+
+end # module
