@@ -127,7 +127,9 @@ def run_product(args):
     torch.cuda.set_device(local_rank)
     dev = local_rank
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         torch.cuda.synchronize()
@@ -297,6 +299,7 @@ def run_product(args):
         cpu, cpu_i = cpu_baseline(inp, cset4, cset1, gK, budget_s=args.cpu_budget)
 
     total_launches = ceg._lib.kernel_launch_count() - launches0
+    d2h_total = sum_over_ranks(d2h_bytes)          # collective: every rank calls it
     if rank == 0:
         line = {
             "metric": "grid points/sec (LJ+Ewald FP64)",
@@ -308,7 +311,7 @@ def run_product(args):
                        "l2": "no L2 flush: inputs (<1 MB image list) are re-read by every tile by design; each step "
                              "writes 1.8 GB of output (> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(sum_over_ranks(d2h_bytes)) if world > 1 else int(d2h_bytes),
+                    "d2h_bytes_per_step": int(d2h_total),
                     "ms_per_step": e2e_ms, "note": "ceg_probe_create + ceg_grid_build into pinned host arrays + free"},
             "roofline": {"bound": "fp64", "achieved": my_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": my_tflops / fp64_peak if fp64_peak else None, "traffic": None,
