@@ -341,7 +341,7 @@ def run_product(args):
             "gpu_launches_total": int(total_launches),
             "device": ceg._lib.device_info(dev),
         }
-        print(json.dumps(line))
+        emit(line)
     eg_v.close()
     eg_c.close()
     if world > 1:
@@ -424,10 +424,24 @@ def run_reference(args):
             "e2e": {"value": value, "unit": "grid points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = CrystalEnergyGrids.jl CPU algorithm restated in C/OpenMP (oracle/ceg_oracle.c); "
                     "Julia is not installed in this image"}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was
+    redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -385,21 +385,35 @@ static void build_ext_list(const ceg_probe_s* h, const double lo[3], const doubl
     }
 }
 
-template <int TX, int TY, int TZ, int NP, bool COUL, bool POLY>
+template <int NT, int NP, bool COUL, bool POLY>
 static cudaError_t launch_tiled(const BuildParams& P, int n_tiles, cudaStream_t s) {
-    grid_build_tiled_kernel<TX, TY, TZ, NP, COUL, POLY><<<n_tiles, TX * TY * TZ, 0, s>>>(P);
+    grid_build_tiled_kernel<NT, NP, COUL, POLY><<<n_tiles, NT, 0, s>>>(P);
     count_launch();
     return cudaGetLastError();
 }
 
+// Tile shapes.  The main shape is the most compact one (best pruning radius); a slab whose plane count
+// is not a multiple of its x extent finishes with flatter shapes of the same thread count (x extent 4, 2,
+// 1), so that no CTA carries idle planes and x-slabs of any size stay balanced across GPUs.
 struct TileShape { int tx, ty, tz; };
-static TileShape tile_shape(int n_probes) { return n_probes <= 2 ? TileShape{8, 8, 8} : TileShape{4, 8, 8}; }
+static int threads_per_tile(int n_probes) { return n_probes <= 2 ? 512 : 256; }
+static TileShape tile_shape_for(int n_probes, int tx) {
+    if (n_probes <= 2) {
+        switch (tx) { case 8: return {8, 8, 8}; case 4: return {4, 8, 16}; case 2: return {2, 16, 16}; default: return {1, 16, 32}; }
+    }
+    switch (tx) { case 4: return {4, 8, 8}; case 2: return {2, 8, 16}; default: return {1, 16, 16}; }
+}
+static int main_tx(int n_probes) { return n_probes <= 2 ? 8 : 4; }
+static double tile_radius(const TileShape& t, const double* delta) {
+    const double hx = 0.5 * (t.tx - 1) * delta[0], hy = 0.5 * (t.ty - 1) * delta[1], hz = 0.5 * (t.tz - 1) * delta[2];
+    return std::sqrt(hx * hx + hy * hy + hz * hz);
+}
 
 template <int NP, bool COUL>
 static cudaError_t dispatch_np(const BuildParams& P, int n_tiles, cudaStream_t s) {
-    constexpr int TX = NP <= 2 ? 8 : 4;
-    if (COUL && P.poly_erfcx) return launch_tiled<TX, 8, 8, NP, COUL, true>(P, n_tiles, s);
-    return launch_tiled<TX, 8, 8, NP, COUL, false>(P, n_tiles, s);
+    constexpr int NT = NP <= 2 ? 512 : 256;
+    if (COUL && P.poly_erfcx) return launch_tiled<NT, NP, COUL, true>(P, n_tiles, s);
+    return launch_tiled<NT, NP, COUL, false>(P, n_tiles, s);
 }
 
 static cudaError_t dispatch_tiled(int np, bool coul, const BuildParams& P, int n_tiles, cudaStream_t s) {
@@ -415,6 +429,28 @@ static cudaError_t dispatch_tiled(int np, bool coul, const BuildParams& P, int n
         case 9: return dispatch_np<4, true>(P, n_tiles, s);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// Launch the planes [a, b) of the slab described by P: full rows of the main shape, then the tail.
+static cudaError_t launch_planes(const ceg_probe_s* h, BuildParams P, const ceg_gridspec_t* gs, double cutoff, int a, int b,
+                                 cudaStream_t s) {
+    int tx = main_tx(h->n_probes);
+    while (a < b) {
+        while (tx > b - a) tx >>= 1;
+        const int rows = (b - a) / tx;
+        const TileShape t = tile_shape_for(h->n_probes, tx);
+        const double reach = cutoff + tile_radius(t, gs->delta) + 1e-6;
+        P.reach2 = reach * reach;
+        P.tile[0] = t.tx; P.tile[1] = t.ty; P.tile[2] = t.tz;
+        P.a0 = a; P.a1 = a + rows * tx;
+        P.tiles_x = rows;
+        P.tiles_y = (gs->dims[1] + 1 + t.ty - 1) / t.ty;
+        P.tiles_z = (gs->dims[2] + 1 + t.tz - 1) / t.tz;
+        cudaError_t e = dispatch_tiled(h->n_probes, h->want_coulomb != 0, P, P.tiles_x * P.tiles_y * P.tiles_z, s);
+        if (e != cudaSuccess) return e;
+        a = P.a1;
+    }
+    return cudaSuccess;
 }
 
 // Fill BuildParams and make sure the image list for slab [i0,i1) is resident.
@@ -442,15 +478,15 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     if (!h->cell.ortho && h->cell.safemin2 < h->cutoff2) fhi = std::min(fhi, h->cell.safemin2 - GUARD_BAND);
     P.fast_hi = fhi;
     P.poly_erfcx = (h->alpha * cutoff <= ERFCX_XMAX && h->alpha >= 0) ? 1 : 0;
-    const TileShape ts = tile_shape(h->n_probes);
-    const double hx = 0.5 * (ts.tx - 1) * gs->delta[0], hy = 0.5 * (ts.ty - 1) * gs->delta[1], hz = 0.5 * (ts.tz - 1) * gs->delta[2];
-    const double reach = cutoff + std::sqrt(hx * hx + hy * hy + hz * hz) + 1e-6;
-    P.reach2 = reach * reach;
+    double rmax = 0.0;
+    for (int tx = main_tx(h->n_probes); tx >= 1; tx >>= 1)
+        rmax = std::max(rmax, tile_radius(tile_shape_for(h->n_probes, tx), gs->delta));
+    const double reach = cutoff + rmax + 1e-6;      // image-list margin: the widest tile shape
+    P.reach2 = reach * reach;                        // per launch: launch_planes
     P.lam_v = lam_v; P.thr_v = thr_v; P.lam_c = lam_c; P.thr_c = thr_c;
     P.i0 = i0; P.i1 = i1; P.a0 = i0; P.a1 = i1;
-    P.tiles_y = (gs->dims[1] + 1 + ts.ty - 1) / ts.ty;
-    P.tiles_z = (gs->dims[2] + 1 + ts.tz - 1) / ts.tz;
-    P.tiles_x = (i1 - i0 + ts.tx - 1) / ts.tx;
+    P.tiles_x = P.tiles_y = P.tiles_z = 0;
+    P.tile[0] = P.tile[1] = P.tile[2] = 0;
     P.atoms_xyz = h->d_xyz.as<double>();
     P.table = h->d_table.as<PairDev>();
     P.n_types = h->n_types;
@@ -467,6 +503,7 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
         std::vector<ExtAtom> ext;
         std::vector<ExtMeta> meta;
         build_ext_list(h, lo, hi, reach + 1e-6, ext, meta);
+        CEG_CK(cudaDeviceSynchronize());   // an earlier asynchronous build may still be reading the old list
         h->n_ext = (int)ext.size();
         CEG_CK(h->d_ext.reserve(sizeof(ExtAtom) * std::max<size_t>(1, ext.size())));
         CEG_CK(h->d_ext_meta.reserve(sizeof(ExtMeta) * std::max<size_t>(1, meta.size())));
@@ -494,8 +531,7 @@ extern "C" int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32
     for (int g = 0; g < ng; g++) P.out[g] = d_out[g];
     cudaStream_t s = (cudaStream_t)stream;
     CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), s));
-    const int n_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
-    CEG_CK(dispatch_tiled(h->n_probes, h->want_coulomb != 0, P, n_tiles, s));
+    CEG_CK(launch_planes(h, P, gs, std::sqrt(h->cutoff2), i0, i1, s));
     h->last_points = (int64_t)(i1 - i0) * (gs->dims[1] + 1) * (gs->dims[2] + 1);
     return 0;
 }
@@ -518,16 +554,13 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
     P.raw = raw_f64 ? h->d_raw.as<double>() : nullptr;
     CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), h->s_compute));
     // x-chunks: compute chunk c on s_compute while chunk c-1 drains to the host on s_copy
-    const TileShape ts = tile_shape(h->n_probes);
-    const int chunk = std::max(ts.tx, ((int)((48ll << 20) / (plane * 8 * 4 * ng)) / ts.tx) * ts.tx);
+    const int mtx = main_tx(h->n_probes);
+    const int chunk = std::max(mtx, ((int)((48ll << 20) / (plane * 8 * 4 * ng)) / mtx) * mtx);
     std::vector<cudaEvent_t> evs;
     int rc = 0;
     for (int a = i0; a < i1 && !rc; a += chunk) {
         const int b = std::min(i1, a + chunk);
-        P.a0 = a; P.a1 = b;
-        P.tiles_x = (b - a + ts.tx - 1) / ts.tx;
-        const int n_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
-        cudaError_t e = dispatch_tiled(h->n_probes, h->want_coulomb != 0, P, n_tiles, h->s_compute);
+        cudaError_t e = launch_planes(h, P, gs, std::sqrt(h->cutoff2), a, b, h->s_compute);
         if (e != cudaSuccess) { rc = fail_cuda(e, "grid_build_tiled_kernel", __FILE__, __LINE__); break; }
         if (any_out) {
             cudaEvent_t ev;

@@ -11,7 +11,7 @@
 //    (min-image search of utils.jl:210-246 for every supercell atom, division-based formulas).
 //    Backs ceg_compute_derivatives; its device functions are also the "exact" path of the tiled
 //    kernel.
-//  * grid_build_tiled_kernel — the production kernel.  One CTA owns a TXxTYxTZ tile of grid
+//  * grid_build_tiled_kernel — the production kernel.  One CTA owns a TXxTYxTZ tile (8x8x8) of grid
 //    nodes; it scans the pre-expanded list of periodic atom IMAGES (atom-major order, built on the
 //    host for the slab's bounding region), keeps those within cutoff + tile radius of the tile
 //    centre with an ORDERED compaction into shared memory, and every thread (one node each) walks
@@ -263,6 +263,7 @@ struct BuildParams {
     int i0, i1;                // slab of x planes held by the output buffers
     int a0, a1;                // planes computed by this launch (i0 <= a0 < a1 <= i1)
     int tiles_x, tiles_y, tiles_z;
+    int tile[3];               // nodes per tile along x, y, z (product = threads per CTA)
     int poly_erfcx;            // alpha*cutoff within the fitted range of erfcx_fast
     const ExtAtom* ext;
     const ExtMeta* ext_meta;
@@ -275,10 +276,10 @@ struct BuildParams {
     unsigned long long* stats; // [0] pairs tested, [1] pairs in cutoff
 };
 
-template <int TX, int TY, int TZ, int NP, bool COUL, bool POLY>
-__global__ void __launch_bounds__(TX* TY* TZ) grid_build_tiled_kernel(const BuildParams P) {
-    constexpr int NT = TX * TY * TZ;
+template <int NT, int NP, bool COUL, bool POLY>
+__global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams P) {
     constexpr int NW = NT / 32;
+    const int TX = P.tile[0], TY = P.tile[1], TZ = P.tile[2];   // TX*TY*TZ == NT (8x8x8 main, flatter tail shapes)
     constexpr int NG = NP + (COUL ? 1 : 0);
     __shared__ ExtAtom s_atom[LIST_CAP];
     __shared__ ExtMeta s_meta[LIST_CAP];

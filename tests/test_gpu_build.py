@@ -91,6 +91,14 @@ def test_tiled_slab_mfi_synthetic(cuda_lib, orc):
     _check_slab(orc, inp, cset, 10, 14, "mfi")
 
 
+def test_ragged_slab_uses_every_tile_shape(cuda_lib, orc):
+    """13 planes = one 8-plane row + the 4-, and 1-plane tail shapes; 7 planes = 4 + 2 + 1."""
+    inp, cset, _ = wl.load_fixture("cha_na")
+    cs = wl.respace(cset, 0.45)
+    _check_slab(orc, inp, cs, 5, 18, "ragged 13")
+    _check_slab(orc, inp, cs, 40, 47, "ragged 7")
+
+
 def test_single_plane_and_vdw_only_and_coulomb_only(cuda_lib, orc):
     inp, cset, _ = wl.load_fixture("cha_na")
     cs = wl.respace(cset, 0.6)
