@@ -159,6 +159,7 @@ def run_product(args):
     lam_c, thr_c = ceg.coulomb_scaling()
     launches0 = ceg._lib.kernel_launch_count()
     fp64_peak = ceg._lib.measure_fp64_peak(dev)
+    fp64_peak_regops = ceg._lib.measure_fp64_peak_regops(dev)
     hbm_peak, hbm_src = measured_peaks()
 
     # ================= construction: kernel-only, outputs resident in HBM ===========================
@@ -315,10 +316,12 @@ def run_product(args):
                     "ms_per_step": e2e_ms, "note": "ceg_probe_create + ceg_grid_build into pinned host arrays + free"},
             "roofline": {"bound": "fp64", "achieved": my_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": my_tflops / fp64_peak if fp64_peak else None, "traffic": None,
-                         "peak_source": "ceg_measure_fp64_peak (DFMA chain, this run); nominal 37-40",
+                         "peak_source": "ceg_measure_fp64_peak (DFMA chains with uniform operands, this run); nominal 37.2",
+                         "peak_register_operands": fp64_peak_regops,
+                         "frac_of_register_operand_peak": my_tflops / fp64_peak_regops if fp64_peak_regops else None,
                          "algorithmic_flop_per_point": fl_pp, "pairs_in_cutoff_per_point": n_in_pp,
                          "pairs_tested_per_point": stats["pairs_tested"] / max(1, stats["n_points"]),
-                         "kernel": "grid_build_tiled_kernel<8,8,8,1,true>", "kernel_ms": my_ms},
+                         "kernel": "grid_build_tiled_kernel<512,1,true,true>", "kernel_ms": my_ms},
             "gpu_launches": int(build_launches),
             "clocks": clocks,
             "c1": {"workload": "C1: same framework, 0.15 Å (218x204x190 = 8,449,680 points), VdW + Coulomb grids, 1 GPU",

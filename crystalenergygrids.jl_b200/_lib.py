@@ -38,7 +38,7 @@ class ceg_gridspec_t(C.Structure):
 
 EXPORTS = [
     "ceg_last_error", "ceg_abi_version", "ceg_device_count", "ceg_device_info", "ceg_kernel_launch_count",
-    "ceg_measure_fp64_peak", "ceg_selftest_math", "ceg_host_register",
+    "ceg_measure_fp64_peak", "ceg_measure_fp64_peak_regops", "ceg_selftest_math", "ceg_host_register",
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
     "ceg_interpolate", "ceg_interpolate_dev", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
@@ -125,6 +125,12 @@ def kernel_launch_count() -> int:
 def measure_fp64_peak(device: int = 0) -> float:
     t = C.c_double(0.0)
     _check(load().ceg_measure_fp64_peak(C.c_int32(device), C.byref(t)))
+    return t.value
+
+
+def measure_fp64_peak_regops(device: int = 0) -> float:
+    t = C.c_double(0.0)
+    _check(load().ceg_measure_fp64_peak_regops(C.c_int32(device), C.byref(t)))
     return t.value
 
 

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libceg_cuda.so")
 SOURCES = ["ceg_cuda.cu"]
-HEADERS = ["common.cuh", "grid_build.cuh", "interp.cuh", "ewald.cuh"]
+HEADERS = ["common.cuh", "grid_build.cuh", "interp.cuh", "ewald.cuh", "fastmath.cuh", "math_coeffs.cuh"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -37,7 +37,8 @@ def needs_build() -> bool:
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("CEG_NVCC_DEFS", "").split()     # experiment switches, e.g. -DCEG_EXP_TABLE=1
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

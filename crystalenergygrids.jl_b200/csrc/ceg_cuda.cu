@@ -137,25 +137,33 @@ extern "C" int ceg_kernel_launch_count(int64_t* n) {
 
 namespace ceg {
 // 8 independent FMA chains per thread; the result is stored so the chains cannot be removed.
+// REGOPS = false: x = fma(x, a, b) with uniform a, b (one register operand per DFMA);
+// REGOPS = true : x = fma(x, y_i, z_i) with per-thread registers (three register operands per DFMA),
+// which is what a real kernel mostly issues.  On B200 the second form peaks ~30 % lower (register
+// read bandwidth), so both are reported.
+template <bool REGOPS>
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-    for (int i = 0; i < iters; i++) {
+    double x[8], y[8], z[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-        }
+    for (int i = 0; i < 8; i++) {
+        x[i] = threadIdx.x + i;
+        y[i] = REGOPS ? 0.999999 + 1e-9 * threadIdx.x * (i + 1) : a;
+        z[i] = REGOPS ? 1e-9 * (threadIdx.x + i) : b;
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = fma(x[i], y[i], z[i]);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
 }
-}  // namespace ceg
 
-extern "C" int ceg_measure_fp64_peak(int32_t device, double* tflops) {
-    if (!tflops) return fail("null argument");
-    if (use_device(device)) return 1;
+template <bool REGOPS>
+static int measure_fp64(int device, double* tflops) {
     cudaDeviceProp p;
     CEG_CK(cudaGetDeviceProperties(&p, device));
-    const int blocks = p.multiProcessorCount * 8, threads = 256, iters = 4096;
+    const int blocks = p.multiProcessorCount * 2, threads = 256, iters = 4096;
     DevBuf buf;
     CEG_CK(buf.reserve(sizeof(double) * blocks * threads));
     cudaEvent_t e0, e1;
@@ -164,7 +172,7 @@ extern "C" int ceg_measure_fp64_peak(int32_t device, double* tflops) {
     double best = 0.0;
     for (int rep = 0; rep < 6; rep++) {
         CEG_CK(cudaEventRecord(e0, 0));
-        fp64_peak_kernel<<<blocks, threads>>>(buf.as<double>(), iters, 0.999999, 1e-9);
+        fp64_peak_kernel<REGOPS><<<blocks, threads>>>(buf.as<double>(), iters, 0.999999, 1e-9);
         count_launch();
         CEG_CK(cudaGetLastError());
         CEG_CK(cudaEventRecord(e1, 0));
@@ -179,13 +187,29 @@ extern "C" int ceg_measure_fp64_peak(int32_t device, double* tflops) {
     *tflops = best;
     return 0;
 }
+}  // namespace ceg
+
+extern "C" int ceg_measure_fp64_peak(int32_t device, double* tflops) {
+    if (!tflops) return fail("null argument");
+    if (use_device(device)) return 1;
+    return measure_fp64<false>(device, tflops);
+}
+
+extern "C" int ceg_measure_fp64_peak_regops(int32_t device, double* tflops) {
+    if (!tflops) return fail("null argument");
+    if (use_device(device)) return 1;
+    return measure_fp64<true>(device, tflops);
+}
 
 namespace ceg {
 __global__ void selftest_math_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ out) {
+    __shared__ double s_etab[EXP_TAB];
+    for (int i = threadIdx.x; i < EXP_TAB; i += blockDim.x) s_etab[i] = c_exp_tab[i];
+    __syncthreads();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
-    out[4 * i] = exp_neg_fast(-v);
+    out[4 * i] = exp_neg_fast(-v, s_etab);
     out[4 * i + 1] = erfcx_fast(v);
     out[4 * i + 2] = rsqrt_fast(v);
     out[4 * i + 3] = rcp_fast(v);
@@ -477,6 +501,14 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     double fhi = h->cutoff2 - GUARD_BAND;
     if (!h->cell.ortho && h->cell.safemin2 < h->cutoff2) fhi = std::min(fhi, h->cell.safemin2 - GUARD_BAND);
     P.fast_hi = fhi;
+    {   // integer versions (high words): fast iff hi_fast_lo <= hi(d2) < hi_fast_lo + span, i.e. strictly
+        // above the high word of fast_lo and strictly below that of fast_hi
+        auto hiword = [](double v) { long long b; memcpy(&b, &v, 8); return (int)(b >> 32); };
+        P.hi_cut = hiword(P.cut_hi);
+        P.hi_fast_lo = hiword(P.fast_lo) + 1;
+        const int top = hiword(P.fast_hi);          // exclusive
+        P.hi_fast_span = top > P.hi_fast_lo ? (unsigned)(top - P.hi_fast_lo) : 0u;
+    }
     P.poly_erfcx = (h->alpha * cutoff <= ERFCX_XMAX && h->alpha >= 0) ? 1 : 0;
     double rmax = 0.0;
     for (int tx = main_tx(h->n_probes); tx >= 1; tx >>= 1)

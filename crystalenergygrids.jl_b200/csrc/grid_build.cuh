@@ -112,53 +112,61 @@ __device__ __forceinline__ void lj_terms(const PairDev& p, const PairGeom& g, do
     p3 = 384.0 * (ex6 * fma(-28.0, x6, 5.0)) * (ir4 * ir4);
 }
 
-// Buckingham terms (interactions.jl:447-457), no branches
-__device__ __forceinline__ void buck_terms(const PairDev& p, const PairGeom& g, double& v, double& p1, double& p2,
-                                           double& p3) {
+// Buckingham terms (interactions.jl:447-457), no branches.  With X = A e^{-Br}, y = B X / r:
+//   D X = -y,  D^2 X = (y + B^2 X)/r^2,  D^3 X = -(3 D^2 X + B^2 y)/r^2   (D = (1/r) d/dr),
+// and the dispersion part -C/r^6 contributes 6, -48, 480 times C/r^8, C/r^10, C/r^12.
+__device__ __forceinline__ void buck_terms(const PairDev& p, const PairGeom& g, const double* etab, double& v,
+                                           double& p1, double& p2, double& p3) {
     const double B = p.bB;
+    const double X = p.bA * exp_neg_fast(-(B * g.r), etab);
+    const double BX = B * X;
+    const double y = BX * g.ir;
+    const double d2x = fma(B, BX, y) * g.ir2;
+    const double d3x = fma(3.0, d2x, (B * B) * y) * g.ir2;       // = -D^3 X
     const double ir4 = g.ir2 * g.ir2;
-    const double ir6 = ir4 * g.ir2;
-    const double x6 = p.bC * ir6;
-    const double Br = B * g.r;
-    const double xe = p.bA * exp_neg_fast(-Br);
-    const double Bxe = B * xe;
-    const double ir3 = g.ir2 * g.ir;
-    const double x6ir2 = x6 * g.ir2;
-    v = (xe - x6) - p.b_shift;
-    p1 = fma(6.0, x6ir2, -(Bxe * g.ir));
-    p2 = fma(fma(Bxe, Br, Bxe), ir3, -48.0 * (x6ir2 * g.ir2));
-    p3 = fma(-(fma(Br, Br + 3.0, 3.0) * Bxe), ir3 * g.ir2, 480.0 * (x6 * ir6));
+    const double x6 = p.bC * (ir4 * g.ir2);
+    const double x8 = x6 * g.ir2, x10 = x8 * g.ir2, x12 = x10 * g.ir2;
+    v = (X - x6) - p.b_shift;
+    p1 = fma(6.0, x8, -y);
+    p2 = fma(-48.0, x10, d2x);
+    p3 = fma(480.0, x12, -d3x);
 }
 
-__device__ __forceinline__ void vdw_pair_fast(const PairDev& p, const PairGeom& g, double& v, double& p1, double& p2,
-                                              double& p3) {
+__device__ __forceinline__ void vdw_pair_fast(const PairDev& p, const PairGeom& g, const double* etab, double& v,
+                                              double& p1, double& p2, double& p3) {
     v = 0.0; p1 = 0.0; p2 = 0.0; p3 = 0.0;
     const int fl = p.flags;
     // hard sphere: the fast path only sees r2 >= fast_lo > every hs_r2, where the term is exactly 0
     if (fl & CEG_PAIR_LJ) lj_terms(p, g, v, p1, p2, p3);
     if (fl & CEG_PAIR_BUCK) {
         double bv, b1, b2, b3;
-        buck_terms(p, g, bv, b1, b2, b3);
+        buck_terms(p, g, etab, bv, b1, b2, b3);
         v += bv; p1 += b1; p2 += b2; p3 += b3;
     }
 }
 
-// ewald.jl:299-312 with erfc(x) = exp(-x^2) erfcx(x): one exp serves both terms.  POLY: alpha*cutoff lies
-// inside the fitted range of erfcx_fast (the default Ewald precision), else the library erfcx.
+// ewald.jl:299-312 through the standard recurrence of the real-space Ewald radial functions.  With
+// E = e^{-alpha^2 r^2}, K1 = 2 alpha/sqrt(pi), B0 = erfc(alpha r)/r and
+//   B_{n} = ((2n-1) B_{n-1} + K1 (2 alpha^2)^{n-1} E) / r^2,
+// the reference's (U, DU, D^2U, D^3U) are q (B0, -B1, B2, -B3): 11 FP64 operations after erfc instead
+// of 19 for the expanded polynomials in alpha^2 r^2.  erfc(x) = E erfcx(x) shares the one exponential.
+// POLY: alpha*cutoff lies inside the fitted range of erfcx_fast (the default Ewald precision), else
+// the library erfcx.  kk = {K1, 2 alpha^2 K1, (2 alpha^2)^2 K1}.
 template <bool POLY>
-__device__ __forceinline__ void ewald_pair_fast(double alpha, double two_alpha_over_sqrtpi, double q,
-                                                const PairGeom& g, double& v, double& p1, double& p2, double& p3) {
+__device__ __forceinline__ void ewald_pair_fast(double alpha, double alpha2, const double* kk, double q,
+                                                const PairGeom& g, const double* etab, double& v, double& p1,
+                                                double& p2, double& p3) {
+    const double E = exp_neg_fast(-(alpha2 * g.r2), etab);   // independent of the rsqrt chain
     const double ar = alpha * g.r;
-    const double a2 = ar * ar;                    // r2 * alpha^2
-    const double E = exp_neg_fast(-a2);
-    const double e2 = (two_alpha_over_sqrtpi * g.r) * E;
-    const double c = E * (POLY ? erfcx_fast(ar) : erfcx(ar));
-    const double qir = q * g.ir;
-    const double qir3 = qir * g.ir2, qir5 = qir3 * g.ir2, qir7 = qir5 * g.ir2;
-    v = qir * c;
-    p1 = -(qir3 * (e2 + c));
-    p2 = qir5 * fma(e2, fma(2.0, a2, 3.0), 3.0 * c);
-    p3 = -(qir7 * fma(e2, fma(fma(4.0, a2, 10.0), a2, 15.0), 15.0 * c));
+    const double w = POLY ? erfcx_fast(ar) : erfcx(ar);
+    const double qE = q * E;
+    v = (qE * w) * g.ir;                                     // q B0
+    const double b1 = fma(kk[0], qE, v) * g.ir2;             // q B1
+    const double b2 = fma(3.0, b1, kk[1] * qE) * g.ir2;      // q B2
+    const double b3 = fma(5.0, b2, kk[2] * qE) * g.ir2;      // q B3
+    p1 = -b1;
+    p2 = b2;
+    p3 = -b3;
 }
 
 __device__ __forceinline__ void accumulate(double* acc, double v, double p1, double p2, double p3, double dx,
@@ -258,6 +266,8 @@ struct BuildParams {
     double cutoff2, alpha;
     double cut_hi;             // cutoff2 + GUARD_BAND: pairs below enter the pair code
     double fast_lo, fast_hi;   // d2 in [fast_lo, fast_hi] takes the fast path, anything else the literal one
+    int hi_cut, hi_fast_lo;    // the same windows on the high 32 bits of d2 (see the kernel)
+    unsigned hi_fast_span;
     double reach2;             // (cutoff + tile radius + slack)^2
     double lam_v, thr_v, lam_c, thr_c;
     int i0, i1;                // slab of x planes held by the output buffers
@@ -286,10 +296,12 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
     __shared__ PairDev s_table[NP > 0 ? NP * TABLE_SMEM_TYPES : 1];   // (probe x present species), <= 24 species
     __shared__ CellDev s_cell;
     __shared__ int s_wcount[NW];
+    __shared__ double s_etab[EXP_TAB];   // 2^(j/256) for exp_neg_fast
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_cell = P.cell;
+    for (int i = tid; i < EXP_TAB; i += NT) s_etab[i] = c_exp_tab[i];
     if (NP > 0)
         for (int i = tid; i < NP * P.n_types; i += NT) s_table[i] = P.table[i];
 
@@ -316,7 +328,9 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
 #pragma unroll
         for (int c = 0; c < 8; c++) acc[g][c] = 0.0;
     double smallest = CUDART_INF;
-    const double taosp = 2.0 * P.alpha / sqrt(CUDART_PI);
+    const double alpha2 = P.alpha * P.alpha;
+    const double k1_ = 2.0 * P.alpha / sqrt(CUDART_PI);
+    const double kk[3] = {k1_, 2.0 * alpha2 * k1_, 4.0 * alpha2 * alpha2 * k1_};
     unsigned int n_tested = 0, n_in = 0;
     int count = 0;
     __syncthreads();
@@ -328,9 +342,13 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
             const ExtAtom a = s_atom[e];
             double dx = px - a.x, dy = py - a.y, dz = pz - a.z;
             double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
-            if (d2 < P.cut_hi) {
+            // Window tests on the high word of d2 (>= 0, so it orders like an integer): they run on the
+            // integer pipe and are conservative — anything not strictly inside the fast window, up to the
+            // first high word above cutoff^2 + band, goes to the literal path, which decides exactly.
+            const int d2hi = __double2hiint(d2);
+            if (d2hi <= P.hi_cut) {
                 const int ty_ = s_meta[e].type;
-                if (d2 >= P.fast_lo && d2 <= P.fast_hi) {
+                if ((unsigned)(d2hi - P.hi_fast_lo) < P.hi_fast_span) {
                     // ---- hot path ----
                     n_in++;
                     const PairGeom geo = make_geom(d2);
@@ -342,21 +360,21 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
                         const int fl = pr.flags & ~CEG_PAIR_HS;   // hard spheres contribute exactly 0 here
                         double v, p1, p2, p3, ev, e1, e2, e3;
                         if (fl == CEG_PAIR_BUCK) {
-                            buck_terms(pr, geo, v, p1, p2, p3);
-                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, ev, e1, e2, e3);
+                            buck_terms(pr, geo, s_etab, v, p1, p2, p3);
+                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         } else if (fl == CEG_PAIR_LJ) {
                             lj_terms(pr, geo, v, p1, p2, p3);
-                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, ev, e1, e2, e3);
+                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         } else if (fl == 0) {
-                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, ev, e1, e2, e3);
+                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         } else {
-                            vdw_pair_fast(pr, geo, v, p1, p2, p3);
-                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, ev, e1, e2, e3);
+                            vdw_pair_fast(pr, geo, s_etab, v, p1, p2, p3);
+                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         }
@@ -366,13 +384,13 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
                             const PairDev& pr = s_table[g * P.n_types + ty_];
                             if (pr.flags != 0) {
                                 double v, p1, p2, p3;
-                                vdw_pair_fast(pr, geo, v, p1, p2, p3);
+                                vdw_pair_fast(pr, geo, s_etab, v, p1, p2, p3);
                                 accumulate(acc[g], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             }
                         }
                         if (COUL) {   // d2 >= fast_lo > 1 Å^2 here: `smallest` (probes.jl:108) is tracked on the literal path
                             double v, p1, p2, p3;
-                            ewald_pair_fast<POLY>(P.alpha, taosp, a.q, geo, v, p1, p2, p3);
+                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, v, p1, p2, p3);
                             accumulate(acc[NG - 1], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                         }
                     }

@@ -84,6 +84,9 @@ int ceg_kernel_launch_count(int64_t* n);
 /* FP64 FMA-chain microbenchmark: sustained DFMA throughput of the device in TFLOP/s (2 flop per FMA).
  * The roofline denominator of the construction kernels (MEASURED_PEAKS.json has no FP64 entry). */
 int ceg_measure_fp64_peak(int32_t device, double* tflops);
+/* Same chains with three per-thread register operands per DFMA (what real kernels issue): on B200 the
+ * register-file read bandwidth caps this form ~30 % below the uniform-operand figure. */
+int ceg_measure_fp64_peak_regops(int32_t device, double* tflops);
 
 /* Self-test hook for the branch-free device math of the construction kernels (fastmath.cuh):
  * out[4*i..] = exp_neg_fast(-x[i]), erfcx_fast(x[i]), rsqrt_fast(x[i]), rcp_fast(x[i]), x[i] > 0. */

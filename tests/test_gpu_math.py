@@ -13,7 +13,7 @@ def test_fastmath_accuracy(cuda_lib):
     rng = np.random.default_rng(0)
     x = np.concatenate([rng.random(200000) * 3.5, np.linspace(1e-6, 3.5, 20001), [3.5, 1e-300 * 0 + 1e-12]])
     out = ceg._lib.selftest_math(x)
-    assert np.max(np.abs(out[:, 1] - erfcx(x)) / erfcx(x)) < 2e-13          # erfcx_fast on [0, 3.5]
+    assert np.max(np.abs(out[:, 1] - erfcx(x)) / erfcx(x)) < 5e-13          # erfcx_fast on [0, 3.5] (degree 12: 3.2e-13)
     # exp over the range the kernels use it on: [-B r, 0] with B r up to ~700
     y = np.concatenate([rng.random(200000) * 60.0, rng.random(20000) * 690.0, [0.0, 1e-300, 700.0]])
     o2 = ceg._lib.selftest_math(np.maximum(y, 1e-300))
