@@ -41,7 +41,7 @@ EXPORTS = [
     "ceg_measure_fp64_peak", "ceg_measure_fp64_peak_regops", "ceg_selftest_math", "ceg_host_register",
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
-    "ceg_interpolate", "ceg_interpolate_dev", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
+    "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
     "ceg_ewald_reciprocal_dev", "ceg_block_upload", "ceg_block_free", "ceg_energy_points",
 ]
 
@@ -249,6 +249,19 @@ def interpolate(h, xyz) -> np.ndarray:
     out = np.empty(xyz.shape[0], dtype=np.float64)
     _check(load().ceg_interpolate(h, C.c_int64(xyz.shape[0]), _p(xyz, C.c_double), _p(out, C.c_double)))
     return out
+
+
+def interpolate_multi(handles, xyz, outs=None) -> np.ndarray:
+    """(n_grids, n) energies of several grids at the same positions (uploaded once)."""
+    xyz = _f64(xyz, (-1, 3))
+    G, n = len(handles), xyz.shape[0]
+    if outs is None:
+        outs = np.empty((G, n), dtype=np.float64)
+    assert outs.shape == (G, n) and outs.dtype == np.float64 and outs.flags.c_contiguous
+    hs = (C.c_void_p * G)(*handles)
+    ptrs = (c_double_p * G)(*[_p(outs[g], C.c_double) for g in range(G)])
+    _check(load().ceg_interpolate_multi(C.c_int32(G), hs, C.c_int64(n), _p(xyz, C.c_double), ptrs))
+    return outs
 
 
 def interpolate_dev(h, n: int, d_xyz: int, d_out: int, stream: int = 0):

@@ -75,9 +75,9 @@ struct ceg_probe_s {
 struct ceg_grid_s {
     int device = 0;
     std::mutex mu;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // ping-pong pair for the pipelined host path
     GridDev g;
-    DevBuf d_nodes, d_xyz, d_out;
+    DevBuf d_nodes, d_xyz[2], d_out[2];
 };
 
 struct ceg_ewald_s {
@@ -524,6 +524,8 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     P.n_types = h->n_types;
     for (int g = 0; g < MAX_GRIDS; g++) P.out[g] = nullptr;
     P.raw = nullptr;
+    P.raw_slab = 0;
+    P.raw_plane0 = 0;
     P.stats = h->d_stats.as<unsigned long long>();
     // image list for the slab's bounding box
     double lo[3], hi[3];
@@ -580,40 +582,57 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
     const int64_t plane = ny * nz, slab = (int64_t)(i1 - i0) * plane, npts = nx * plane;
     bool any_out = false;
     for (int g = 0; g < ng; g++) any_out |= (out_f32 && out_f32[g]);
-    if (any_out) CEG_CK(h->d_out.reserve(sizeof(float) * 8 * slab * ng));
-    if (raw_f64) CEG_CK(h->d_raw.reserve(sizeof(double) * 8 * slab * ng));
-    for (int g = 0; g < ng; g++) P.out[g] = (out_f32 && out_f32[g]) ? h->d_out.as<float>() + (int64_t)g * 8 * slab : nullptr;
-    P.raw = raw_f64 ? h->d_raw.as<double>() : nullptr;
-    CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), h->s_compute));
-    // x-chunks: compute chunk c on s_compute while chunk c-1 drains to the host on s_copy
+    // Device scratch is a ring of RING x-chunks (not the whole slab): chunk c is computed on s_compute into
+    // slot c % RING while earlier chunks drain to the host on s_copy, so the footprint stays ~150 MB for any
+    // grid size and no large allocation is made or freed per call.
+    constexpr int RING = 3;
     const int mtx = main_tx(h->n_probes);
     const int chunk = std::max(mtx, ((int)((48ll << 20) / (plane * 8 * 4 * ng)) / mtx) * mtx);
-    std::vector<cudaEvent_t> evs;
-    int rc = 0;
-    for (int a = i0; a < i1 && !rc; a += chunk) {
+    const int64_t chunk_slab = (int64_t)chunk * plane;
+    if (any_out) CEG_CK(h->d_out.reserve(sizeof(float) * 8 * chunk_slab * ng * RING));
+    if (raw_f64) CEG_CK(h->d_raw.reserve(sizeof(double) * 8 * slab * ng));
+    CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), h->s_compute));
+    cudaEvent_t ev_done[RING], ev_free[RING];
+    for (int r = 0; r < RING; r++) {
+        CEG_CK(cudaEventCreateWithFlags(&ev_done[r], cudaEventDisableTiming));
+        CEG_CK(cudaEventCreateWithFlags(&ev_free[r], cudaEventDisableTiming));
+    }
+    int rc = 0, c = 0;
+    for (int a = i0; a < i1 && !rc; a += chunk, c++) {
         const int b = std::min(i1, a + chunk);
-        cudaError_t e = launch_planes(h, P, gs, std::sqrt(h->cutoff2), a, b, h->s_compute);
+        const int slot = c % RING;
+        float* base = any_out ? h->d_out.as<float>() + (int64_t)slot * 8 * chunk_slab * ng : nullptr;
+        const int64_t cslab = (int64_t)(b - a) * plane;       // the kernel indexes outputs relative to [P.i0, P.i1)
+        BuildParams Q = P;
+        Q.i0 = a; Q.i1 = b;
+        for (int g = 0; g < ng; g++) Q.out[g] = (out_f32 && out_f32[g]) ? base + (int64_t)g * 8 * cslab : nullptr;
+        Q.raw = nullptr;
+        if (raw_f64) {   // parity-test output: whole slab on the device, written through an offset view
+            Q.raw = h->d_raw.as<double>();
+            Q.raw_slab = slab;
+            Q.raw_plane0 = a - i0;
+        }
+        if (c >= RING) cudaStreamWaitEvent(h->s_compute, ev_free[slot], 0);   // slot drained?
+        cudaError_t e = launch_planes(h, Q, gs, std::sqrt(h->cutoff2), a, b, h->s_compute);
         if (e != cudaSuccess) { rc = fail_cuda(e, "grid_build_tiled_kernel", __FILE__, __LINE__); break; }
         if (any_out) {
-            cudaEvent_t ev;
-            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-            cudaEventRecord(ev, h->s_compute);
-            cudaStreamWaitEvent(h->s_copy, ev, 0);
-            evs.push_back(ev);
+            cudaEventRecord(ev_done[slot], h->s_compute);
+            cudaStreamWaitEvent(h->s_copy, ev_done[slot], 0);
             for (int g = 0; g < ng && !rc; g++) {
-                if (!P.out[g]) continue;
-                for (int c = 0; c < 8; c++) {
-                    const float* src = P.out[g] + (int64_t)c * slab + (int64_t)(a - i0) * plane;
-                    float* dst = out_f32[g] + (int64_t)c * npts + (int64_t)a * plane;
-                    e = cudaMemcpyAsync(dst, src, sizeof(float) * (int64_t)(b - a) * plane, cudaMemcpyDeviceToHost, h->s_copy);
+                if (!Q.out[g]) continue;
+                for (int ch = 0; ch < 8; ch++) {
+                    const float* src = Q.out[g] + (int64_t)ch * cslab;
+                    float* dst = out_f32[g] + (int64_t)ch * npts + (int64_t)a * plane;
+                    e = cudaMemcpyAsync(dst, src, sizeof(float) * cslab, cudaMemcpyDeviceToHost, h->s_copy);
                     if (e != cudaSuccess) { rc = fail_cuda(e, "cudaMemcpyAsync(D2H slab)", __FILE__, __LINE__); break; }
                 }
             }
+            cudaEventRecord(ev_free[slot], h->s_copy);
         }
     }
     cudaError_t e1 = cudaStreamSynchronize(h->s_compute);
     cudaError_t e2 = cudaStreamSynchronize(h->s_copy);
-    for (auto ev : evs) cudaEventDestroy(ev);
+    for (int r = 0; r < RING; r++) { cudaEventDestroy(ev_done[r]); cudaEventDestroy(ev_free[r]); }
     if (rc) return rc;
     if (e1 != cudaSuccess) return fail_cuda(e1, "grid build (compute stream)", __FILE__, __LINE__);
     if (e2 != cudaSuccess) return fail_cuda(e2, "grid build (copy stream)", __FILE__, __LINE__);
@@ -700,6 +719,7 @@ extern "C" int ceg_grid_free(ceg_grid_h h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
     return 0;
 }
@@ -725,18 +745,53 @@ extern "C" int ceg_interpolate_dev(ceg_grid_h h, int64_t n, const double* d_xyz,
     return 0;
 }
 
+// Host-pointer path: queries are streamed through the device in chunks on two streams, so that the
+// upload of chunk c+1, the kernels of chunk c and the download of chunk c-1 overlap (PCIe is full
+// duplex).  Every grid of `grids` is evaluated at the same positions, which are uploaded once.
+static int interpolate_pipelined(int n_grids, ceg_grid_s* const* grids, int64_t n, const double* xyz, double* const* outs) {
+    ceg_grid_s* h0 = grids[0];
+    std::lock_guard<std::mutex> lk(h0->mu);
+    if (use_device(h0->device)) return 1;
+    if (!h0->stream2) CEG_CK(cudaStreamCreateWithFlags(&h0->stream2, cudaStreamNonBlocking));
+    const int64_t chunk = std::min<int64_t>(n, 1 << 20);
+    for (int b = 0; b < 2; b++) {
+        CEG_CK(h0->d_xyz[b].reserve(sizeof(double) * 3 * chunk));
+        CEG_CK(h0->d_out[b].reserve(sizeof(double) * chunk * n_grids));
+    }
+    cudaStream_t st[2] = {h0->stream, h0->stream2};
+    int c = 0;
+    for (int64_t q0 = 0; q0 < n; q0 += chunk, c++) {
+        const int64_t m = std::min(chunk, n - q0);
+        const int b = c & 1;
+        CEG_CK(cudaMemcpyAsync(h0->d_xyz[b].p, xyz + 3 * q0, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, st[b]));
+        for (int g = 0; g < n_grids; g++) {
+            double* d_o = h0->d_out[b].as<double>() + (int64_t)g * chunk;
+            CEG_CK(launch_interpolate(grids[g]->g, m, h0->d_xyz[b].as<double>(), d_o, st[b]));
+            CEG_CK(cudaMemcpyAsync(outs[g] + q0, d_o, sizeof(double) * m, cudaMemcpyDeviceToHost, st[b]));
+        }
+    }
+    CEG_CK(cudaStreamSynchronize(st[0]));
+    CEG_CK(cudaStreamSynchronize(st[1]));
+    return 0;
+}
+
 extern "C" int ceg_interpolate(ceg_grid_h h, int64_t n, const double* xyz, double* out) {
     if (!h || n < 0 || (n > 0 && (!xyz || !out))) return fail("ceg_interpolate: bad argument");
     if (n == 0) return 0;
-    std::lock_guard<std::mutex> lk(h->mu);
-    if (use_device(h->device)) return 1;
-    CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * n));
-    CEG_CK(h->d_out.reserve(sizeof(double) * n));
-    CEG_CK(cudaMemcpyAsync(h->d_xyz.p, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
-    CEG_CK(launch_interpolate(h->g, n, h->d_xyz.as<double>(), h->d_out.as<double>(), h->stream));
-    CEG_CK(cudaMemcpyAsync(out, h->d_out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
-    CEG_CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    ceg_grid_s* g[1] = {h};
+    double* o[1] = {out};
+    return interpolate_pipelined(1, g, n, xyz, o);
+}
+
+extern "C" int ceg_interpolate_multi(int32_t n_grids, const ceg_grid_h* grids, int64_t n, const double* xyz, double* const* outs) {
+    if (n_grids <= 0 || n_grids > 16 || !grids || n < 0 || (n > 0 && (!xyz || !outs)))
+        return fail("ceg_interpolate_multi: bad argument");
+    for (int g = 0; g < n_grids; g++) {
+        if (!grids[g] || (n > 0 && !outs[g])) return fail("ceg_interpolate_multi: null grid or output");
+        if (grids[g]->device != grids[0]->device) return fail("ceg_interpolate_multi: grids live on different devices");
+    }
+    if (n == 0) return 0;
+    return interpolate_pipelined(n_grids, grids, n, xyz, outs);
 }
 
 // ================================================================================================

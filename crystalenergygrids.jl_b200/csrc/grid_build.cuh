@@ -282,7 +282,9 @@ struct BuildParams {
     const PairDev* table;
     int n_types;
     float* out[MAX_GRIDS];     // each [8][i1-i0][ny][nz]
-    double* raw;               // optional [g][8][i1-i0][ny][nz]
+    double* raw;               // optional [g][8][raw_slab/plane][ny][nz]; this launch's slab starts at raw_plane0
+    int64_t raw_slab;
+    int raw_plane0;
     unsigned long long* stats; // [0] pairs tested, [1] pairs in cutoff
 };
 
@@ -486,7 +488,8 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
         const bool coul = COUL && (g == NG - 1);
         if (P.raw) {
 #pragma unroll
-            for (int c = 0; c < 8; c++) P.raw[((int64_t)g * 8 + c) * slab + node] = acc[g][c];
+            for (int c = 0; c < 8; c++)
+                P.raw[((int64_t)g * 8 + c) * P.raw_slab + (int64_t)P.raw_plane0 * plane + node] = acc[g][c];
         }
         if (P.out[g]) {
             float o[8];

@@ -157,6 +157,9 @@ int ceg_set_interp_layout(int32_t layout);
 int ceg_grid_layout(ceg_grid_h h, int32_t* layout);
 int ceg_interpolate(ceg_grid_h h, int64_t n, const double* xyz /* n x 3 Cartesian Å */, double* out /* n, K */);
 int ceg_interpolate_dev(ceg_grid_h h, int64_t n, const double* d_xyz, double* d_out, void* stream);
+/* Several grids (e.g. the VdW grid of an atom and the Coulomb grid, grids.jl:316-318) at the same
+ * positions: positions are uploaded once; outs[g] receives n energies of grids[g]. */
+int ceg_interpolate_multi(int32_t n_grids, const ceg_grid_h* grids, int64_t n, const double* xyz, double* const* outs);
 
 /* ------------------------------------------------------------------------------------------
  * Ewald reciprocal space.  ceg_ewald_create replaces setup_Eik + ewald_main_loop! for the

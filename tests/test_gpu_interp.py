@@ -82,6 +82,23 @@ def test_nodes_edges_and_empty(cuda_lib, orc, layout):
         ceg.interpolate_grid(ceg.EnergyGrid.invalid(), np.array([1.0, 2.0, 3.0]))
 
 
+def test_interpolate_multi_pipelined(cuda_lib, orc):
+    """ceg_interpolate_multi: several grids at the same positions, more queries than one pipeline chunk."""
+    cset = ceg.GridCoordinatesSetup.from_cell(ceg.mat_from_parameters((9.0, 8.0, 7.0), (85, 95, 100)), 0.5)
+    g1, g2 = _random_grid(cset, 1, hot_fraction=0.05), _random_grid(cset, 2)
+    e1 = ceg.EnergyGrid(cset, (1, 1, 1), np.inf, True, g1)
+    e2 = ceg.EnergyGrid(cset, (1, 1, 1), 1e-6, True, g2)
+    pos = wl.random_positions(cset.cell.mat, 2_300_000, 77)
+    both = ceg._lib.interpolate_multi([e1.handle, e2.handle], pos)
+    assert np.array_equal(both[0], ceg.interpolate_grid(e1, pos)) and np.array_equal(both[1], ceg.interpolate_grid(e2, pos))
+    sub = slice(0, 50000)
+    want = orc.interpolate(cset, g1, True, pos[sub])
+    assert np.array_equal(both[0][sub] == 1e100, want == 1e100)
+    ok = want != 1e100
+    assert (np.abs(both[0][sub][ok] - want[ok]) <= 1e-9 * np.abs(want[ok]) + 1e-6).all()
+    e1.close(); e2.close()
+
+
 def test_c2_on_built_grids_and_goldens(cuda_lib, orc, tmp_path):
     """C1 -> C2 end to end on the device path: build the Ar grid of CHA+Na and the Na+/Coulomb grids of
     CHA at 0.15 Å, write/parse the .grid files, interpolate; check the reference's own known
