@@ -659,7 +659,7 @@ extern "C" int ceg_probe_last_stats(ceg_probe_h h, int64_t* n_points, int64_t* p
 static std::atomic<int> g_interp_layout{-1};   // -1 = automatic
 
 extern "C" int ceg_set_interp_layout(int32_t layout) {
-    if (layout < -1 || layout > LAYOUT_CELL) return fail("ceg_set_interp_layout: layout must be -1 (auto), 0, 1 or 2");
+    if (layout < -1 || layout > LAYOUT_PAIR) return fail("ceg_set_interp_layout: layout must be -1 (default), 0, 1, 2 or 3");
     g_interp_layout.store(layout);
     return 0;
 }
@@ -701,7 +701,7 @@ extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const
         count_launch();
         CEG_CK(cudaGetLastError());
         if (layout != LAYOUT_NODE) {
-            const int corners = (layout == LAYOUT_QUAD) ? 4 : 8;
+            const int corners = (layout == LAYOUT_PAIR) ? 2 : (layout == LAYOUT_QUAD) ? 4 : 8;
             CEG_CK(h->d_nodes.reserve(node_bytes * corners));
             expand_records_kernel<<<148 * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz, corners);
             count_launch();
@@ -731,6 +731,7 @@ static cudaError_t launch_interpolate(const GridDev& g, int64_t n, const double*
     switch (g.layout) {
         case LAYOUT_CELL: interpolate_kernel<LAYOUT_CELL><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
         case LAYOUT_QUAD: interpolate_kernel<LAYOUT_QUAD><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
+        case LAYOUT_PAIR: interpolate_kernel<LAYOUT_PAIR><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
         default: interpolate_kernel<LAYOUT_NODE><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
     }
     count_launch();

@@ -8,6 +8,7 @@
 // (8 channels x f32 = 32 B = one sector per node) and, memory permitting, expanded further so that a
 // query's 8 corner records are contiguous and aligned:
 //   NODE  [x][y][z]            32 B records, 1x memory: 8 sectors per query, 4 runs of 64 B;
+//   PAIR  [x][y][z0]           64 B records = nodes (z0),(z0+1), 2x memory: 4 aligned 64 B fetches;
 //   QUAD  [x][y0][z0]         128 B records = nodes (y0,z0),(y0,z1),(y1,z0),(y1,z1), 4x memory:
 //                              2 aligned 128 B lines per query;
 //   CELL  [x0][y0][z0]        256 B records = all 8 corners, 8x memory: one aligned 256 B block.
@@ -25,7 +26,7 @@
 
 namespace ceg {
 
-enum { LAYOUT_NODE = 0, LAYOUT_QUAD = 1, LAYOUT_CELL = 2 };
+enum { LAYOUT_NODE = 0, LAYOUT_QUAD = 1, LAYOUT_CELL = 2, LAYOUT_PAIR = 3 };
 
 struct GridDev {
     CellDev uc;
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(256) expand_records_kernel(const Rec8* __restr
         const int z = (int)(n % nz); n /= nz;
         const int y = (int)(n % ny);
         const int x = (int)(n / ny);
-        const int iz = c & 1, iy = (c >> 1) & 1, ix = (c >> 2) & 1;   // QUAD never sets ix
+        const int iz = c & 1, iy = (c >> 1) & 1, ix = (c >> 2) & 1;   // PAIR: iz only; QUAD: iy, iz
         const int xx = min(x + ix, nx - 1), yy = min(y + iy, ny - 1), zz = min(z + iz, nz - 1);
         dst[t] = nodes[((int64_t)xx * ny + yy) * nz + zz];
     }
@@ -120,6 +121,16 @@ __device__ __forceinline__ double interp_one(const GridDev& g, const Stencil& st
         const float* rec = g.data + base * 64;
 #pragma unroll
         for (int n = 0; n < 8; n++) ld_rec(rec + 8 * n, lo[n], hi[n]);
+    } else if (LAYOUT == LAYOUT_PAIR) {
+#pragma unroll
+        for (int ix = 0; ix < 2; ix++)
+#pragma unroll
+            for (int iy = 0; iy < 2; iy++) {
+                const int64_t rec = base + ((int64_t)(ix ? st.step[0] : 0) * ny + (iy ? st.step[1] : 0)) * nz;
+                const int n = (ix * 2 + iy) * 2;
+                ld_rec(g.data + rec * 16, lo[n], hi[n]);
+                ld_rec(g.data + rec * 16 + 8, lo[n + 1], hi[n + 1]);
+            }
     } else if (LAYOUT == LAYOUT_QUAD) {
         const float* r0 = g.data + base * 32;
         const float* r1 = r0 + (int64_t)st.step[0] * ny * nz * 32;
@@ -173,6 +184,7 @@ __device__ __forceinline__ double interp_any(const GridDev& g, const Stencil& st
     switch (g.layout) {
         case LAYOUT_CELL: return interp_one<LAYOUT_CELL>(g, st);
         case LAYOUT_QUAD: return interp_one<LAYOUT_QUAD>(g, st);
+        case LAYOUT_PAIR: return interp_one<LAYOUT_PAIR>(g, st);
         default: return interp_one<LAYOUT_NODE>(g, st);
     }
 }

@@ -7,7 +7,10 @@ import ceg_b200 as ceg
 from ceg_b200 import workloads as wl
 
 inp, cset, ex = wl.load_fixture("cha_na")
+if len(sys.argv) > 1:
+    cset = wl.respace(cset, float(sys.argv[1]))
 nx, ny, nz = cset.nodes
+print("grid", nx, ny, nz, nx * ny * nz * 32 / 1e6, "MB")
 rng = np.random.default_rng(0)
 grid = rng.standard_normal((8, nx, ny, nz)).astype(np.float32)
 n = 10_000_000
@@ -15,7 +18,7 @@ pos = torch.from_numpy(wl.random_positions(cset.cell.mat, n, 1)).cuda()
 out = torch.empty(n, dtype=torch.float64, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
 ref = None
-for layout in (0, 1, 2):
+for layout in ((0, 3, 1, 2) if len(sys.argv) < 3 else [int(v) for v in sys.argv[2].split(',')]):
     ceg._lib.set_interp_layout(layout)
     eg = ceg.EnergyGrid(cset, (1, 1, 1), 1e-6, True, grid)
     h = eg.handle
