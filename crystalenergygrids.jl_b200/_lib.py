@@ -37,7 +37,7 @@ class ceg_gridspec_t(C.Structure):
 
 
 EXPORTS = [
-    "ceg_last_error", "ceg_abi_version", "ceg_device_count", "ceg_device_info", "ceg_kernel_launch_count",
+    "ceg_last_error", "ceg_abi_version", "ceg_device_count", "ceg_device_info", "ceg_trim_device_cache", "ceg_kernel_launch_count",
     "ceg_measure_fp64_peak", "ceg_measure_fp64_peak_regops", "ceg_selftest_math", "ceg_host_register",
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
@@ -114,6 +114,10 @@ def device_info(device: int = 0) -> dict:
     sm, mem, clk = C.c_int32(0), C.c_int64(0), C.c_int32(0)
     _check(load().ceg_device_info(C.c_int32(device), name, C.byref(sm), C.byref(mem), C.byref(clk)))
     return {"name": name.value.decode(), "sm_count": sm.value, "mem_bytes": mem.value, "clock_khz": clk.value}
+
+
+def trim_device_cache():
+    _check(load().ceg_trim_device_cache())
 
 
 def kernel_launch_count() -> int:

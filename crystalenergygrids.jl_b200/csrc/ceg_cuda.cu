@@ -29,6 +29,59 @@ int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
     return fail(buf);
 }
 
+// ---- device allocation cache (common.cuh) --------------------------------------------------------
+namespace {
+struct PoolEntry { void* p; size_t bytes; int device; };
+std::mutex g_pool_mu;
+std::vector<PoolEntry> g_pool;
+constexpr size_t POOL_MIN = 1u << 20;
+constexpr size_t POOL_CAP = 4ull << 30;      // at most 4 GiB parked per process
+size_t g_pool_bytes = 0;
+}  // namespace
+void* pool_acquire(size_t bytes, size_t* got) {
+    if (bytes < POOL_MIN) return nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pool.size(); i++)
+        if (g_pool[i].device == dev && g_pool[i].bytes >= bytes && g_pool[i].bytes <= 2 * bytes &&
+            (best < 0 || g_pool[i].bytes < g_pool[best].bytes))
+            best = i;
+    if (best < 0) return nullptr;
+    void* p = g_pool[best].p;
+    *got = g_pool[best].bytes;
+    g_pool_bytes -= g_pool[best].bytes;
+    g_pool.erase(g_pool.begin() + best);
+    return p;
+}
+void pool_release(void* p, size_t bytes) {
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (bytes >= POOL_MIN && g_pool_bytes + bytes <= POOL_CAP) {
+            g_pool.push_back({p, bytes, dev});
+            g_pool_bytes += bytes;
+            return;
+        }
+    }
+    cudaFree(p);
+}
+void pool_trim() {
+    std::vector<PoolEntry> old;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        old.swap(g_pool);
+        g_pool_bytes = 0;
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& e : old) { cudaSetDevice(e.device); cudaFree(e.p); }
+    cudaSetDevice(cur);
+}
+
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -126,6 +179,11 @@ extern "C" int ceg_device_info(int32_t device, char* name256, int32_t* sm_count,
         cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
         *clock_khz = khz;
     }
+    return 0;
+}
+
+extern "C" int ceg_trim_device_cache(void) {
+    pool_trim();
     return 0;
 }
 

@@ -26,6 +26,14 @@ int fail_cuda(cudaError_t e, const char* what, const char* file, int line);
 // every kernel launch of the library goes through this counter (ceg_kernel_launch_count)
 void count_launch(int n = 1);
 
+// Process-wide cache of device allocations (per device): cudaMalloc/cudaFree of the large scratch
+// buffers cost up to hundreds of ms (cudaFree synchronises the device and unmaps), which would
+// dominate a create-build-free cycle of a probe handle.  Buffers of >= 1 MiB are parked here on
+// release and handed out again to the next request of a similar size; ceg_trim_device_cache() frees them.
+void* pool_acquire(size_t bytes, size_t* got);
+void pool_release(void* p, size_t bytes);
+void pool_trim();
+
 // RAII device buffer
 struct DevBuf {
     void* p = nullptr;
@@ -35,7 +43,7 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pool_release(p, bytes);
         p = nullptr;
         bytes = 0;
     }
@@ -43,8 +51,16 @@ struct DevBuf {
         if (n <= bytes && p) return cudaSuccess;
         release();
         if (n == 0) n = 16;
+        size_t got = 0;
+        p = pool_acquire(n, &got);
+        if (p) { bytes = got; return cudaSuccess; }
         cudaError_t e = cudaMalloc(&p, n);
-        if (e == cudaSuccess) bytes = n;
+        if (e != cudaSuccess) {          // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            pool_trim();
+            e = cudaMalloc(&p, n);
+        }
+        if (e == cudaSuccess) bytes = n; else p = nullptr;
         return e;
     }
     template <class T>

@@ -79,6 +79,10 @@ int ceg_device_count(int32_t* n);
 /* name (<=255 chars), SM count, memory bytes, SM clock kHz of a device */
 int ceg_device_info(int32_t device, char* name256, int32_t* sm_count, int64_t* mem_bytes, int32_t* clock_khz);
 
+/* Large device scratch buffers are cached per process between calls/handles (cudaMalloc/cudaFree cost
+ * up to hundreds of ms); this releases the cache back to the driver. */
+int ceg_trim_device_cache(void);
+
 /* Number of kernels this library has launched in this process (all handles, all threads). */
 int ceg_kernel_launch_count(int64_t* n);
 /* FP64 FMA-chain microbenchmark: sustained DFMA throughput of the device in TFLOP/s (2 flop per FMA).
