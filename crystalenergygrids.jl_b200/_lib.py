@@ -42,7 +42,7 @@ EXPORTS = [
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
     "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
-    "ceg_ewald_reciprocal_dev", "ceg_block_upload", "ceg_block_free", "ceg_energy_points",
+    "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_block_upload", "ceg_block_free", "ceg_energy_points",
 ]
 
 _lib = None
@@ -302,6 +302,16 @@ def ewald_reciprocal(h, xyz, q, energy_net_charges: float, static_contribution: 
     _check(load().ceg_ewald_reciprocal(h, C.c_int64(xyz.shape[0]), C.c_int32(q.shape[0]), _p(xyz, C.c_double),
                                        _p(q, C.c_double), C.c_double(energy_net_charges),
                                        C.c_double(static_contribution), _p(out, C.c_double)))
+    return out
+
+
+def ewald_single_contribution(h, rest: np.ndarray, xyz, q) -> np.ndarray:
+    q = _f64(q, (-1,))
+    xyz = _f64(xyz, (-1, q.shape[0], 3))
+    r = np.ascontiguousarray(np.stack([np.real(rest), np.imag(rest)], axis=1), dtype=np.float64)
+    out = np.empty(xyz.shape[0], dtype=np.float64)
+    _check(load().ceg_ewald_single_contribution(h, _p(r, C.c_double), C.c_int64(xyz.shape[0]), C.c_int32(q.shape[0]),
+                                                _p(xyz, C.c_double), _p(q, C.c_double), _p(out, C.c_double)))
     return out
 
 

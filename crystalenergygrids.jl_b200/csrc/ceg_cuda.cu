@@ -914,8 +914,9 @@ extern "C" int ceg_ewald_free(ceg_ewald_h h) {
 
 static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const double* d_xyz, const double* d_q,
                              double enc, double stat, double* d_out, const uint8_t* d_skip, int accumulate,
-                             cudaStream_t s) {
+                             cudaStream_t s, const double2* d_rest = nullptr) {
     RecipParams P;
+    P.rest = d_rest;
     memcpy(P.invmat, h->invmat, sizeof P.invmat);
     P.kx = h->kmax[0]; P.ky = h->kmax[1]; P.kz = h->kmax[2];
     P.n_k = h->n_k;
@@ -965,6 +966,34 @@ extern "C" int ceg_ewald_reciprocal(ceg_ewald_h h, int64_t n_pos, int32_t n_atom
     CEG_CK(cudaMemcpyAsync(h->d_q.p, q, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, h->stream));
     if (launch_reciprocal(h, n_pos, n_atoms, h->d_xyz.as<double>(), h->d_q.as<double>(), energy_net_charges,
                           static_contribution, h->d_out.as<double>(), nullptr, 0, h->stream))
+        return 1;
+    CEG_CK(cudaMemcpyAsync(out, h->d_out.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, h->stream));
+    CEG_CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// single_contribution_ewald (ewald.jl:704-738) for many trial placements of ONE molecule:
+// out = 2 sum_k kf Re(rest conj S_single) + sum_k kf |S_single|^2, where `rest` = framework + all other
+// adsorbates (StoreRigidChargeFramework + sums[:,1] - sums[:,ij+1]) is supplied by the caller.
+extern "C" int ceg_ewald_single_contribution(ceg_ewald_h h, const double* rest_reim, int64_t n_pos, int32_t n_atoms,
+                                             const double* xyz, const double* q, double* out) {
+    if (!h || !rest_reim || n_pos < 0 || n_atoms <= 0 || !q || (n_pos > 0 && (!xyz || !out)))
+        return fail("ceg_ewald_single_contribution: bad argument");
+    if (n_pos == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    DevBuf d_rest;
+    CEG_CK(d_rest.reserve(sizeof(double) * 2 * std::max<int64_t>(1, h->n_k)));
+    CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * n_atoms * n_pos));
+    CEG_CK(h->d_out.reserve(sizeof(double) * n_pos));
+    CEG_CK(h->d_q.reserve(sizeof(double) * n_atoms));
+    if (h->n_k > 0)
+        CEG_CK(cudaMemcpyAsync(d_rest.p, rest_reim, sizeof(double) * 2 * h->n_k, cudaMemcpyHostToDevice, h->stream));
+    CEG_CK(cudaMemcpyAsync(h->d_xyz.p, xyz, sizeof(double) * 3 * n_atoms * n_pos, cudaMemcpyHostToDevice, h->stream));
+    CEG_CK(cudaMemcpyAsync(h->d_q.p, q, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, h->stream));
+    // host = 2*(fa + 0), ads = aa + 0  ->  2*rest_single + single_single (ewald.jl:737)
+    if (launch_reciprocal(h, n_pos, n_atoms, h->d_xyz.as<double>(), h->d_q.as<double>(), 0.0, 0.0, h->d_out.as<double>(),
+                          nullptr, 0, h->stream, d_rest.as<double2>()))
         return 1;
     CEG_CK(cudaMemcpyAsync(out, h->d_out.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, h->stream));
     CEG_CK(cudaStreamSynchronize(h->stream));

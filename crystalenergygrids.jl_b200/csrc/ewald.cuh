@@ -102,6 +102,7 @@ struct RecipParams {
     const double* q;       // n_atoms (device)
     double energy_net_charges, static_contribution;
     double* out;
+    const double2* rest;   // optional: replaces S_f (single_contribution_ewald's `rest`, ewald.jl:722-729)
     const uint8_t* skip;   // optional: placements flagged here are left untouched
     int accumulate;        // 1: out[i] += E (fused energy_point), 0: out[i] = E
 };
@@ -150,7 +151,8 @@ __global__ void __launch_bounds__(RECIP_WARPS * 32) reciprocal_kernel(const Reci
                 sre += qa * (ex.x * yzr - ex.y * yzi);
                 sim += qa * (ex.x * yzi + ex.y * yzr);
             }
-            fa += kv.kf * (kv.sf_re * sre + kv.sf_im * sim);
+            const double2 sf = P.rest ? P.rest[k] : make_double2(kv.sf_re, kv.sf_im);
+            fa += kv.kf * (sf.x * sre + sf.y * sim);
             aa += kv.kf * (sre * sre + sim * sim);
         }
 #pragma unroll

@@ -223,3 +223,23 @@ def compute_ewald(ctx_or_framework, systems=None, positions=None) -> float | np.
     pos = ctx.positions[None, :, :] if single else np.asarray(positions, dtype=np.float64).reshape(-1, len(ctx.charges), 3)
     out = _lib.ewald_reciprocal(ef.handle, pos, ctx.charges, ctx.energy_net_charges, ctx.static_contribution)
     return float(out[0]) if single else out
+
+
+def adsorbate_sums(eframework: EwaldFramework, charges, positions) -> np.ndarray:
+    """S_a(k) = sum_a q_a exp(i k.r_a) of a set of point charges (ewald_main_loop!, ewald.jl:148-185) —
+    one column of IncrementalEwaldContext.sums.  Host helper for setting up trial evaluations."""
+    frac = np.asarray(positions, dtype=np.float64).reshape(-1, 3) @ eframework.invmat.T
+    kv = eframework.kspace.kvec_array().astype(np.float64)
+    ph = frac @ kv.T                      # (n_atoms, n_k)
+    ph -= np.floor(ph)
+    return (np.asarray(charges, dtype=np.float64)[:, None] * np.exp(2j * np.pi * ph)).sum(axis=0)
+
+
+def single_contribution_ewald(eframework: EwaldFramework, rest: np.ndarray, charges, positions) -> np.ndarray:
+    """ewald.jl:704-738, batched: contribution of one molecule (charges, n_atoms) at each of the trial
+    placements `positions` (n_pos, n_atoms, 3) to the reciprocal Ewald sum, `rest` being the structure
+    factor of everything else (framework + other adsorbates).  The difference of two such values is the
+    reciprocal-space energy change of a Monte-Carlo move (montecarlo.jl:563-606)."""
+    if eframework.alpha == 0:
+        return np.zeros(np.asarray(positions).reshape(-1, len(charges), 3).shape[0])
+    return _lib.ewald_single_contribution(eframework.handle, np.asarray(rest, dtype=np.complex128), positions, charges)

@@ -183,6 +183,12 @@ int ceg_ewald_free(ceg_ewald_h h);
 int ceg_ewald_reciprocal(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms,
                          const double* xyz /* n_pos x n_atoms x 3 Cartesian Å */, const double* q /* n_atoms */,
                          double energy_net_charges, double static_contribution, double* out /* n_pos, K */);
+/* single_contribution_ewald (ewald.jl:704-738) for n_pos trial placements of one molecule — the Ewald half of a
+ * batched Monte-Carlo trial evaluation (montecarlo.jl:563-606).  rest_reim (n_k x 2, host) = framework + all
+ * other adsorbates: StoreRigidChargeFramework + sums[:,1] - sums[:,ij+1].
+ *   out = 2 sum_k kf Re(rest conj S_single) + sum_k kf |S_single|^2 */
+int ceg_ewald_single_contribution(ceg_ewald_h h, const double* rest_reim, int64_t n_pos, int32_t n_atoms,
+                                  const double* xyz, const double* q, double* out);
 int ceg_ewald_reciprocal_dev(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, const double* d_xyz, const double* q_host,
                              double energy_net_charges, double static_contribution, double* d_out, void* stream);
 

@@ -91,6 +91,13 @@ def test_tiled_slab_mfi_synthetic(cuda_lib, orc):
     _check_slab(orc, inp, cset, 10, 14, "mfi")
 
 
+def test_tiled_slab_mof_synthetic(cuda_lib, orc):
+    """C5: 50 Å cubic cell, 5000 atoms of four species, supercell (1,1,1); LJ probe + Coulomb."""
+    inp, cset, fw = wl.synthetic_inputs("mof", 0.8, ("C_ch4",), True)
+    assert len(inp.positions) >= 4900 and inp.supercell == (1, 1, 1)
+    _check_slab(orc, inp, cset, 30, 33, "mof")
+
+
 def test_ragged_slab_uses_every_tile_shape(cuda_lib, orc):
     """13 planes = one 8-plane row + the 4-, and 1-plane tail shapes; 7 planes = 4 + 2 + 1."""
     inp, cset, _ = wl.load_fixture("cha_na")

@@ -176,3 +176,32 @@ def test_energy_grid_reference_testset(cuda_lib, orc):
     v0, c0 = ceg.energy_point(setup, np.zeros((1, 3)))
     assert v0 + c0 == eg[0, 0, 0]
     gv.close(); gc.close()
+
+
+def test_single_contribution_ewald_batched(cuda_lib, orc):
+    """ewald.jl:704-738 batched over trial placements (the Ewald half of a Monte-Carlo trial evaluation):
+    vs the oracle, and the reference's own identity (test/runtests.jl:62-121): the difference of two
+    single contributions equals the difference of the full reciprocal energies."""
+    inp, cset, ex = wl.load_fixture("cha_na")
+    fw = _framework_from_fixture(ex)
+    ef = ceg.initialize_ewald(fw)
+    oe = orc.OracleEwald(fw)
+    q = np.array([-0.3256, 0.6512, -0.3256])
+    geom = np.array([[0, 0, 1.149], [0, 0, 0.0], [0, 0, -1.149]])
+    co2 = ceg.RASPASystem(np.diag([np.inf] * 3), geom, ["O_co2", "C_co2", "O_co2"], np.ones(3), q, True)
+    A = co2.with_positions(geom + [1.3, 2.9, 0.0])
+    B_old = geom + [4.7, 10.1, 0.0]
+    centers = wl.random_positions(fw.mat, 300, 5)
+    trials = centers[:, None, :] + geom[None, :, :]
+    rest = ef.StoreRigidChargeFramework + ceg.adsorbate_sums(ef, q, A.position)      # framework + molecule A
+    got = ceg.single_contribution_ewald(ef, rest, q, trials)
+    # oracle: same k-sum with S_f := rest and no constant terms
+    oe.S = rest
+    want = oe.reciprocal(trials, q, 0.0, 0.0)
+    assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    # identity: E(A, B_new) - E(A, B_old) == single(B_new) - single(B_old)
+    old = ceg.single_contribution_ewald(ef, rest, q, B_old[None])[0]
+    for i in (0, 17, 123):
+        e_new = ceg.compute_ewald(ef, ([A, co2.with_positions(trials[i])],))
+        e_old = ceg.compute_ewald(ef, ([A, co2.with_positions(B_old)],))
+        assert abs((e_new - e_old) - (got[i] - old)) <= 1e-9 * max(abs(e_new), abs(e_old))
