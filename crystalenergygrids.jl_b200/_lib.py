@@ -42,7 +42,7 @@ EXPORTS = [
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
     "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
-    "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_block_upload", "ceg_block_free", "ceg_energy_points",
+    "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
 ]
 
 _lib = None
@@ -329,6 +329,23 @@ def block_upload(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, mask: np.nda
     h = C.c_void_p()
     _check(load().ceg_block_upload(C.c_int32(device), C.byref(cell), C.byref(gs), _p(m, C.c_uint8), C.byref(h)))
     return h
+
+
+def block_from_spheres(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, centers, radius2, nodes) -> np.ndarray:
+    centers = _f64(centers, (-1, 3))
+    radius2 = _f64(radius2, (-1,))
+    mask = np.empty(nodes, dtype=np.uint8)
+    _check(load().ceg_block_from_spheres(C.c_int32(device), C.byref(cell), C.byref(gs), C.c_int32(centers.shape[0]),
+                                         _p(centers, C.c_double), _p(radius2, C.c_double), _p(mask, C.c_uint8)))
+    return mask.astype(bool)
+
+
+def block_from_values(device: int, gs: ceg_gridspec_t, values: np.ndarray, threshold: float) -> np.ndarray:
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    mask = np.empty(v.shape, dtype=np.uint8)
+    _check(load().ceg_block_from_values(C.c_int32(device), C.byref(gs), _p(v, C.c_float), C.c_float(threshold),
+                                        _p(mask, C.c_uint8)))
+    return mask.astype(bool)
 
 
 def block_free(h):

@@ -102,38 +102,39 @@ class BlockFile:
         return bool(self.block[a - 1, b - 1, c - 1])
 
 
-def parse_blockfile(file, csetup: GridCoordinatesSetup) -> BlockFile:
-    """coordinates.jl:112-167 — blocking spheres projected on the grid nodes.
-
-    Host-side setup step (runs once per framework); the per-position lookup is done on the
-    device inside ceg_energy_points.
-    """
+def read_blockfile(file, csetup: GridCoordinatesSetup):
+    """Text part of parse_blockfile (coordinates.jl:113-135): sphere centres mapped through
+    inverse_offsetpoint(offsetpoint(.)) and squared radii."""
     with open(file) as f:
         lines = f.read().splitlines()
     num = int(lines[0].split()[0])
-    if num == 0:
-        return BlockFile(csetup)
-    a, b, c = csetup.nodes
-    mat = csetup.cell.mat
-    invmat = csetup.cell.invmat
-    ortho, safemin = prepare_periodic_distance_computations(mat)
-    safemin2 = safemin * safemin
-    block = np.zeros((a, b, c), dtype=bool)
-    ii, jj, kk = np.meshgrid(np.arange(1, a + 1), np.arange(1, b + 1), np.arange(1, c + 1), indexing="ij")
-    nodes = inverse_offsetpoint(np.stack([ii, jj, kk], axis=-1), csetup)
+    centers, radius2 = [], []
     for l in lines[1:1 + num]:
         sl = l.split()
         radius = float(sl[-1])
-        _center = mat @ np.array([float(x) for x in sl[:3]])
-        ofscenter = offsetpoint(_center, csetup)
-        center = inverse_offsetpoint(ofscenter, csetup)
-        d2 = _periodic_distance2(center - nodes, mat, invmat, ortho, safemin2)
-        block |= d2 < radius * radius
-    return BlockFile.from_mask(csetup, block)
+        _center = csetup.cell.mat @ np.array([float(x) for x in sl[:3]])
+        centers.append(inverse_offsetpoint(offsetpoint(_center, csetup), csetup))
+        radius2.append(radius * radius)
+    return np.array(centers, dtype=np.float64).reshape(-1, 3), np.array(radius2, dtype=np.float64)
+
+
+def parse_blockfile(file, csetup: GridCoordinatesSetup, device: int = 0) -> BlockFile:
+    """coordinates.jl:112-167 — blocking spheres projected on the grid nodes (ceg_block_from_spheres)."""
+    from . import _lib
+    from .cell import flat
+    centers, radius2 = read_blockfile(file, csetup)
+    if len(radius2) == 0:
+        return BlockFile(csetup)
+    ortho, safemin = prepare_periodic_distance_computations(csetup.cell.mat)
+    cell = _lib.make_cell(flat(csetup.cell.mat), flat(csetup.cell.invmat), ortho, safemin * safemin)
+    mask = _lib.block_from_spheres(device, cell, _lib.make_gridspec(csetup), centers, radius2, csetup.nodes)
+    return BlockFile.from_mask(csetup, mask)
 
 
 def _periodic_distance2(buffer, mat, invmat, ortho, safemin2):
-    """utils.jl:210-246, vectorised; returns squared distances only."""
+    """utils.jl:210-246, vectorised; returns squared distances only.  Host helper for the O(atoms^2)
+    intramolecular terms of the EwaldContext constructor (ewald.jl:516-525); grid-sized work goes
+    through the device."""
     f = buffer @ invmat.T
     f = f + 0.5
     f = f - np.floor(f) - 0.5
@@ -161,18 +162,9 @@ def _periodic_distance2(buffer, mat, invmat, ortho, safemin2):
     return out
 
 
-def blockfile_from_grid(g) -> BlockFile:
-    """grids.jl:188-204 — voxel-dilated mask of VdW nodes whose value exceeds 5e6 K.
-
-    ``g.grid`` has the reference layout [channel][x][y][z] (z fastest).
-    """
-    a, b, c = g.csetup.nodes
-    v = g.grid[0]  # (nx, ny, nz)
-    hot = np.zeros((a, b, c), dtype=bool)
-    hot[:a - 1, :b - 1, :c - 1] = v[:a - 1, :b - 1, :c - 1] > 5e6
-    block = np.zeros((a, b, c), dtype=bool)
-    for di in (0, 1):
-        for dj in (0, 1):
-            for dk in (0, 1):
-                block[di:, dj:, dk:] |= hot[:a - di, :b - dj, :c - dk]
-    return BlockFile.from_mask(g.csetup, block)
+def blockfile_from_grid(g, device: int = 0) -> BlockFile:
+    """grids.jl:188-204 — voxel-dilated mask of VdW nodes whose value exceeds 5e6 K
+    (ceg_block_from_values).  ``g.grid`` has the reference layout [channel][x][y][z] (z fastest)."""
+    from . import _lib
+    mask = _lib.block_from_values(device, _lib.make_gridspec(g.csetup), g.grid[0], 5e6)
+    return BlockFile.from_mask(g.csetup, mask)

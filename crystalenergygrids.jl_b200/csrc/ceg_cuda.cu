@@ -1019,6 +1019,47 @@ extern "C" int ceg_block_upload(int32_t device, const ceg_cell_t* unitcell, cons
     return 0;
 }
 
+// parse_blockfile's projection of blocking spheres on the grid nodes (coordinates.jl:112-167).
+extern "C" int ceg_block_from_spheres(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs,
+                                      int32_t n_spheres, const double* centers, const double* radius2, uint8_t* mask) {
+    if (!unitcell || !gs || !mask || n_spheres < 0 || (n_spheres > 0 && (!centers || !radius2)))
+        return fail("ceg_block_from_spheres: bad argument");
+    if (use_device(device)) return 1;
+    const int64_t npts = (int64_t)(gs->dims[0] + 1) * (gs->dims[1] + 1) * (gs->dims[2] + 1);
+    DevBuf d_c, d_r, d_m;
+    CEG_CK(d_c.reserve(sizeof(double) * 3 * std::max(1, n_spheres)));
+    CEG_CK(d_r.reserve(sizeof(double) * std::max(1, n_spheres)));
+    CEG_CK(d_m.reserve(npts));
+    if (n_spheres > 0) {
+        CEG_CK(cudaMemcpy(d_c.p, centers, sizeof(double) * 3 * n_spheres, cudaMemcpyHostToDevice));
+        CEG_CK(cudaMemcpy(d_r.p, radius2, sizeof(double) * n_spheres, cudaMemcpyHostToDevice));
+    }
+    block_spheres_kernel<<<148 * 8, 256>>>(to_dev(*unitcell), to_dev(*gs), n_spheres, d_c.as<double>(), d_r.as<double>(),
+                                          d_m.as<uint8_t>());
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    CEG_CK(cudaMemcpy(mask, d_m.p, npts, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// BlockFile(g::EnergyGrid) (grids.jl:188-204) from the value channel [nx][ny][nz] of a VdW grid.
+extern "C" int ceg_block_from_values(int32_t device, const ceg_gridspec_t* gs, const float* values, float threshold,
+                                     uint8_t* mask) {
+    if (!gs || !values || !mask) return fail("ceg_block_from_values: bad argument");
+    if (use_device(device)) return 1;
+    const int nx = gs->dims[0] + 1, ny = gs->dims[1] + 1, nz = gs->dims[2] + 1;
+    const int64_t npts = (int64_t)nx * ny * nz;
+    DevBuf d_v, d_m;
+    CEG_CK(d_v.reserve(sizeof(float) * npts));
+    CEG_CK(d_m.reserve(npts));
+    CEG_CK(cudaMemcpy(d_v.p, values, sizeof(float) * npts, cudaMemcpyHostToDevice));
+    block_from_values_kernel<<<148 * 8, 256>>>(d_v.as<float>(), threshold, nx, ny, nz, d_m.as<uint8_t>());
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    CEG_CK(cudaMemcpy(mask, d_m.p, npts, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int ceg_block_free(ceg_block_h h) {
     if (!h) return 0;
     cudaSetDevice(h->device);

@@ -200,6 +200,55 @@ __global__ void __launch_bounds__(256) interpolate_kernel(const GridDev g, int64
     }
 }
 
+// ---- blocking masks ----------------------------------------------------------------------------------
+// parse_blockfile (coordinates.jl:112-167): node (i,j,k) is blocked if it lies within `radius` of a sphere
+// centre under the reference's periodic distance (utils.jl:210-246, literal).  Node positions are
+// inverse_offsetpoint(i+1,j+1,k+1) = index * delta + shift (coordinates.jl:68-70).
+__global__ void __launch_bounds__(256) block_spheres_kernel(const CellDev uc, const GridSpecDev gs, int n_spheres,
+                                                            const double* __restrict__ centers,
+                                                            const double* __restrict__ radius2, uint8_t* __restrict__ mask) {
+    __shared__ CellDev s_cell;
+    if (threadIdx.x == 0) s_cell = uc;
+    __syncthreads();
+    const int64_t total = (int64_t)gs.n[0] * gs.n[1] * gs.n[2];
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = t;
+        const int k = (int)(n % gs.n[2]); n /= gs.n[2];
+        const int j = (int)(n % gs.n[1]);
+        const int i = (int)(n / gs.n[1]);
+        const double px = xadd(xmul((double)i, gs.delta[0]), gs.shift[0]);
+        const double py = xadd(xmul((double)j, gs.delta[1]), gs.shift[1]);
+        const double pz = xadd(xmul((double)k, gs.delta[2]), gs.shift[2]);
+        uint8_t hit = 0;
+        for (int s = 0; s < n_spheres && !hit; s++) {
+            double b[3] = {xsub(centers[3 * s], px), xsub(centers[3 * s + 1], py), xsub(centers[3 * s + 2], pz)};
+            hit = periodic_distance2_ref(b, s_cell) < radius2[s];
+        }
+        mask[t] = hit;
+    }
+}
+
+// BlockFile(g) (grids.jl:188-204): every node of a cell whose lower corner (i,j,k), i < a-1, j < b-1, k < c-1
+// (0-based), has a value above the threshold is blocked.  One thread per node gathers its 8 candidate corners.
+__global__ void __launch_bounds__(256) block_from_values_kernel(const float* __restrict__ values, float threshold, int nx,
+                                                                int ny, int nz, uint8_t* __restrict__ mask) {
+    const int64_t total = (int64_t)nx * ny * nz;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = t;
+        const int k = (int)(n % nz); n /= nz;
+        const int j = (int)(n % ny);
+        const int i = (int)(n / ny);
+        uint8_t hit = 0;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int ii = i - ((c >> 2) & 1), jj = j - ((c >> 1) & 1), kk = k - (c & 1);
+            if (ii >= 0 && jj >= 0 && kk >= 0 && ii < nx - 1 && jj < ny - 1 && kk < nz - 1)
+                hit |= values[((int64_t)ii * ny + jj) * nz + kk] > threshold;
+        }
+        mask[t] = hit;
+    }
+}
+
 // ---- fused energy_point (grids.jl:311-318): block test + VdW and Coulomb interpolation ------------
 constexpr int EP_MAX_VDW = 8;
 struct EnergyPointsParams {

@@ -203,6 +203,14 @@ int ceg_ewald_reciprocal_dev(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, cons
 int ceg_block_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs,
                      const uint8_t* mask, ceg_block_h* out);
 int ceg_block_free(ceg_block_h h);
+/* parse_blockfile (coordinates.jl:112-167): mask[(a*ny+b)*nz+c] = 1 if node (a,b,c) lies within radius of a
+ * blocking sphere under the reference's periodic distance.  centers: n x 3 Cartesian Å, already passed
+ * through inverse_offsetpoint(offsetpoint(.)) by the caller (coordinates.jl:131-134); radius2 = radius^2. */
+int ceg_block_from_spheres(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, int32_t n_spheres,
+                           const double* centers, const double* radius2, uint8_t* mask);
+/* BlockFile(g::EnergyGrid) (grids.jl:188-204): voxel-dilated mask of the nodes whose VdW value exceeds
+ * `threshold` (5e6 K); values = channel 0 of the grid, [nx][ny][nz]. */
+int ceg_block_from_values(int32_t device, const ceg_gridspec_t* gs, const float* values, float threshold, uint8_t* mask);
 int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, ceg_ewald_h ewald, ceg_block_h block,
                       int64_t n_pos, int32_t n_atoms, const int32_t* atomsidx /* n_atoms, 0-based into vdw[] */,
                       const double* charges /* n_atoms */, const double* xyz /* n_pos x n_atoms x 3 */,

@@ -293,3 +293,33 @@ def compute_ewald(oe: OracleEwald, systems) -> float:
     """compute_ewald(eframework, systems) (ewald.jl:579-581)."""
     ctx = ceg.ewald_context(oe.as_framework(), systems)
     return float(oe.reciprocal(ctx.positions[None], ctx.charges, ctx.energy_net_charges, ctx.static_contribution)[0])
+
+
+# ---- blocking masks ---------------------------------------------------------------------------------------
+def parse_blockfile(file, cset) -> np.ndarray:
+    """coordinates.jl:112-167 restated with numpy: boolean mask [nx][ny][nz]."""
+    from ceg_b200.coordinates import _periodic_distance2, inverse_offsetpoint, read_blockfile
+    centers, radius2 = read_blockfile(file, cset)
+    a, b, c = cset.nodes
+    mask = np.zeros((a, b, c), dtype=bool)
+    if len(radius2) == 0:
+        return mask
+    ortho, safemin = ceg.prepare_periodic_distance_computations(cset.cell.mat)
+    ii, jj, kk = np.meshgrid(np.arange(1, a + 1), np.arange(1, b + 1), np.arange(1, c + 1), indexing="ij")
+    nodes = inverse_offsetpoint(np.stack([ii, jj, kk], axis=-1), cset)
+    for ctr, r2 in zip(centers, radius2):
+        mask |= _periodic_distance2(ctr - nodes, cset.cell.mat, cset.cell.invmat, ortho, safemin * safemin) < r2
+    return mask
+
+
+def blockfile_from_values(values: np.ndarray, threshold: float = 5e6) -> np.ndarray:
+    """grids.jl:188-204 restated with numpy."""
+    a, b, c = values.shape
+    hot = np.zeros((a, b, c), dtype=bool)
+    hot[:a - 1, :b - 1, :c - 1] = values[:a - 1, :b - 1, :c - 1] > threshold
+    block = np.zeros((a, b, c), dtype=bool)
+    for di in (0, 1):
+        for dj in (0, 1):
+            for dk in (0, 1):
+                block[di:, dj:, dk:] |= hot[:a - di, :b - dj, :c - dk]
+    return block

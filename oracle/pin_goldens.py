@@ -124,9 +124,14 @@ def main():
     # ---- blocking sphere across a periodic boundary (runtests.jl:269-272) -------------------------
     fw4 = ceg.load_framework_RASPA("CIT7block", ffname)
     cset4 = ceg.GridCoordinatesSetup.from_cell(fw4.mat, 0.15)
-    blk = ceg.parse_blockfile(os.path.join(REF_RASPA, "structures", "block", "CIT7block.block"), cset4)
+    blockpath = os.path.join(REF_RASPA, "structures", "block", "CIT7block.block")
+    blk = ceg.BlockFile.from_mask(cset4, orc.parse_blockfile(blockpath, cset4))
     b1 = blk[np.array([12.5, 0.8, 0.3])]
     b2 = blk[np.array([20.175808361078516, 10.58027451750961, 9.185277912816744])]
+    if args.write:
+        ctr, r2 = ceg.coordinates.read_blockfile(blockpath, cset4)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "cit7block.npz"), unit_mat=fw4.mat, spacing=0.15, centers=ctr, radius2=r2,
+                            blocked_points=np.array([[12.5, 0.8, 0.3], [20.175808361078516, 10.58027451750961, 9.185277912816744]]))
     results["cit7block_blocked"] = [bool(b1), bool(b2)]
     assert b1 and b2, "blocking-sphere golden failed"
 

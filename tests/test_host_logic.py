@@ -97,17 +97,15 @@ def test_grid_file_roundtrip(tmp_path):
     assert ceg.parse_grid(tmp_path / "short.grid", False, cset.cell.mat).grid.shape == (8, nx, ny, nz)
 
 
-def test_blockfile_from_grid():
-    cset = ceg.GridCoordinatesSetup.from_cell(np.diag([3.0, 3.0, 3.0]), 0.5)
-    nx, ny, nz = cset.nodes
-    g = np.zeros((8, nx, ny, nz), dtype=np.float32)
-    g[0, 2, 3, 1] = 6e6
-    eg = ceg.EnergyGrid(cset, (1, 1, 1), math.inf, True, g)
-    b = ceg.blockfile_from_grid(eg)
-    assert b.block.sum() == 8 and b.block[2:4, 3:5, 1:3].all()
-    g[0, 2, 3, 1] = 0
-    g[0, nx - 1, 0, 0] = 6e6        # last node along x is not scanned (grids.jl:191)
-    assert ceg.blockfile_from_grid(ceg.EnergyGrid(cset, (1, 1, 1), math.inf, True, g)).empty
+def test_blockfile_from_values_oracle(orc):
+    """grids.jl:188-204 (oracle restatement; the product computes it on the device)."""
+    v = np.zeros((7, 7, 7), dtype=np.float32)
+    v[2, 3, 1] = 6e6
+    b = orc.blockfile_from_values(v)
+    assert b.sum() == 8 and b[2:4, 3:5, 1:3].all()
+    v[2, 3, 1] = 0
+    v[6, 0, 0] = 6e6        # last node along x is not scanned (grids.jl:191)
+    assert not orc.blockfile_from_values(v).any()
 
 
 def test_pair_table_flattening():
