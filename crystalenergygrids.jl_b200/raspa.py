@@ -483,6 +483,34 @@ def retrieve_or_create_grid(grid_path, syst_framework, forcefield, gridstep, ato
     return parse_grid(grid_path, iscoulomb, mat)
 
 
+def _create_missing_grids_fused(syst_framework, forcefield, gridstep, cutoff, new, devices, coulomb_path, ewald,
+                                vdw_atoms_paths):
+    """Create the `.grid` files of one setup that do not exist yet (or all of them if `new`), fusing
+    up to four VdW probes and the Coulomb grid per pass (grids.jl:137-185 writes them one by one)."""
+    from .grids import build_grids, write_grid
+    if cutoff != 12.0:
+        raise ValueError("Cutoff other than 12 Å or infinity is not supported.")
+    todo_vdw = [(a, p) for a, p in vdw_atoms_paths if p and (new or not os.path.isfile(p))]
+    todo_coul = bool(coulomb_path) and (new or not os.path.isfile(coulomb_path))
+    if not todo_vdw and not todo_coul:
+        return
+    num_vdw = find_supercell(syst_framework.mat, forcefield.cutoff)
+    num_coul = find_supercell(syst_framework.mat, CUTOFF_COULOMB)
+    first = True
+    while todo_vdw or (todo_coul and first):
+        batch, todo_vdw = todo_vdw[:4], todo_vdw[4:]
+        with_coul = todo_coul and first
+        cset, grids, _ = build_grids(syst_framework, forcefield, gridstep, atoms=tuple(a for a, _ in batch),
+                                     coulomb=with_coul, alpha=ewald.alpha if with_coul else 0.0, devices=devices)
+        for (a, p), g in zip(batch, grids):
+            os.makedirs(os.path.dirname(p), exist_ok=True)
+            write_grid(p, cset, num_vdw, g)
+        if with_coul:
+            os.makedirs(os.path.dirname(coulomb_path), exist_ok=True)
+            write_grid(coulomb_path, cset, num_coul, grids[-1], ewald_precision=ewald.precision)
+        first = False
+
+
 def setup_RASPA(framework, pff, molecule, ffname_molecule: str | None = None, *, gridstep: float = 0.15,
                 supercell=None, blockfile=None, new: bool = False, cutoff: float = 12.0, grids_root: str | None = None,
                 devices=None):
@@ -512,8 +540,16 @@ def setup_RASPA(framework, pff, molecule, ffname_molecule: str | None = None, *,
     coulomb_grid_path, vdws = grid_locations(framework, pff, forcefield, rev_atomdict, gridstep, supercell, grids_root)
 
     needcoulomb = bool(np.any(syst_mol.atomic_charge != 0))
+    ewald = initialize_ewald(syst_framework, supercell) if needcoulomb else None
+    if isinstance(framework, str) and not math.isinf(cutoff):
+        # Every missing grid of this setup is built in fused passes over the framework atoms (up to four
+        # VdW probes + the Coulomb grid share one distance computation), instead of one pass per grid as
+        # the loop below would do through retrieve_or_create_grid; the files written are the same.
+        _create_missing_grids_fused(syst_framework, forcefield, gridstep, cutoff, new, devices,
+                                    coulomb_grid_path if needcoulomb else None, ewald,
+                                    [(a, p) for a, p in zip(rev_atomdict, vdws) if FF.needsvdwgrid(forcefield, a)])
+        new = False
     if needcoulomb:
-        ewald = initialize_ewald(syst_framework, supercell)
         if not isinstance(framework, str):
             coulomb = EnergyGrid.zero()
         else:
