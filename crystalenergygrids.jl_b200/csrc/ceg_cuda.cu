@@ -123,6 +123,10 @@ struct ceg_probe_s {
     // scratch for host-facing builds
     DevBuf d_out, d_raw, d_pos, d_der;
     int64_t last_points = 0;
+    ~ceg_probe_s() {
+        if (s_compute) cudaStreamDestroy(s_compute);
+        if (s_copy) cudaStreamDestroy(s_copy);
+    }
 };
 
 struct ceg_grid_s {
@@ -131,6 +135,10 @@ struct ceg_grid_s {
     cudaStream_t stream = nullptr, stream2 = nullptr;   // ping-pong pair for the pipelined host path
     GridDev g;
     DevBuf d_nodes, d_xyz[2], d_out[2];
+    ~ceg_grid_s() {
+        if (stream) cudaStreamDestroy(stream);
+        if (stream2) cudaStreamDestroy(stream2);
+    }
 };
 
 struct ceg_ewald_s {
@@ -141,6 +149,9 @@ struct ceg_ewald_s {
     int kmax[3];
     int64_t n_k = 0;
     DevBuf d_kv, d_xyz, d_out, d_q;
+    ~ceg_ewald_s() {
+        if (stream) cudaStreamDestroy(stream);
+    }
 };
 
 struct ceg_block_s {
@@ -364,6 +375,7 @@ extern "C" int ceg_probe_create(int32_t device, const ceg_cell_t* supercell, int
             d.hs_r2 = s.hs_r * s.hs_r;
             d.lj_eps = s.lj_eps; d.lj_sig2 = s.lj_sigma * s.lj_sigma; d.lj_shift = s.lj_shift;
             d.bA = s.buck_A; d.bB = s.buck_B; d.bC = s.buck_C; d.b_shift = s.buck_shift;
+            d.bB2 = s.buck_B * s.buck_B;
             if (s.flags & CEG_PAIR_HS) h->max_hs_r2 = std::max(h->max_hs_r2, d.hs_r2);
         }
     CEG_CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
@@ -387,8 +399,6 @@ extern "C" int ceg_probe_create(int32_t device, const ceg_cell_t* supercell, int
 extern "C" int ceg_probe_free(ceg_probe_h h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    if (h->s_compute) cudaStreamDestroy(h->s_compute);
-    if (h->s_copy) cudaStreamDestroy(h->s_copy);
     delete h;
     return 0;
 }
@@ -478,7 +488,6 @@ static cudaError_t launch_tiled(const BuildParams& P, int n_tiles, cudaStream_t 
 // is not a multiple of its x extent finishes with flatter shapes of the same thread count (x extent 4, 2,
 // 1), so that no CTA carries idle planes and x-slabs of any size stay balanced across GPUs.
 struct TileShape { int tx, ty, tz; };
-static int threads_per_tile(int n_probes) { return n_probes <= 2 ? 512 : 256; }
 static TileShape tile_shape_for(int n_probes, int tx) {
     if (n_probes <= 2) {
         switch (tx) { case 8: return {8, 8, 8}; case 4: return {4, 8, 16}; case 2: return {2, 16, 16}; default: return {1, 16, 32}; }
@@ -776,8 +785,6 @@ extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const
 extern "C" int ceg_grid_free(ceg_grid_h h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamDestroy(h->stream);
-    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
     return 0;
 }
@@ -907,7 +914,6 @@ extern "C" int ceg_ewald_create(int32_t device, const double* invmat, const int3
 extern "C" int ceg_ewald_free(ceg_ewald_h h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
 }

@@ -11,7 +11,7 @@
 
 namespace ceg {
 
-// 1/sqrt(s), s > 0 normal: MUFU.RSQ64H seed (~2^-22) + one third-order step -> ~2^-60.
+// 1/sqrt(s), s > 0 normal: MUFU.RSQ64H seed (~2^-19) + one third-order step -> ~1e-16.
 __device__ __forceinline__ double rsqrt_fast(double s) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
@@ -21,7 +21,8 @@ __device__ __forceinline__ double rsqrt_fast(double s) {
     return fma(ye, t, y);                           // y (1 + e/2 + 3 e^2/8)
 }
 
-// 1/d, d > 0 normal: MUFU.RCP64H seed + one third-order step.
+// 1/d, d > 0 normal: MUFU.RCP64H seed (measured ~2^-19) + one third-order step -> ~1e-17.
+// (A plain Newton step leaves 3e-12, measured — not enough for erfcx_fast.)
 __device__ __forceinline__ double rcp_fast(double d) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));

@@ -34,6 +34,7 @@ struct PairDev {
     double hs_r2;
     double lj_eps, lj_sig2, lj_shift;
     double bA, bB, bC, b_shift;
+    double bB2;        // B^2
 };
 
 constexpr int MAX_GRIDS = 5;       // up to 4 fused VdW probes + Coulomb per pass
@@ -122,7 +123,7 @@ __device__ __forceinline__ void buck_terms(const PairDev& p, const PairGeom& g, 
     const double BX = B * X;
     const double y = BX * g.ir;
     const double d2x = fma(B, BX, y) * g.ir2;
-    const double d3x = fma(3.0, d2x, (B * B) * y) * g.ir2;       // = -D^3 X
+    const double d3x = fma(3.0, d2x, p.bB2 * y) * g.ir2;        // = -D^3 X
     const double ir4 = g.ir2 * g.ir2;
     const double x6 = p.bC * (ir4 * g.ir2);
     const double x8 = x6 * g.ir2, x10 = x8 * g.ir2, x12 = x10 * g.ir2;
