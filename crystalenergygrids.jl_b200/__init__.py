@@ -12,6 +12,8 @@ from .cell import (CellMatrix, cell_parameters, find_supercell, flat, inv3, mat_
 from .constants import COULOMBIC_CONVERSION_FACTOR, GRID_TO_KELVIN
 from .coordinates import (BlockFile, GridCoordinatesSetup, abc_to_xyz, blockfile_from_grid, inverse_offsetpoint,
                           offsetpoint, parse_blockfile, wrap_atom)
+from .energy import (GuestEnvironment, compute_vdw, flatten_pair_energy, movement_energies, pair_energy_dtype,
+                     pair_energy_table, single_contribution_vdw)
 from .ewald import (EwaldContext, EwaldFramework, EwaldKspace, adsorbate_sums, build_kfactors, build_kspace, compute_ewald,
                     single_contribution_ewald,
                     ewald_context, ewald_parameters, framework_sites, initialize_ewald)

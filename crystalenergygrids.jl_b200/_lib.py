@@ -42,7 +42,7 @@ EXPORTS = [
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
     "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
-    "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
+    "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
 ]
 
 _lib = None
@@ -321,6 +321,26 @@ def ewald_reciprocal_dev(h, n_pos: int, q, d_xyz: int, energy_net_charges, stati
                                            _p(q, C.c_double), C.c_double(energy_net_charges),
                                            C.c_double(static_contribution), C.c_void_p(int(d_out)),
                                            C.c_void_p(int(stream))))
+
+
+# ---- guest-guest pair energies -----------------------------------------------------------------------
+def guest_energy(device: int, cell: ceg_cell_t, cutoff2: float, table: np.ndarray, env_xyz, env_species, env_mol,
+                 mol_species, skip_mol: int, trial_xyz) -> np.ndarray:
+    table = np.ascontiguousarray(table)
+    assert table.ndim == 2 and table.shape[0] == table.shape[1] and table.dtype.itemsize == 96
+    env_xyz = _f64(env_xyz, (-1, 3))
+    env_species = np.ascontiguousarray(env_species, dtype=np.int32)
+    env_mol = np.ascontiguousarray(env_mol, dtype=np.int32)
+    mol_species = np.ascontiguousarray(mol_species, dtype=np.int32)
+    na = mol_species.shape[0]
+    trial_xyz = _f64(trial_xyz, (-1, na, 3))
+    out = np.empty(trial_xyz.shape[0], dtype=np.float64)
+    _check(load().ceg_guest_energy(C.c_int32(device), C.byref(cell), C.c_double(cutoff2), C.c_int32(table.shape[0]),
+                                   C.c_void_p(table.ctypes.data), C.c_int64(env_xyz.shape[0]), _p(env_xyz, C.c_double),
+                                   _p(env_species, C.c_int32), _p(env_mol, C.c_int32), C.c_int64(trial_xyz.shape[0]),
+                                   C.c_int32(na), _p(mol_species, C.c_int32), C.c_int32(skip_mol),
+                                   _p(trial_xyz, C.c_double), _p(out, C.c_double)))
+    return out
 
 
 # ---- block mask + fused evaluation -----------------------------------------------------------------

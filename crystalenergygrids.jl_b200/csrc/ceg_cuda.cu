@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "ewald.cuh"
 #include "grid_build.cuh"
+#include "guest.cuh"
 #include "interp.cuh"
 
 namespace ceg {
@@ -1003,6 +1004,63 @@ extern "C" int ceg_ewald_single_contribution(ceg_ewald_h h, const double* rest_r
         return 1;
     CEG_CK(cudaMemcpyAsync(out, h->d_out.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, h->stream));
     CEG_CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ================================================================================================
+// guest-guest pair energies (energy.jl:339-427)
+// ================================================================================================
+extern "C" int ceg_guest_energy(int32_t device, const ceg_cell_t* cell, double cutoff2, int32_t n_species,
+                                const ceg_pair_energy_t* table, int64_t n_env, const double* env_xyz,
+                                const int32_t* env_species, const int32_t* env_mol, int64_t n_trials, int32_t n_atoms,
+                                const int32_t* mol_species, int32_t skip_mol, const double* trial_xyz, double* out) {
+    if (!cell || n_species <= 0 || !table || n_env < 0 || n_trials < 0 || n_atoms <= 0 || !mol_species ||
+        (n_env > 0 && (!env_xyz || !env_species || !env_mol)) || (n_trials > 0 && (!trial_xyz || !out)))
+        return fail("ceg_guest_energy: bad argument");
+    if (n_env > (1ll << 30)) return fail("ceg_guest_energy: too many environment atoms");
+    for (int64_t i = 0; i < n_env; i++)
+        if (env_species[i] < 0 || env_species[i] >= n_species) return fail("ceg_guest_energy: species out of range");
+    for (int a = 0; a < n_atoms; a++)
+        if (mol_species[a] < 0 || mol_species[a] >= n_species) return fail("ceg_guest_energy: species out of range");
+    for (int i = 0; i < n_species * n_species; i++)
+        if (table[i].flags < 0) return fail("Undefined interaction");
+    if (n_trials == 0) return 0;
+    if (use_device(device)) return 1;
+    std::vector<PairEnergyDev> tab((size_t)n_species * n_species);
+    for (size_t i = 0; i < tab.size(); i++) {
+        const ceg_pair_energy_t& s = table[i];
+        PairEnergyDev& d = tab[i];
+        d.flags = s.flags; d._pad = 0;
+        d.hs_r2 = s.hs_r * s.hs_r;
+        d.lj_eps = s.lj_eps; d.lj_sig2 = s.lj_sigma * s.lj_sigma; d.lj_shift = s.lj_shift;
+        d.bA = s.buck_A; d.bB = s.buck_B; d.bC = s.buck_C; d.b_shift = s.buck_shift;
+        d.ew_alpha = s.ewald_alpha; d.ew_qq = s.ewald_qq; d.coul_qq = s.coulomb_qq;
+    }
+    DevBuf d_tab, d_exyz, d_esp, d_emol, d_msp, d_txyz, d_out;
+    CEG_CK(d_tab.reserve(sizeof(PairEnergyDev) * tab.size()));
+    CEG_CK(d_exyz.reserve(sizeof(double) * 3 * std::max<int64_t>(1, n_env)));
+    CEG_CK(d_esp.reserve(sizeof(int) * std::max<int64_t>(1, n_env)));
+    CEG_CK(d_emol.reserve(sizeof(int) * std::max<int64_t>(1, n_env)));
+    CEG_CK(d_msp.reserve(sizeof(int) * n_atoms));
+    CEG_CK(d_txyz.reserve(sizeof(double) * 3 * n_atoms * n_trials));
+    CEG_CK(d_out.reserve(sizeof(double) * n_trials));
+    CEG_CK(cudaMemcpy(d_tab.p, tab.data(), sizeof(PairEnergyDev) * tab.size(), cudaMemcpyHostToDevice));
+    if (n_env > 0) {
+        CEG_CK(cudaMemcpy(d_exyz.p, env_xyz, sizeof(double) * 3 * n_env, cudaMemcpyHostToDevice));
+        CEG_CK(cudaMemcpy(d_esp.p, env_species, sizeof(int) * n_env, cudaMemcpyHostToDevice));
+        CEG_CK(cudaMemcpy(d_emol.p, env_mol, sizeof(int) * n_env, cudaMemcpyHostToDevice));
+    }
+    CEG_CK(cudaMemcpy(d_msp.p, mol_species, sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
+    CEG_CK(cudaMemcpy(d_txyz.p, trial_xyz, sizeof(double) * 3 * n_atoms * n_trials, cudaMemcpyHostToDevice));
+    GuestParams P;
+    P.cell = to_dev(*cell); P.cutoff2 = cutoff2; P.n_species = n_species; P.table = d_tab.as<PairEnergyDev>();
+    P.n_env = (int)n_env; P.env_xyz = d_exyz.as<double>(); P.env_species = d_esp.as<int>(); P.env_mol = d_emol.as<int>();
+    P.n_trials = n_trials; P.n_atoms = n_atoms; P.mol_species = d_msp.as<int>(); P.skip_mol = skip_mol;
+    P.trial_xyz = d_txyz.as<double>(); P.out = d_out.as<double>();
+    guest_energy_kernel<<<(unsigned)((n_trials + 127) / 128), 128>>>(P);
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    CEG_CK(cudaMemcpy(out, d_out.p, sizeof(double) * n_trials, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -282,8 +282,10 @@ class CrystalEnergySetup:
                 pass
 
 
-def energy_points(setup: CrystalEnergySetup, positions):
-    """Batched energy_point: positions (n_pos, n_atoms, 3) -> (vdw[n_pos], coulomb[n_pos])."""
+def energy_points(setup: CrystalEnergySetup, positions, reciprocal: bool = True):
+    """Batched energy_point: positions (n_pos, n_atoms, 3) -> (vdw[n_pos], coulomb[n_pos]).
+    With reciprocal=False the Coulomb part is only the interpolated real-space grid term, i.e.
+    framework_interactions of the Monte-Carlo loop (montecarlo.jl:490-504)."""
     na = len(setup.atomsidx)
     pos = np.asarray(positions, dtype=np.float64).reshape(-1, na, 3)
     for g in setup.grids:
@@ -293,7 +295,7 @@ def energy_points(setup: CrystalEnergySetup, positions):
     has_coulomb = setup.coulomb.ewald_precision != -math.inf
     coul = setup.coulomb.handle if has_coulomb else None
     ew, enc, static = None, 0.0, 0.0
-    if has_coulomb and setup.ewald.alpha != 0:
+    if has_coulomb and reciprocal and setup.ewald.alpha != 0:
         ctx = setup.ewald_ctx()
         ew, enc, static = setup.ewald.handle, ctx.energy_net_charges, ctx.static_contribution
     return _lib.energy_points(vdw_handles, coul, ew, setup.block_handle(), setup.atomsidx, setup.charges, pos, enc, static)

@@ -68,6 +68,21 @@ typedef struct ceg_pair_t {
     double buck_A, buck_B, buck_C, buck_shift;
 } ceg_pair_t;
 
+/* One (species, species) entry of ForceField.interactions as seen by the ENERGY call rule(d^2)
+ * (interactions.jl:367-409) between guest atoms: ceg_pair_t's terms plus the real-space Ewald term
+ * CoulombEwaldDirect (raspa.jl:688-700) and bare Coulomb.  qq = COULOMBIC_CONVERSION_FACTOR * q1 * q2. */
+#define CEG_PAIR_EWALD   8
+#define CEG_PAIR_COULOMB 16
+typedef struct ceg_pair_energy_t {
+    int32_t flags;
+    int32_t _pad;
+    double hs_r;
+    double lj_eps, lj_sigma, lj_shift;
+    double buck_A, buck_B, buck_C, buck_shift;
+    double ewald_alpha, ewald_qq;
+    double coulomb_qq;
+} ceg_pair_energy_t;
+
 typedef struct ceg_probe_s* ceg_probe_h;   /* ProbeSystem(s)            probes.jl:12-63   */
 typedef struct ceg_grid_s*  ceg_grid_h;    /* device-resident EnergyGrid grids.jl:10-16   */
 typedef struct ceg_ewald_s* ceg_ewald_h;   /* EwaldFramework            ewald.jl:40-50    */
@@ -191,6 +206,20 @@ int ceg_ewald_single_contribution(ceg_ewald_h h, const double* rest_reim, int64_
                                   const double* xyz, const double* q, double* out);
 int ceg_ewald_reciprocal_dev(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, const double* d_xyz, const double* q_host,
                              double energy_net_charges, double static_contribution, double* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Guest-guest pair energies: single_contribution_vdw_noneighbour (energy.jl:407-427) for n_trials
+ * placements of one molecule (n_atoms atoms of species mol_species) against the n_env atoms of the other
+ * guests; atoms whose molecule id equals skip_mol (the molecule being moved) are ignored.  `cell` is the
+ * simulation cell (distances by unsafe_periodic_distance2!, utils.jl:294-302: wrap only).
+ * out[t] = sum over pairs with d2 < cutoff2 of rule(d2).  Together with ceg_energy_points (framework
+ * grids) and ceg_ewald_single_contribution (reciprocal part) this evaluates movement_energy
+ * (montecarlo.jl:563-606) for a batch of trial moves.
+ * ------------------------------------------------------------------------------------------ */
+int ceg_guest_energy(int32_t device, const ceg_cell_t* cell, double cutoff2, int32_t n_species,
+                     const ceg_pair_energy_t* table /* n_species x n_species */, int64_t n_env, const double* env_xyz,
+                     const int32_t* env_species, const int32_t* env_mol, int64_t n_trials, int32_t n_atoms,
+                     const int32_t* mol_species, int32_t skip_mol, const double* trial_xyz, double* out);
 
 /* ------------------------------------------------------------------------------------------
  * Blocking mask (coordinates.jl:83-101) and fused batched evaluation: energy_point over n_pos

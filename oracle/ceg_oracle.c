@@ -420,6 +420,52 @@ void ceg_o_ewald_reciprocal_batch(const double* invmat, const int32_t* kmax, int
                                         xyz + (size_t)3 * n_atoms * i, q, energy_net_charges, static_contribution);
 }
 
+/* ---- guest-guest pair energies ------------------------------------------------------------------- */
+/* interactions.jl:391-409 rule(d2) (and :367-387 through sqrt), summed in the kind order of
+ * InteractionRuleSum: HardSphere, CoulombEwaldDirect, Coulomb, LennardJones, Buckingham. */
+static double pair_energy(const ceg_pair_energy_t* p, double r2) {
+    double e = 0.0;
+    if (p->flags & CEG_PAIR_HS) e += (r2 < p->hs_r * p->hs_r) ? INFINITY : 0.0;
+    if (p->flags & CEG_PAIR_EWALD) { double r = sqrt(r2); e += p->ewald_qq * erfc(p->ewald_alpha * r) / r; }
+    if (p->flags & CEG_PAIR_COULOMB) { double r = sqrt(r2); e += p->coulomb_qq / r; }
+    if (p->flags & CEG_PAIR_LJ) {
+        double t = (p->lj_sigma * p->lj_sigma) / r2;
+        double x6 = t * t * t;
+        e += 4 * p->lj_eps * x6 * (x6 - 1) - p->lj_shift;
+    }
+    if (p->flags & CEG_PAIR_BUCK) {
+        double r = sqrt(r2);
+        e += (p->buck_A * exp(-p->buck_B * r) - p->buck_C / pow(r, 6)) - p->buck_shift;
+    }
+    return e;
+}
+
+/* energy.jl:407-427 single_contribution_vdw_noneighbour for n_trials placements (rigid molecule). */
+void ceg_o_guest_energy(const ceg_cell_t* cell, double cutoff2, int32_t n_species, const ceg_pair_energy_t* table,
+                        int64_t n_env, const double* env_xyz, const int32_t* env_species, const int32_t* env_mol,
+                        int64_t n_trials, int32_t n_atoms, const int32_t* mol_species, int32_t skip_mol,
+                        const double* trial_xyz, double* out) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t t = 0; t < n_trials; t++) {
+        double energy = 0.0;
+        for (int k2 = 0; k2 < n_atoms; k2++) {
+            const double* p2 = trial_xyz + (t * n_atoms + k2) * 3;
+            for (int64_t l1 = 0; l1 < n_env; l1++) {
+                if (env_mol[l1] == skip_mol) continue;
+                /* utils.jl:294-302 unsafe_periodic_distance2! */
+                double b[3] = {p2[0] - env_xyz[3 * l1], p2[1] - env_xyz[3 * l1 + 1], p2[2] - env_xyz[3 * l1 + 2]};
+                double f[3];
+                matvec(cell->invmat, b, f);
+                for (int d = 0; d < 3; d++) { double diff = f[d] + 0.5; f[d] = diff - floor(diff) - 0.5; }
+                matvec(cell->mat, f, b);
+                double d2 = norm2(b);
+                if (d2 < cutoff2) energy += pair_energy(&table[(size_t)mol_species[k2] * n_species + env_species[l1]], d2);
+            }
+        }
+        out[t] = energy;
+    }
+}
+
 int ceg_o_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -323,3 +323,21 @@ def blockfile_from_values(values: np.ndarray, threshold: float = 5e6) -> np.ndar
             for dk in (0, 1):
                 block[di:, dj:, dk:] |= hot[:a - di, :b - dj, :c - dk]
     return block
+
+
+# ---- guest-guest pair energies ------------------------------------------------------------------------------
+def guest_energy(env, mol_species, trial_positions, skip_molecule=-1) -> np.ndarray:
+    """energy.jl:407-427 batched over trial placements (env: ceg_b200.GuestEnvironment)."""
+    ms = np.ascontiguousarray(mol_species, dtype=np.int32)
+    tp = np.ascontiguousarray(trial_positions, dtype=np.float64).reshape(-1, ms.shape[0], 3)
+    out = np.empty(tp.shape[0])
+    cell = env.cell_struct()
+    tab = np.ascontiguousarray(env.table)
+    exyz = np.ascontiguousarray(env.positions, dtype=np.float64)
+    esp = np.ascontiguousarray(env.species, dtype=np.int32)
+    emol = np.ascontiguousarray(env.molecule, dtype=np.int32)
+    lib().ceg_o_guest_energy(C.byref(cell), C.c_double(float(env.cutoff) ** 2), C.c_int32(tab.shape[0]),
+                             C.c_void_p(tab.ctypes.data), C.c_int64(exyz.shape[0]), _p(exyz, C.c_double), _p(esp, C.c_int32),
+                             _p(emol, C.c_int32), C.c_int64(tp.shape[0]), C.c_int32(ms.shape[0]), _p(ms, C.c_int32),
+                             C.c_int32(skip_molecule), _p(tp, C.c_double), _p(out, C.c_double))
+    return out

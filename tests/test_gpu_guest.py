@@ -1,0 +1,100 @@
+"""GPU parity of the guest–guest pair energies (energy.jl:339-427) and the batched
+Monte-Carlo trial evaluation built from the three device pieces (montecarlo.jl:563-606)."""
+import numpy as np
+import pytest
+
+import ceg_b200 as ceg
+from ceg_b200 import forcefields as FF
+from ceg_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+
+def _forcefield():
+    """CO2 sites + Na+ in a force field with shifted LJ, Buckingham+HardSphere and the real-space Ewald term."""
+    alpha = ceg.raspa.ewald_alpha_forcefield(1e-6, 12.0)
+    q = {"C_co2": 0.6512, "O_co2": -0.3256, "Na": 1.0, "Ar": 0.0}
+    names = list(q)
+    sd = {s: i for i, s in enumerate(names)}
+    inputs = [(("C_co2", "C_co2"), FF.make_rule(ceg.Kind.LennardJones, [28.129, 2.757], True, 12.0)),
+              (("O_co2", "O_co2"), FF.make_rule(ceg.Kind.LennardJones, [80.507, 3.033], True, 12.0)),
+              (("Ar", "Ar"), FF.make_rule(ceg.Kind.LennardJones, [124.07, 3.38], True, 12.0)),
+              (("Na", "Na"), FF.NoInteraction()),
+              (("Na", "O_co2"), ceg.InteractionRuleSum.make([FF.make_rule(ceg.Kind.Buckingham, [5.581e7, 3.985, 9.167e5], False, 12.0),
+                                                             FF.make_rule(ceg.Kind.HardSphere, [1.5, 0.0], False, 12.0)]))]
+    ff = ceg.ForceField.build(inputs, ceg.Mixing.LorentzBerthelot, 12.0, True, False, sdict=sd)
+    for a in names:
+        for b in names:
+            if q[a] != 0 and q[b] != 0:
+                i, j = sd[a], sd[b]
+                ff.interactions[i][j] = FF.sum_rules(ff.interactions[i][j],
+                                                     ceg.InteractionRule(ceg.Kind.CoulombEwaldDirect, (alpha, q[a], q[b]), 0.0, False))
+    return ff, names
+
+
+def _environment(ff, names, n_mol, seed):
+    rng = np.random.default_rng(seed)
+    mat = ceg.mat_from_parameters((26.0, 25.0, 27.0), (88.0, 95.0, 101.0))
+    tab = ceg.pair_energy_table(ff, names)
+    geom = np.array([[0, 0, 1.149], [0, 0, 0.0], [0, 0, -1.149]])
+    pos, sp, mol = [], [], []
+    for m in range(n_mol):
+        c = mat @ rng.random(3)
+        kind = m % 3
+        if kind == 0:       # CO2 with a random orientation
+            a = rng.standard_normal(3); a /= np.linalg.norm(a)
+            pos += [c + 1.149 * a, c, c - 1.149 * a]; sp += [1, 0, 1]; mol += [m] * 3
+        elif kind == 1:
+            pos.append(c); sp.append(2); mol.append(m)   # Na
+        else:
+            pos.append(c); sp.append(3); mol.append(m)   # Ar
+    return ceg.GuestEnvironment(mat, 12.0, tab, np.array(pos), np.array(sp, dtype=np.int32), np.array(mol, dtype=np.int32)), geom
+
+
+def test_single_contribution_vdw_batched(cuda_lib, orc):
+    ff, names = _forcefield()
+    env, geom = _environment(ff, names, 60, 1)
+    assert {int(f) for f in np.unique(env.table["flags"])} >= {0, 2, 8, 10}
+    rng = np.random.default_rng(2)
+    centers = (env.mat @ rng.random((3, 4000))).T
+    trials = centers[:, None, :] + geom[None, :, :]
+    got = ceg.single_contribution_vdw(env, [1, 0, 1], trials, skip_molecule=0)
+    want = orc.guest_energy(env, [1, 0, 1], trials, 0)
+    assert np.array_equal(np.isinf(got), np.isinf(want))
+    fin = np.isfinite(want)
+    assert (np.abs(got[fin] - want[fin]) <= 1e-9 * np.abs(want[fin]) + 1e-6).all()
+    # a Na+ trial: Buckingham + hard sphere + Ewald pairs, some placements inside a hard sphere (Inf)
+    na_trials = np.concatenate([centers[:500, None, :], env.positions[env.species == 1][:20, None, :] + 0.4])
+    got = ceg.single_contribution_vdw(env, [2], na_trials, skip_molecule=1)
+    want = orc.guest_energy(env, [2], na_trials, 1)
+    assert np.isinf(want).any() and np.array_equal(np.isinf(got), np.isinf(want))
+    fin = np.isfinite(want)
+    assert (np.abs(got[fin] - want[fin]) <= 1e-9 * np.abs(want[fin]) + 1e-6).all()
+
+
+def test_compute_vdw_and_move_identity(cuda_lib, orc):
+    """compute_vdw (energy.jl:339-385) and the identity the Monte-Carlo loop relies on: moving molecule m
+    changes the total by single(new) - single(old)."""
+    ff, names = _forcefield()
+    env, geom = _environment(ff, names, 45, 3)
+    total = ceg.compute_vdw(env)
+    # oracle: explicit double loop over pairs of different molecules
+    ref = 0.5 * sum(orc.guest_energy(env, env.species[env.molecule == m], env.positions[env.molecule == m][None], int(m))[0]
+                    for m in np.unique(env.molecule))
+    assert np.isfinite(total) and abs(total - ref) <= 1e-9 * abs(ref) + 1e-6
+    m = 6                                                # a CO2 molecule (6 % 3 == 0)
+    sel = env.molecule == m
+    new = env.positions[sel] + np.array([1.3, -0.7, 2.1])
+    old_c = ceg.single_contribution_vdw(env, env.species[sel], env.positions[sel][None], m)[0]
+    new_c = ceg.single_contribution_vdw(env, env.species[sel], new[None], m)[0]
+    import dataclasses
+    pos2 = env.positions.copy(); pos2[sel] = new
+    total2 = ceg.compute_vdw(dataclasses.replace(env, positions=pos2))
+    assert abs((total2 - total) - (new_c - old_c)) <= 1e-9 * max(abs(total), abs(total2)) + 1e-6
+    # more than one shared-memory tile of environment atoms
+    big, _ = _environment(ff, names, 1500, 5)
+    assert len(big.positions) > 2048
+    t = (big.mat @ np.random.default_rng(0).random((3, 300))).T[:, None, :]
+    g = ceg.single_contribution_vdw(big, [3], t, -1)
+    w = orc.guest_energy(big, [3], t, -1)
+    assert (np.abs(g - w) <= 1e-9 * np.abs(w) + 1e-6).all()
