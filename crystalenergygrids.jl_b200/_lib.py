@@ -13,7 +13,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libceg_cuda.so")
+# CEG_LIB_PATH: a differently-compiled libceg_cuda.so for kernel experiments (tools/); same ABI, still CUDA only
+LIB_PATH = os.environ.get("CEG_LIB_PATH") or os.path.join(_HERE, "libceg_cuda.so")
 
 c_int32_p = C.POINTER(C.c_int32)
 c_int64_p = C.POINTER(C.c_int64)

@@ -375,6 +375,7 @@ extern "C" int ceg_probe_create(int32_t device, const ceg_cell_t* supercell, int
             d.flags = s.flags; d._pad = 0;
             d.hs_r2 = s.hs_r * s.hs_r;
             d.lj_eps = s.lj_eps; d.lj_sig2 = s.lj_sigma * s.lj_sigma; d.lj_shift = s.lj_shift;
+            { const double s6 = d.lj_sig2 * d.lj_sig2 * d.lj_sig2; d.lj_c6 = 4.0 * s.lj_eps * s6; d.lj_c12 = d.lj_c6 * s6; }
             d.bA = s.buck_A; d.bB = s.buck_B; d.bC = s.buck_C; d.b_shift = s.buck_shift;
             d.bB2 = s.buck_B * s.buck_B;
             if (s.flags & CEG_PAIR_HS) h->max_hs_r2 = std::max(h->max_hs_r2, d.hs_r2);
@@ -489,13 +490,20 @@ static cudaError_t launch_tiled(const BuildParams& P, int n_tiles, cudaStream_t 
 // is not a multiple of its x extent finishes with flatter shapes of the same thread count (x extent 4, 2,
 // 1), so that no CTA carries idle planes and x-slabs of any size stay balanced across GPUs.
 struct TileShape { int tx, ty, tz; };
+#ifndef CEG_BUILD_NT
+#define CEG_BUILD_NT 256       // threads per CTA of the <= 2 probe variants
+#endif
+static int build_nt(int n_probes) { return n_probes <= 2 ? CEG_BUILD_NT : 256; }
+static int main_tx(int n_probes) { return build_nt(n_probes) / 64; }
+// tx x 8 x 8 nodes, the remaining factor of the thread count going to z and y alternately:
+// 512 threads: {8,8,8} {4,8,16} {2,16,16} {1,16,32};  256: {4,8,8} {2,8,16} {1,16,16};  128: {2,8,8} {1,8,16}
 static TileShape tile_shape_for(int n_probes, int tx) {
-    if (n_probes <= 2) {
-        switch (tx) { case 8: return {8, 8, 8}; case 4: return {4, 8, 16}; case 2: return {2, 16, 16}; default: return {1, 16, 32}; }
+    TileShape t = {tx, 8, 8};
+    for (int f = build_nt(n_probes) / (tx * 64); f > 1; f >>= 1) {
+        if (t.tz <= t.ty) t.tz *= 2; else t.ty *= 2;
     }
-    switch (tx) { case 4: return {4, 8, 8}; case 2: return {2, 8, 16}; default: return {1, 16, 16}; }
+    return t;
 }
-static int main_tx(int n_probes) { return n_probes <= 2 ? 8 : 4; }
 static double tile_radius(const TileShape& t, const double* delta) {
     const double hx = 0.5 * (t.tx - 1) * delta[0], hy = 0.5 * (t.ty - 1) * delta[1], hz = 0.5 * (t.tz - 1) * delta[2];
     return std::sqrt(hx * hx + hy * hy + hz * hz);
@@ -503,7 +511,7 @@ static double tile_radius(const TileShape& t, const double* delta) {
 
 template <int NP, bool COUL>
 static cudaError_t dispatch_np(const BuildParams& P, int n_tiles, cudaStream_t s) {
-    constexpr int NT = NP <= 2 ? 512 : 256;
+    constexpr int NT = NP <= 2 ? CEG_BUILD_NT : 256;
     if (COUL && P.poly_erfcx) return launch_tiled<NT, NP, COUL, true>(P, n_tiles, s);
     return launch_tiled<NT, NP, COUL, false>(P, n_tiles, s);
 }

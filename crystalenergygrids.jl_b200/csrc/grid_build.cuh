@@ -35,6 +35,19 @@ struct PairDev {
     double lj_eps, lj_sig2, lj_shift;
     double bA, bB, bC, b_shift;
     double bB2;        // B^2
+    double lj_c6, lj_c12;   // 4 eps sigma^6, 4 eps sigma^12 (hot path)
+};
+// What the hot path reads of a PairDev (the shared-memory copy; the literal path reads the global table)
+struct PairHot {
+    int flags, _pad;
+    double lj_c6, lj_c12, lj_shift;
+    double bA, bB, bC, b_shift, bB2;
+    __device__ PairHot& operator=(const PairDev& d) {
+        flags = d.flags; _pad = 0;
+        lj_c6 = d.lj_c6; lj_c12 = d.lj_c12; lj_shift = d.lj_shift;
+        bA = d.bA; bB = d.bB; bC = d.bC; b_shift = d.b_shift; bB2 = d.bB2;
+        return *this;
+    }
 };
 
 constexpr int MAX_GRIDS = 5;       // up to 4 fused VdW probes + Coulomb per pass
@@ -100,23 +113,38 @@ __device__ __forceinline__ PairGeom make_geom(double r2) {
     return g;
 }
 
-// Lennard-Jones terms (interactions.jl:434-441), no branches
-__device__ __forceinline__ void lj_terms(const PairDev& p, const PairGeom& g, double& v, double& p1, double& p2,
+// Lennard-Jones terms (interactions.jl:434-441), no branches.  With a = 4 eps sigma^6 / r^6 and
+// b = 4 eps sigma^12 / r^12 the reference's four outputs are
+//   U = b - a - shift,  DU = (6/r^2)(a - 2b),  D^2U = (48/r^4)(3.5 b - a),  D^3U = (480/r^8)(a - 5.6 b);
+// the powers of 1/r^2 are shared by every probe of the pass (7 multiplications per pair), each probe then
+// costs 10 FP64 instructions, none with three register operands.
+struct LJPowers {
+    double u3, u6, k1, k2, k3;   // r^-6, r^-12, 6 r^-2, 48 r^-4, 480 r^-8
+};
+__device__ __forceinline__ LJPowers make_lj_powers(const PairGeom& g) {
+    LJPowers w;
+    const double u2 = g.ir2 * g.ir2;
+    w.u3 = u2 * g.ir2;
+    w.u6 = w.u3 * w.u3;
+    w.k1 = 6.0 * g.ir2;
+    w.k2 = 48.0 * u2;
+    w.k3 = 480.0 * (u2 * u2);
+    return w;
+}
+__device__ __forceinline__ void lj_terms(const PairHot& p, const LJPowers& w, double& v, double& p1, double& p2,
                                          double& p3) {
-    const double t = p.lj_sig2 * g.ir2;
-    const double x6 = t * t * t;
-    const double ir4 = g.ir2 * g.ir2;
-    const double ex6 = p.lj_eps * x6;
-    v = fma(4.0 * ex6, x6 - 1.0, -p.lj_shift);
-    p1 = 24.0 * (ex6 * fma(-2.0, x6, 1.0)) * g.ir2;
-    p2 = 96.0 * (ex6 * fma(7.0, x6, -2.0)) * ir4;
-    p3 = 384.0 * (ex6 * fma(-28.0, x6, 5.0)) * (ir4 * ir4);
+    const double a = p.lj_c6 * w.u3;
+    const double b = p.lj_c12 * w.u6;
+    v = (b - a) - p.lj_shift;
+    p1 = w.k1 * fma(b, -2.0, a);
+    p2 = w.k2 * fma(b, 3.5, -a);
+    p3 = w.k3 * fma(b, -5.6, a);
 }
 
 // Buckingham terms (interactions.jl:447-457), no branches.  With X = A e^{-Br}, y = B X / r:
 //   D X = -y,  D^2 X = (y + B^2 X)/r^2,  D^3 X = -(3 D^2 X + B^2 y)/r^2   (D = (1/r) d/dr),
 // and the dispersion part -C/r^6 contributes 6, -48, 480 times C/r^8, C/r^10, C/r^12.
-__device__ __forceinline__ void buck_terms(const PairDev& p, const PairGeom& g, const double* etab, double& v,
+__device__ __forceinline__ void buck_terms(const PairHot& p, const PairGeom& g, const double* etab, double& v,
                                            double& p1, double& p2, double& p3) {
     const double B = p.bB;
     const double X = p.bA * exp_neg_fast(-(B * g.r), etab);
@@ -133,12 +161,12 @@ __device__ __forceinline__ void buck_terms(const PairDev& p, const PairGeom& g, 
     p3 = fma(480.0, x12, -d3x);
 }
 
-__device__ __forceinline__ void vdw_pair_fast(const PairDev& p, const PairGeom& g, const double* etab, double& v,
-                                              double& p1, double& p2, double& p3) {
+__device__ __forceinline__ void vdw_pair_fast(const PairHot& p, const PairGeom& g, const LJPowers& w, const double* etab,
+                                              double& v, double& p1, double& p2, double& p3) {
     v = 0.0; p1 = 0.0; p2 = 0.0; p3 = 0.0;
     const int fl = p.flags;
     // hard sphere: the fast path only sees r2 >= fast_lo > every hs_r2, where the term is exactly 0
-    if (fl & CEG_PAIR_LJ) lj_terms(p, g, v, p1, p2, p3);
+    if (fl & CEG_PAIR_LJ) lj_terms(p, w, v, p1, p2, p3);
     if (fl & CEG_PAIR_BUCK) {
         double bv, b1, b2, b3;
         buck_terms(p, g, etab, bv, b1, b2, b3);
@@ -289,14 +317,16 @@ struct BuildParams {
     unsigned long long* stats; // [0] pairs tested, [1] pairs in cutoff
 };
 
+// <= 2 probes: 128 registers per thread whatever the CTA size (512/NT CTAs resident per SM); more probes
+// need the registers for their accumulators.
 template <int NT, int NP, bool COUL, bool POLY>
-__global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams P) {
+__global__ void __launch_bounds__(NT, NP <= 2 ? 512 / NT : 1) grid_build_tiled_kernel(const BuildParams P) {
     constexpr int NW = NT / 32;
     const int TX = P.tile[0], TY = P.tile[1], TZ = P.tile[2];   // TX*TY*TZ == NT (8x8x8 main, flatter tail shapes)
     constexpr int NG = NP + (COUL ? 1 : 0);
     __shared__ ExtAtom s_atom[LIST_CAP];
     __shared__ ExtMeta s_meta[LIST_CAP];
-    __shared__ PairDev s_table[NP > 0 ? NP * TABLE_SMEM_TYPES : 1];   // (probe x present species), <= 24 species
+    __shared__ PairHot s_table[NP > 0 ? NP * TABLE_SMEM_TYPES : 1];   // (probe x present species), <= 24 species
     __shared__ CellDev s_cell;
     __shared__ int s_wcount[NW];
     __shared__ double s_etab[EXP_TAB];   // 2^(j/256) for exp_neg_fast
@@ -355,11 +385,12 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
                     // ---- hot path ----
                     n_in++;
                     const PairGeom geo = make_geom(d2);
+                    const LJPowers ljw = make_lj_powers(geo);   // dead code in the blocks without LJ
                     const double dxy = dx * dy, dxz = dx * dz, dyz = dy * dz;
                     if (NP == 1 && COUL) {
                         // one straight-line block per interaction class, so that the independent exp / erfcx /
                         // algebra chains of the VdW and Ewald terms are scheduled against each other
-                        const PairDev& pr = s_table[ty_];
+                        const PairHot& pr = s_table[ty_];
                         const int fl = pr.flags & ~CEG_PAIR_HS;   // hard spheres contribute exactly 0 here
                         double v, p1, p2, p3, ev, e1, e2, e3;
                         if (fl == CEG_PAIR_BUCK) {
@@ -368,7 +399,7 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         } else if (fl == CEG_PAIR_LJ) {
-                            lj_terms(pr, geo, v, p1, p2, p3);
+                            lj_terms(pr, ljw, v, p1, p2, p3);
                             ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
@@ -376,7 +407,7 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
                             ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         } else {
-                            vdw_pair_fast(pr, geo, s_etab, v, p1, p2, p3);
+                            vdw_pair_fast(pr, geo, ljw, s_etab, v, p1, p2, p3);
                             ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
@@ -384,10 +415,10 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
                     } else {
 #pragma unroll
                         for (int g = 0; g < NP; g++) {
-                            const PairDev& pr = s_table[g * P.n_types + ty_];
+                            const PairHot& pr = s_table[g * P.n_types + ty_];
                             if (pr.flags != 0) {
                                 double v, p1, p2, p3;
-                                vdw_pair_fast(pr, geo, s_etab, v, p1, p2, p3);
+                                vdw_pair_fast(pr, geo, ljw, s_etab, v, p1, p2, p3);
                                 accumulate(acc[g], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             }
                         }
@@ -410,7 +441,7 @@ __global__ void __launch_bounds__(NT) grid_build_tiled_kernel(const BuildParams 
                     const double bxy = b[0] * b[1], bxz = b[0] * b[2], byz = b[1] * b[2];
 #pragma unroll
                     for (int g = 0; g < NP; g++) {
-                        const PairDev& pr = s_table[g * P.n_types + ty_];
+                        const PairDev& pr = P.table[g * P.n_types + ty_];
                         if (pr.flags != 0) {
                             double v, p1, p2, p3;
                             vdw_pair_ref(pr, d2x, v, p1, p2, p3);

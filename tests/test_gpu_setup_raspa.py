@@ -144,3 +144,21 @@ def test_setup_raspa_co2_fused_grids_and_cache(cuda_lib, orc, tmp_path):
     assert s3.block.empty and s3.charges[0] == 1.0 and (gdir / "Toy_Na_truncated.grid").exists()
     e = ceg.energy_point(s3, np.array([[3.0, 4.0, 5.0]]))
     assert np.isfinite(e[1]) and (np.isfinite(e[0]) or e[0] == 1e100)
+    # batched Monte-Carlo trial evaluation (montecarlo.jl:563-606) = the three device pieces side by side
+    names = ["O_co2", "C_co2"]
+    tab = ceg.pair_energy_table(ff, names)
+    envc = wl.random_positions(fw.mat, 12, 3)
+    env_pos = (envc[:, None, :] + mol[None, :, :]).reshape(-1, 3)
+    env = ceg.GuestEnvironment(fw.mat, 12.0, tab, env_pos, np.tile(np.array(setup.atomsidx, dtype=np.int32), 12),
+                               np.repeat(np.arange(12, dtype=np.int32), 3))
+    rest = setup.ewald.StoreRigidChargeFramework + ceg.adsorbate_sums(setup.ewald, np.tile(setup.charges, 11), env_pos[3:])
+    fv, fc, rec, gg = ceg.movement_energies(setup, env, rest, setup.atomsidx, pos[:500], skip_molecule=0)
+    assert np.array_equal(fv, v[:500])
+    wdir = sum(setup.charges[a] * orc.interpolate(cset, setup.coulomb.grid, False, pos[:500, a]) for a in range(3))
+    okk = ok[:500]
+    assert (np.abs(fc[okk] - wdir[okk]) <= 1e-9 * np.abs(wdir[okk]) + 1e-6).all()
+    oe.S = rest
+    wrec = oe.reciprocal(pos[:500], setup.charges, 0.0, 0.0)
+    assert np.abs(rec - wrec).max() <= 1e-9 * np.abs(wrec).max()
+    wgg = orc.guest_energy(env, setup.atomsidx, pos[:500], 0)
+    assert np.abs(wgg).max() > 0 and (np.abs(gg - wgg) <= 1e-9 * np.abs(wgg) + 1e-6).all()
