@@ -568,6 +568,10 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     P.gs = to_dev(*gs);
     P.cutoff2 = h->cutoff2;
     P.alpha = h->alpha;
+    P.alpha2 = h->alpha * h->alpha;
+    P.kk[0] = 2.0 * h->alpha / std::sqrt(M_PI);
+    P.kk[1] = 2.0 * P.alpha2 * P.kk[0];
+    P.kk[2] = 4.0 * P.alpha2 * P.alpha2 * P.kk[0];
     P.cut_hi = h->cutoff2 + GUARD_BAND;
     // fast path window: away from every mask threshold (hard spheres, the 1 Å rule, the cutoff, the
     // entry of the reference's non-orthogonal image search) and from r -> 0

@@ -293,6 +293,7 @@ struct BuildParams {
     CellDev cell;
     GridSpecDev gs;
     double cutoff2, alpha;
+    double alpha2, kk[3];      // alpha^2; K1, 2 alpha^2 K1, (2 alpha^2)^2 K1 with K1 = 2 alpha / sqrt(pi): constant-bank operands
     double cut_hi;             // cutoff2 + GUARD_BAND: pairs below enter the pair code
     double fast_lo, fast_hi;   // d2 in [fast_lo, fast_hi] takes the fast path, anything else the literal one
     int hi_cut, hi_fast_lo;    // the same windows on the high 32 bits of d2 (see the kernel)
@@ -361,9 +362,6 @@ __global__ void __launch_bounds__(NT, NP <= 2 ? 512 / NT : 1) grid_build_tiled_k
 #pragma unroll
         for (int c = 0; c < 8; c++) acc[g][c] = 0.0;
     double smallest = CUDART_INF;
-    const double alpha2 = P.alpha * P.alpha;
-    const double k1_ = 2.0 * P.alpha / sqrt(CUDART_PI);
-    const double kk[3] = {k1_, 2.0 * alpha2 * k1_, 4.0 * alpha2 * alpha2 * k1_};
     unsigned int n_tested = 0, n_in = 0;
     int count = 0;
     __syncthreads();
@@ -395,20 +393,20 @@ __global__ void __launch_bounds__(NT, NP <= 2 ? 512 / NT : 1) grid_build_tiled_k
                         double v, p1, p2, p3, ev, e1, e2, e3;
                         if (fl == CEG_PAIR_BUCK) {
                             buck_terms(pr, geo, s_etab, v, p1, p2, p3);
-                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
+                            ewald_pair_fast<POLY>(P.alpha, P.alpha2, P.kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         } else if (fl == CEG_PAIR_LJ) {
                             lj_terms(pr, ljw, v, p1, p2, p3);
-                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
+                            ewald_pair_fast<POLY>(P.alpha, P.alpha2, P.kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         } else if (fl == 0) {
-                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
+                            ewald_pair_fast<POLY>(P.alpha, P.alpha2, P.kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         } else {
                             vdw_pair_fast(pr, geo, ljw, s_etab, v, p1, p2, p3);
-                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, ev, e1, e2, e3);
+                            ewald_pair_fast<POLY>(P.alpha, P.alpha2, P.kk, a.q, geo, s_etab, ev, e1, e2, e3);
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         }
@@ -424,7 +422,7 @@ __global__ void __launch_bounds__(NT, NP <= 2 ? 512 / NT : 1) grid_build_tiled_k
                         }
                         if (COUL) {   // d2 >= fast_lo > 1 Å^2 here: `smallest` (probes.jl:108) is tracked on the literal path
                             double v, p1, p2, p3;
-                            ewald_pair_fast<POLY>(P.alpha, alpha2, kk, a.q, geo, s_etab, v, p1, p2, p3);
+                            ewald_pair_fast<POLY>(P.alpha, P.alpha2, P.kk, a.q, geo, s_etab, v, p1, p2, p3);
                             accumulate(acc[NG - 1], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                         }
                     }
