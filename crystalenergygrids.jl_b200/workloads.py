@@ -139,10 +139,29 @@ def mof_shaped(n_atoms: int = 5000, edge: float = 50.0):
     return fw, ff, species
 
 
+def rhombo60_shaped():
+    """Edge case of the minimum-image search (utils.jl:226-246): rhombohedral 10.2 Å cell with 60° angles.
+    Its (3,3,3) supercell has safemin = 10.82 Å < 12 Å cutoff, so pairs with safemin^2 < d^2 < cutoff^2 go
+    through the reference's +-1 image search, including its stale-vector exit."""
+    from .cell import mat_from_parameters
+    mat = mat_from_parameters((10.2, 10.2, 10.2), (60.0, 60.0, 60.0))
+    pts = _jittered_lattice(mat, (3, 3, 3), 0.3, 1.4, 5, 27)
+    n = len(pts)
+    symbols = ["Si" if (i % 3 == 0) else "O" for i in range(n)]
+    n_si = sum(s == "Si" for s in symbols)
+    q_si = 2.05
+    q_o = -q_si * n_si / (n - n_si)
+    species = {"O": (53.0, 3.30, q_o), "Si": (22.0, 2.30, q_si), "C_ch4": (148.0, 3.73, 0.0), "Na": (15.1, 2.66, 1.0)}
+    ff = _lj_forcefield(species)
+    charges = np.array([species[s][2] for s in symbols])
+    fw = RASPASystem(mat, pts, symbols, np.ones(n), charges, False)
+    return fw, ff, species
+
+
 def synthetic_inputs(kind: str, spacing: float, probes, coulomb: bool):
     """-> (ProbeInputs, GridCoordinatesSetup, framework)."""
     from .ewald import ewald_parameters
-    fw, ff, _ = mfi_shaped() if kind == "mfi" else mof_shaped()
+    fw, ff, _ = {"mfi": mfi_shaped, "mof": mof_shaped, "rhombo60": rhombo60_shaped}[kind]()
     alpha = ewald_parameters(1e-6)[0] if coulomb else 0.0
     inp = probe_inputs(fw, ff, tuple(probes), coulomb, alpha)
     cset = GridCoordinatesSetup.from_cell(fw.mat, spacing)

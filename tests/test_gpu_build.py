@@ -98,6 +98,24 @@ def test_tiled_slab_mof_synthetic(cuda_lib, orc):
     _check_slab(orc, inp, cset, 30, 33, "mof")
 
 
+def test_tiled_slab_rhombohedral_image_search(cuda_lib, orc):
+    """safemin < cutoff: pairs between the two radii go through the reference's +-1 image search
+    (utils.jl:226-246), whose exits leave either the first smaller image or a stale displacement vector in
+    the buffer the derivative tensors are built from.  Tiled kernel and literal kernel vs the oracle."""
+    inp, cset, fw = wl.synthetic_inputs("rhombo60", 0.4, ("C_ch4", "Na"), True)
+    assert not inp.ortho and inp.supercell == (3, 3, 3) and 100.0 < inp.safemin2 < inp.cutoff2
+    nx = cset.nodes[0]
+    _check_slab(orc, inp, cset, 0, 5, "rhombo60[0:5]")
+    _check_slab(orc, inp, cset, nx - 3, nx, "rhombo60[last]")
+    pos = _rand_positions(cset.cell.mat, 400, 3)
+    ps = _probe(inp)
+    got = ps.compute_derivatives(pos)
+    ps.close()
+    want = orc.compute_derivatives(inp, pos)
+    for g in range(got.shape[0]):
+        assert_close_f64(got[g], want[g], g == got.shape[0] - 1, f"rhombo60 literal grid {g}")
+
+
 def test_ragged_slab_uses_every_tile_shape(cuda_lib, orc):
     """13 planes = one 8-plane row + the 4-, and 1-plane tail shapes; 7 planes = 4 + 2 + 1."""
     inp, cset, _ = wl.load_fixture("cha_na")

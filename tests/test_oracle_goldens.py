@@ -128,3 +128,50 @@ def test_pin_script_passes():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "oracle", "pin_goldens.py")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_oracle_min_image_search_exits(orc):
+    """utils.jl:226-246 on a cell with safemin < cutoff: the oracle's distance AND the vector it leaves in the
+    buffer, against a scalar restatement written from the reference text, with every exit of the search hit
+    (inside safemin; first smaller image; no smaller image -> stale vector of the last tried image)."""
+    import ctypes as C
+    from ceg_b200 import workloads as wl
+    inp, cset, fw = wl.synthetic_inputs("rhombo60", 0.4, ("C_ch4",), False)
+    mat, invmat = np.asarray(inp.mat, dtype=np.float64), np.asarray(inp.invmat, dtype=np.float64)
+    assert not inp.ortho and inp.safemin2 < inp.cutoff2
+
+    def restated(b):
+        f = invmat @ b
+        f = f + 0.5
+        f = f - np.floor(f) - 0.5
+        v = mat @ f
+        ref2 = float(v @ v)
+        if ref2 <= inp.safemin2:
+            return ref2, v, "safe"
+        for i in range(3):
+            for step in (1.0, -2.0):
+                f[i] += step
+                v = mat @ f
+                n2 = float(v @ v)
+                if n2 < ref2:
+                    return n2, v, "smaller"
+            f[i] += 1.0
+        return ref2, v, "stale"
+
+    lib = orc.lib()
+    lib.ceg_o_periodic_distance2.restype = C.c_double
+    fm, fi = np.ascontiguousarray(mat.T).ravel(), np.ascontiguousarray(invmat.T).ravel()   # column-major 3x3
+    rng = np.random.default_rng(12)
+    seen = {"safe": 0, "smaller": 0, "stale": 0}
+    for _ in range(4000):
+        b = mat @ (rng.random(3) * 3 - 1.5)
+        want2, wantv, kind = restated(b.copy())
+        buf = b.copy()
+        got2 = lib.ceg_o_periodic_distance2(buf.ctypes.data_as(C.POINTER(C.c_double)), fm.ctypes.data_as(C.POINTER(C.c_double)),
+                                            fi.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(0), C.c_double(inp.safemin2))
+        assert abs(got2 - want2) <= 1e-12 * max(1.0, want2)
+        assert np.allclose(buf, wantv, rtol=0, atol=1e-10), kind
+        if kind == "stale":
+            assert abs(float(buf @ buf) - got2) > 1.0      # the vector left behind is not the measured image
+        seen[kind] += 1
+    assert min(seen.values()) > 20, seen
