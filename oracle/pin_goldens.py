@@ -1,7 +1,7 @@
 """ORACLE pinning — test infrastructure.
 
 Checks the CPU oracle against every known-answer value the reference's own tests hold for the
-hot path (/root/reference/test/runtests.jl:24-56, 165-169, 269-272), reading the
+hot path (/root/reference/test/runtests.jl:24-56, 165-169, 269-272, 446-450), reading the
 reference's RASPA fixtures where they lie, and (re)generates the flattened input fixtures under
 tests/golden/ that the GPU box uses (it has no /root/reference).
 
@@ -34,7 +34,43 @@ GOLDENS = {
     "two_co2_reciprocal": 1177.5215489122043 + 7.4133039820109055,  # :56
     "ar_cit7_point": -1043.35893781,                    # :169 (stale at ~2e-8)
     "na_cha_min": -1.9278944364761321e6,                # :50  (29,60,60); stale at 4e-5, rtol 1e-3 only
+    "restart_baseline_co2": -14128.888030042883,        # :450 one CO2 in CHA+Na from the restart file (rtol 1e-3 there)
 }
+
+
+def tail_correction_pair(rule, cut):
+    """interactions.jl:411-430, 646-652 — only needed to compare with the restart baseline, which includes the
+    (out-of-scope) TailCorrection term of the Monte-Carlo setup."""
+    from ceg_b200.forcefields import InteractionRuleSum, Kind
+    if isinstance(rule, InteractionRuleSum):
+        return sum(tail_correction_pair(r, cut) for r in rule.rules)
+    if (not rule.tailcorrection) or rule.kind in (Kind.NoInteraction, Kind.HardSphere, Kind.CoulombEwaldDirect):
+        return 0.0
+    if rule.kind is Kind.LennardJones:
+        e, sg = rule.params
+        x3 = (sg / cut) ** 3
+        return (4 / 3) * e * sg ** 3 * (x3 ** 3 / 3 - x3)
+    if rule.kind is Kind.Buckingham:
+        A, B, C = rule.params
+        return A * np.exp(-B * cut) * (2.0 + B * cut * (2.0 + B * cut)) / B ** 3 - C / (3 * cut ** 3)
+    raise ValueError(rule.kind)
+
+
+def tail_correction_one_molecule(ff, fw, mol_names, cut=12.0):
+    """tailcorrection.jl:23-79 for a framework plus ONE molecule of one species."""
+    from ceg_b200.forcefields import get_atom_name
+    n = len(ff.sdict)
+    cnt = np.zeros(n, dtype=int)
+    for sym in fw.atomic_symbol:
+        cnt[ff.sdict[get_atom_name(str(sym))]] += 1
+    lam = 2 * np.pi / abs(np.linalg.det(fw.mat))
+    idx = [ff.sdict[a] for a in mol_names]
+    present = [k for k in range(n) if cnt[k] > 0]
+    ap = lambda i, j: tail_correction_pair(ff.interactions[i][j], cut) * lam   # noqa: E731
+    value = sum(cnt[i] * cnt[j] * ap(i, j) for i in present for j in present)
+    f = sum(ap(k1, k2) * cnt[k2] for k2 in present for k1 in idx)
+    c = sum(ap(a, b) for a in idx for b in idx)
+    return value + 2 * f + c
 
 
 def save_inputs(name, inp, cset, extra=None):
@@ -108,6 +144,26 @@ def main():
     if args.write:
         save_inputs("chana_ar", inp2, cset2)
 
+    # ---- restart baseline: one CO2 in CHA+Na (runtests.jl:446-450) -------------------------------
+    rpos = np.array([[float(x) for x in line.split()[3:6]]
+                     for line in open("/root/reference/test/CHA_1.4_3b4eeb96_Na_11812.restart")
+                     if line.startswith("Adsorbate-atom-position:")])
+    oe2 = orc.OracleEwald(fw2)
+    names = [str(x) for x in co2.atomic_symbol]
+    inp2c = ceg.probe_inputs(fw2, ff, atoms=("O_co2", "C_co2"), coulomb=True, alpha=oe2.alpha)
+    gidx = {"O_co2": 0, "C_co2": 1}
+    r_vdw = sum(orc.interpolate_sparse(inp2c, gidx[nm], cset2, True, p) for nm, p in zip(names, rpos))
+    r_dir = sum(q * orc.interpolate_sparse(inp2c, 2, cset2, False, p) for q, p in zip(co2.atomic_charge, rpos))
+    ctx2 = ceg.ewald_context(oe2.as_framework(), ((co2.with_positions(rpos),),))
+    r_rec = oe2.reciprocal(rpos[None], ctx2.charges, ctx2.energy_net_charges, ctx2.static_contribution)[0]
+    r_tail = tail_correction_one_molecule(ff, fw2, names)
+    results["restart_baseline_co2"] = r_vdw + r_dir + r_rec + r_tail
+    print(f"restart CO2: vdw {r_vdw!r} direct {r_dir!r} reciprocal {r_rec!r} tail correction {r_tail!r}")
+    if args.write:
+        save_inputs("chana_co2", inp2c, cset2, dict(
+            site_charge=ceg.framework_sites(fw2, oe2.supercell)[1], restart_positions=rpos, co2_charges=np.asarray(co2.atomic_charge),
+            oracle_vdw=r_vdw, oracle_direct=r_dir, oracle_reciprocal=r_rec, tail_correction=r_tail))
+
     # ---- Ar in triclinic CIT-7 (runtests.jl:165-169) ---------------------------------------------
     fw3 = ceg.load_framework_RASPA("CIT-7", ffname)
     assert ceg.find_supercell(fw3.mat, 12.0) == (2, 3, 3)
@@ -139,14 +195,14 @@ def main():
     for k, gold in GOLDENS.items():
         got = results[k]
         rel = abs(got - gold) / abs(gold)
-        tol = {"na_cha_min": 1e-3, "ar_cit7_point": 1e-7}.get(k, 1e-9)
+        tol = {"na_cha_min": 1e-3, "ar_cit7_point": 1e-7, "restart_baseline_co2": 1e-6}.get(k, 1e-9)
         flag = "OK " if rel <= tol else "FAIL"
         ok &= rel <= tol
         print(f"{flag} {k:28s} oracle {got!r:26}  golden {gold!r:26}  rel {rel:.2e} (tol {tol:g})")
     if args.write:
         with open(os.path.join(GOLDEN_DIR, "goldens.json"), "w") as f:
             json.dump({"reference_values": GOLDENS, "oracle_values": {k: (float(v) if not isinstance(v, list) else v) for k, v in results.items()},
-                       "source": "test/runtests.jl:24-56,165-169,269-272"}, f, indent=1)
+                       "source": "test/runtests.jl:24-56,165-169,269-272,446-450"}, f, indent=1)
     sys.exit(0 if ok else 1)
 
 

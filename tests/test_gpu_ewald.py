@@ -205,3 +205,35 @@ def test_single_contribution_ewald_batched(cuda_lib, orc):
         e_new = ceg.compute_ewald(ef, ([A, co2.with_positions(trials[i])],))
         e_old = ceg.compute_ewald(ef, ([A, co2.with_positions(B_old)],))
         assert abs((e_new - e_old) - (got[i] - old)) <= 1e-9 * max(abs(e_new), abs(e_old))
+
+
+def test_restart_baseline_co2_in_cha_na(cuda_lib, orc):
+    """test/runtests.jl:446-450: baseline energy of the one CO2 of the restart file in CHA+Na (1107 framework
+    atoms), end to end on the device path: fused O_co2 + C_co2 + Coulomb grids at 0.15 Å, interpolation, direct
+    and reciprocal Ewald.  Compared with the oracle's three parts at 1e-9 and, after adding the constant
+    TailCorrection term of the Monte-Carlo setup (tailcorrection.jl, not part of this library; value computed by
+    oracle/pin_goldens.py), with the reference's number at 1e-6 (its own tolerance is 1e-3)."""
+    gold = json.load(open(os.path.join(wl.GOLDEN_DIR, "goldens.json")))["reference_values"]
+    inp, cset, ex = wl.load_fixture("chana_co2")
+    fw = _framework_from_fixture(ex)
+    nx, ny, nz = cset.nodes
+    ps = ceg.ProbeSystem(None, None, inputs=inp)
+    outs = [np.empty((8, nx, ny, nz), dtype=np.float32) for _ in range(3)]
+    lam_v, thr_v = ceg.vdw_scaling()
+    lam_c, thr_c = ceg.coulomb_scaling()
+    ceg._lib.grid_build(ps.handle, ceg._lib.make_gridspec(cset), 0, nx, lam_v, thr_v, lam_c, thr_c, outs, None)
+    ps.close()
+    grids = [ceg.EnergyGrid(cset, inp.supercell, np.inf, True, orc.scale_to_kelvin(outs[g])) for g in range(2)]
+    gc = ceg.EnergyGrid(cset, inp.supercell, 1e-6, True, orc.scale_to_kelvin(outs[2]))
+    ef = ceg.initialize_ewald(fw)
+    q = ex["co2_charges"]
+    co2 = ceg.RASPASystem(np.diag([np.inf] * 3), ex["restart_positions"], ["O_co2", "C_co2", "O_co2"], np.ones(3), q, True)
+    setup = ceg.CrystalEnergySetup(fw, co2, gc, q, grids, [0, 1, 0], ef, None, ceg.BlockFile(cset))
+    v, c = ceg.energy_point(setup, ex["restart_positions"])
+    assert abs(v - float(ex["oracle_vdw"])) <= 1e-9 * abs(v)
+    want_c = float(ex["oracle_direct"]) + float(ex["oracle_reciprocal"])
+    assert abs(c - want_c) <= 1e-9 * abs(want_c)
+    total = v + c + float(ex["tail_correction"])
+    assert abs(total - gold["restart_baseline_co2"]) <= 1e-6 * abs(total), total
+    for g in grids + [gc]:
+        g.close()

@@ -72,6 +72,20 @@ def test_ar_cit7_point(orc, gold):
     assert abs(v - gold["ar_cit7_point"]) <= 1e-7 * abs(v)
 
 
+def test_restart_baseline_co2(orc, gold):
+    """runtests.jl:446-450: one CO2 in CHA+Na.  Framework VdW and direct Coulomb from the fixture (the reciprocal
+    and the out-of-scope TailCorrection constant are the values oracle/pin_goldens.py computed beside the
+    reference); the sum reproduces the reference's number at 2.7e-7 (its own tolerance: 1e-3)."""
+    inp, cset, ex = wl.load_fixture("chana_co2")
+    pos, q = ex["restart_positions"], ex["co2_charges"]
+    vdw = sum(orc.interpolate_sparse(inp, g, cset, True, p) for g, p in zip((0, 1, 0), pos))
+    direct = sum(qa * orc.interpolate_sparse(inp, 2, cset, False, p) for qa, p in zip(q, pos))
+    assert abs(vdw - float(ex["oracle_vdw"])) <= 1e-12 * abs(vdw)
+    assert abs(direct - float(ex["oracle_direct"])) <= 1e-12 * abs(direct)
+    total = vdw + direct + float(ex["oracle_reciprocal"]) + float(ex["tail_correction"])
+    assert abs(total - gold["restart_baseline_co2"]) <= 1e-6 * abs(total)
+
+
 def test_dense_interpolation_matches_sparse(orc):
     """ceg_o_interpolate (C, dense grid) == the numpy statement of grids.jl:227-258 used above."""
     inp, cset, _ = wl.load_fixture("chana_ar")
