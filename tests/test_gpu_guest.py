@@ -98,3 +98,37 @@ def test_compute_vdw_and_move_identity(cuda_lib, orc):
     g = ceg.single_contribution_vdw(big, [3], t, -1)
     w = orc.guest_energy(big, [3], t, -1)
     assert (np.abs(g - w) <= 1e-9 * np.abs(w) + 1e-6).all()
+
+
+def test_grid_vs_explicit_supercell_cit7(cuda_lib, orc):
+    """test/runtests.jl:186-198 ("Triclinic"): the energy of Ar in CIT-7 from the interpolated grid agrees (rtol
+    5e-3, the reference's tolerance) with the pair sum over the explicit (2,3,3) supercell atoms treated as guest
+    molecules; and that pair sum (ceg_guest_energy) equals the un-interpolated grid-point sum of the literal
+    derivative kernel (ceg_compute_derivatives, channel 0) to 1e-9 — two independent device code paths."""
+    inp, cset, _ = wl.load_fixture("cit7_multi")                 # probes Ar, C_co2, O_co2 + Coulomb
+    nt = inp.n_types
+    tab = np.zeros((nt + 1, nt + 1), dtype=ceg.pair_energy_dtype)
+    for t in range(nt):
+        for name in ("flags", "hs_r", "lj_eps", "lj_sigma", "lj_shift", "buck_A", "buck_B", "buck_C", "buck_shift"):
+            tab[t, nt][name] = tab[nt, t][name] = inp.table[0, t][name]
+    n = len(inp.positions)
+    env = ceg.GuestEnvironment(inp.mat, 12.0, tab, inp.positions, inp.types, np.arange(n, dtype=np.int32))
+    pts = np.concatenate([np.array([[5.86207, 16.23616, 17.52779]]), wl.random_positions(cset.cell.mat, 200, 8)])
+    pair_sum = ceg.single_contribution_vdw(env, [nt], pts[:, None, :])
+    ps = ceg.ProbeSystem(None, None, inputs=inp)
+    exact = ps.compute_derivatives(pts)[0][:, 0]
+    both = np.isfinite(pair_sum) & np.isfinite(exact)
+    assert both.sum() > 150 and np.array_equal(np.isfinite(pair_sum), np.isfinite(exact))
+    assert (np.abs(pair_sum[both] - exact[both]) <= 1e-9 * np.abs(exact[both]) + 1e-6).all()
+    # the Ar grid at 0.15 Å and its interpolation at the reference's point
+    nx, ny, nz = cset.nodes
+    outs = [np.empty((8, nx, ny, nz), dtype=np.float32) for _ in range(4)]
+    lam_v, thr_v = ceg.vdw_scaling()
+    lam_c, thr_c = ceg.coulomb_scaling()
+    ceg._lib.grid_build(ps.handle, ceg._lib.make_gridspec(cset), 0, nx, lam_v, thr_v, lam_c, thr_c, outs, None)
+    ps.close()
+    g = ceg.EnergyGrid(cset, inp.supercell, np.inf, True, orc.scale_to_kelvin(outs[0]))
+    e_grid = ceg.interpolate_grid(g, pts[:1])[0]
+    g.close()
+    # (a repulsive site, ~2.5e5 K: the tricubic interpolant is 1.4e-3 off the exact sum there)
+    assert abs(e_grid - pair_sum[0]) <= 5e-3 * abs(pair_sum[0]), (e_grid, pair_sum[0])
