@@ -150,6 +150,10 @@ struct ceg_ewald_s {
     int kmax[3];
     int64_t n_k = 0;
     DevBuf d_kv, d_xyz, d_out, d_q;
+    // thread-per-placement kernel: rows of the k-list, kfactor and kfactor * S_f in list order
+    bool rows_ok = false;
+    double sum_kf = 0.0;
+    DevBuf d_rows, d_kf, d_ksf, d_ksf_rest;
     ~ceg_ewald_s() {
         if (stream) cudaStreamDestroy(stream);
     }
@@ -894,7 +898,8 @@ extern "C" int ceg_ewald_create(int32_t device, const double* invmat, const int3
     CEG_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CEG_CK(h->d_kv.reserve(sizeof(KVecDev) * std::max<int64_t>(1, n_k)));
     if (n_k > 0) {
-        DevBuf d_kvec, d_kf, d_frac, d_q, d_part, d_S;
+        DevBuf d_kvec, d_frac, d_q, d_part, d_S;
+        DevBuf& d_kf = h->d_kf;
         const int n_blocks = (int)std::max<int64_t>(1, (n_sites + SF_SITES_PER_BLOCK - 1) / SF_SITES_PER_BLOCK);
         CEG_CK(d_kvec.reserve(sizeof(int) * 3 * n_k));
         CEG_CK(d_kf.reserve(sizeof(double) * n_k));
@@ -918,6 +923,29 @@ extern "C" int ceg_ewald_create(int32_t device, const double* invmat, const int3
         count_launch();
         CEG_CK(cudaGetLastError());
         if (S_f_reim) CEG_CK(cudaMemcpyAsync(S_f_reim, d_S.p, sizeof(double) * 2 * n_k, cudaMemcpyDeviceToHost, h->stream));
+        // rows of the k-list (ewald.jl:213-236: one contiguous ix range per (jy, jz)); any other list keeps the
+        // warp-per-placement kernel
+        const int ny = 2 * kmax[1] + 1, nz = 2 * kmax[2] + 1;
+        std::vector<RowDev> rows((size_t)ny * nz, RowDev{0, 0, 0});
+        bool ok = true;
+        for (int64_t k = 0; k < n_k && ok; k++) {
+            RowDev& r = rows[(size_t)(kvec[3 * k + 1] + kmax[1]) * nz + (kvec[3 * k + 2] + kmax[2])];
+            if (r.count == 0) { r.ix0 = kvec[3 * k]; r.count = 1; r.offset = k; }
+            else if (k == r.offset + r.count && kvec[3 * k] == r.ix0 + r.count) r.count++;
+            else ok = false;
+        }
+        h->rows_ok = ok;
+        h->sum_kf = 0.0;
+        for (int64_t k = 0; k < n_k; k++) h->sum_kf += kfactor[k];
+        if (ok) {
+            CEG_CK(h->d_rows.reserve(sizeof(RowDev) * rows.size()));
+            CEG_CK(h->d_ksf.reserve(sizeof(double2) * n_k));
+            CEG_CK(cudaMemcpyAsync(h->d_rows.p, rows.data(), sizeof(RowDev) * rows.size(), cudaMemcpyHostToDevice, h->stream));
+            scale_structure_factor_kernel<<<(unsigned)((n_k + 127) / 128), 128, 0, h->stream>>>(
+                n_k, d_kf.as<double>(), d_S.as<double2>(), h->d_ksf.as<double2>());
+            count_launch();
+            CEG_CK(cudaGetLastError());
+        }
         CEG_CK(cudaStreamSynchronize(h->stream));
     }
     *out = h.release();
@@ -934,6 +962,36 @@ extern "C" int ceg_ewald_free(ceg_ewald_h h) {
 static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const double* d_xyz, const double* d_q,
                              double enc, double stat, double* d_out, const uint8_t* d_skip, int accumulate,
                              cudaStream_t s, const double2* d_rest = nullptr) {
+    if (h->rows_ok && n_atoms <= ROWS_MAX_ATOMS) {
+        RowsParams R;
+        memcpy(R.invmat, h->invmat, sizeof R.invmat);
+        R.ky = h->kmax[1]; R.kz = h->kmax[2];
+        R.rows = h->d_rows.as<RowDev>();
+        R.kf = h->d_kf.as<double>();
+        R.ksf = h->d_ksf.as<double2>();
+        R.sum_kf = h->sum_kf;
+        if (d_rest) {   // single_contribution_ewald: the framework sums are replaced by `rest`
+            CEG_CK(h->d_ksf_rest.reserve(sizeof(double2) * h->n_k));
+            scale_structure_factor_kernel<<<(unsigned)((h->n_k + 127) / 128), 128, 0, s>>>(h->n_k, R.kf, d_rest,
+                                                                                         h->d_ksf_rest.as<double2>());
+            count_launch();
+            CEG_CK(cudaGetLastError());
+            R.ksf = h->d_ksf_rest.as<double2>();
+        }
+        R.n_pos = n_pos; R.xyz = d_xyz; R.q = d_q;
+        R.energy_net_charges = enc; R.static_contribution = stat;
+        R.out = d_out; R.skip = d_skip; R.accumulate = accumulate;
+        const unsigned blocks = (unsigned)((n_pos + ROWS_THREADS - 1) / ROWS_THREADS);
+        switch (n_atoms) {
+            case 1: reciprocal_rows_kernel<1><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
+            case 2: reciprocal_rows_kernel<2><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
+            case 3: reciprocal_rows_kernel<3><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
+            default: reciprocal_rows_kernel<4><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
+        }
+        count_launch();
+        CEG_CK(cudaGetLastError());
+        return 0;
+    }
     RecipParams P;
     P.rest = d_rest;
     memcpy(P.invmat, h->invmat, sizeof P.invmat);

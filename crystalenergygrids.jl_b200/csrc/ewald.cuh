@@ -170,4 +170,123 @@ __global__ void __launch_bounds__(RECIP_WARPS * 32) reciprocal_kernel(const Reci
     }
 }
 
+// ---- thread-per-placement variant ------------------------------------------------------------------
+// The k-list of ewald.jl:213-236 is a set of rows: for each (jy, jz) a contiguous range of ix.  One thread
+// owns one placement and walks the full (2ky+1) x (2kz+1) rectangle of rows in a fixed order, so that every
+// phase factor comes from a recurrence (the reference builds its tables the same way, ewald.jl:69-86):
+//   ey <- ey * e^{2 pi i fy} per jy,  w = q ey ez <- w * e^{2 pi i fz} per row,  t = w Ex[ix] <- t * e^{2 pi i fx} per k.
+// No tables, no shuffles; the k data (kfactor, kfactor * S_f) is read at warp-uniform addresses.  Per k-vector
+// and atom 4 FP64 instructions (+5 per k-vector) against 16 for the warp-per-placement kernel above, which
+// stays as the general fallback (molecules of more than 4 atoms, k-lists that are not made of rows).
+struct RowDev {
+    int ix0, count;        // first ix and number of k-vectors of the row (0: row absent from the list)
+    int64_t offset;        // index of the row's first k-vector in the list
+};
+
+struct RowsParams {
+    double invmat[9];
+    int ky, kz;
+    const RowDev* rows;    // (2ky+1) x (2kz+1), jy-major
+    const double* kf;      // kfactor per k-vector (list order)
+    const double2* ksf;    // kfactor * S_f (or kfactor * rest)
+    double sum_kf;         // sum of the kfactors in list order (single-atom molecules: |S_a|^2 = q^2 for every k)
+    int64_t n_pos;
+    const double* xyz;
+    const double* q;
+    double energy_net_charges, static_contribution;
+    double* out;
+    const uint8_t* skip;
+    int accumulate;
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 cis2pi(double ph) {   // exp(2 pi i ph), ph in [0, 1)
+    double sn, cs;
+    sincospi(2.0 * ph, &sn, &cs);
+    return make_double2(cs, sn);
+}
+
+__global__ void scale_structure_factor_kernel(int64_t n_k, const double* __restrict__ kf, const double2* __restrict__ sf,
+                                              double2* __restrict__ ksf) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n_k) ksf[k] = make_double2(kf[k] * sf[k].x, kf[k] * sf[k].y);
+}
+
+constexpr int ROWS_THREADS = 128;
+constexpr int ROWS_MAX_ATOMS = 4;
+
+template <int NA>
+__global__ void __launch_bounds__(ROWS_THREADS) reciprocal_rows_kernel(const RowsParams P) {
+    const int64_t i = blockIdx.x * (int64_t)ROWS_THREADS + threadIdx.x;
+    if (i >= P.n_pos) return;
+    if (P.skip && P.skip[i]) return;
+    const int ny = 2 * P.ky + 1, nz = 2 * P.kz + 1;
+    double2 e1x[NA], e1y[NA], e1z[NA], ey[NA], ez0[NA], w[NA], t[NA];
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+        const double* r = P.xyz + ((int64_t)NA * i + a) * 3;
+        const double x = r[0], y = r[1], z = r[2];
+        double f[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {   // row d of invmat * pos (ewald.jl:358), reduced to [0, 1)
+            const double v = P.invmat[d] * x + P.invmat[3 + d] * y + P.invmat[6 + d] * z;
+            f[d] = v - floor(v);
+        }
+        e1x[a] = cis2pi(f[0]);
+        e1y[a] = cis2pi(f[1]);
+        e1z[a] = cis2pi(f[2]);
+        ey[a] = cis2pi(red_prod(-(double)P.ky, f[1]));
+        const double2 ez = cis2pi(red_prod(-(double)P.kz, f[2]));
+        const double qa = P.q[a];
+        ez0[a] = make_double2(qa * ez.x, qa * ez.y);
+    }
+    double fa = 0.0, aa = 0.0;
+    const RowDev* row = P.rows;
+    for (int jy = 0; jy < ny; jy++) {
+#pragma unroll
+        for (int a = 0; a < NA; a++) w[a] = cmul(ey[a], ez0[a]);
+        for (int jz = 0; jz < nz; jz++, row++) {
+            const RowDev rd = *row;
+            if (rd.count > 0) {
+#pragma unroll
+                for (int a = 0; a < NA; a++) t[a] = w[a];
+                for (int s = 0; s < rd.ix0; s++) {
+#pragma unroll
+                    for (int a = 0; a < NA; a++) t[a] = cmul(t[a], e1x[a]);
+                }
+                const double* kf = P.kf + rd.offset;
+                const double2* ksf = P.ksf + rd.offset;
+                for (int c = 0; c < rd.count; c++) {
+                    double sre = t[0].x, sim = t[0].y;
+#pragma unroll
+                    for (int a = 1; a < NA; a++) { sre += t[a].x; sim += t[a].y; }
+                    const double2 ks = ksf[c];
+                    fa = fma(ks.x, sre, fma(ks.y, sim, fa));
+                    if (NA > 1) aa = fma(kf[c], fma(sim, sim, sre * sre), aa);
+                    if (c + 1 < rd.count) {
+#pragma unroll
+                        for (int a = 0; a < NA; a++) t[a] = cmul(t[a], e1x[a]);
+                    }
+                }
+            }
+            if (jz + 1 < nz) {
+#pragma unroll
+                for (int a = 0; a < NA; a++) w[a] = cmul(w[a], e1z[a]);
+            }
+        }
+        if (jy + 1 < ny) {
+#pragma unroll
+            for (int a = 0; a < NA; a++) ey[a] = cmul(ey[a], e1y[a]);
+        }
+    }
+    // one atom: S_a(k) = q e^{i phase}, so sum_k kf |S_a|^2 = q^2 sum_k kf (equal to the reference's abs2 sum to
+    // rounding, 1e-16 relative)
+    if (NA == 1) aa = (P.q[0] * P.q[0]) * P.sum_kf;
+    // ewald.jl:572-576
+    const double E = 2.0 * (fa + P.energy_net_charges) + (aa + P.static_contribution);
+    if (P.accumulate) P.out[i] += E; else P.out[i] = E;
+}
+
 }  // namespace ceg

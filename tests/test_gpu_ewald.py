@@ -32,8 +32,12 @@ def test_structure_factor_and_reciprocal_vs_oracle(cuda_lib, orc):
     # batched placements of a 3-site molecule (CO2 geometry) and of a single ion
     rng = np.random.default_rng(3)
     centers = wl.random_positions(fw.mat, 500, 31) * 3.0 - 20.0
-    for q, offs in [(np.array([-0.3256, 0.6512, -0.3256]), np.array([[0, 0, 1.149], [0, 0, 0], [0, 0, -1.149]])),
-                    (np.array([0.9094]), np.zeros((1, 3)))]:
+    # 1-4 atoms: thread-per-placement kernel (rows of the k-list, recurrences); 5: warp-per-placement kernel
+    cases = [(np.array([-0.3256, 0.6512, -0.3256]), np.array([[0, 0, 1.149], [0, 0, 0], [0, 0, -1.149]])),
+             (np.array([0.9094]), np.zeros((1, 3)))]
+    for na in (2, 4, 5):
+        cases.append((rng.standard_normal(na), rng.standard_normal((na, 3)) * 1.5))
+    for q, offs in cases:
         pos = centers[:, None, :] + offs[None, :, :]
         enc, stat = 12.5, -3.25
         got = ceg._lib.ewald_reciprocal(ef.handle, pos, q, enc, stat)

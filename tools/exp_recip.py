@@ -33,3 +33,27 @@ for na in (1, 3):
     nk = ef.kspace.num_kvecs
     print(f"reciprocal: {n} placements x {na} atoms, {nk} k-vectors: {ms:.2f} ms, {n/ms/1e3:.2f} M placements/s, "
           f"{n*na*nk/ms/1e6:.1f} G (atom,k) terms/s, checksum {float(d_out.sum()):.9e}")
+
+# ---- fused energy_points / energy_grid through the host API (grids.jl:311-424), wall clock -----------------
+import time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+nx, ny, nz = cset.nodes
+ps = ceg.ProbeSystem(None, None, inputs=inp)
+outs = [np.empty((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
+lam_v, thr_v = ceg.vdw_scaling(); lam_c, thr_c = ceg.coulomb_scaling()
+ceg._lib.grid_build(ps.handle, ceg._lib.make_gridspec(cset), 0, nx, lam_v, thr_v, lam_c, thr_c, outs, None)
+ps.close()
+k = np.float32(ceg.GRID_TO_KELVIN)
+gv = ceg.EnergyGrid(cset, inp.supercell, np.inf, True, (outs[0].astype(np.float64) * ceg.GRID_TO_KELVIN).astype(np.float32))
+gc = ceg.EnergyGrid(cset, inp.supercell, 1e-6, True, (outs[1].astype(np.float64) * ceg.GRID_TO_KELVIN).astype(np.float32))
+qna = float(ex["probe_charge"])
+na_sys = ceg.RASPASystem(np.diag([np.inf] * 3), np.zeros((1, 3)), ["Na"], np.ones(1), np.array([qna]), True)
+setup = ceg.CrystalEnergySetup(fw, na_sys, gc, np.array([qna]), [gv], [0], ef, None, ceg.BlockFile(cset))
+pos = wl.random_positions(fw.mat, n, 6)[:, None, :]
+ceg.energy_points(setup, pos[:1000])
+for rep in range(2):
+    t0 = time.perf_counter(); v, c = ceg.energy_points(setup, pos); t1 = time.perf_counter()
+    print(f"energy_points (host API, {n} Na+ placements): {1e3*(t1-t0):.2f} ms, {n/(t1-t0)/1e6:.1f} M points/s")
+for rep in range(2):
+    t0 = time.perf_counter(); eg = ceg.energy_grid(setup, 0.3); t1 = time.perf_counter()
+    print(f"energy_grid(0.3 Å) {eg.shape}: {1e3*(t1-t0):.1f} ms, min {eg.min():.6f} at {np.unravel_index(eg.argmin(), eg.shape)}")
