@@ -30,6 +30,7 @@ WORKLOAD_BUILD = ("C4: CHA_1.4_3b4eeb96 (972 framework atoms, rhombohedral 28.37
 WORKLOAD_INTERP = ("C2: tricubic interpolation of 10^7 random positions (splitmix64 seed 1) on the C1 Na+ VdW and "
                    "Coulomb grids (0.15 Å, 218x204x190 nodes, 270 MB each)")
 N_QUERIES = 10_000_000
+N_RECIP = 1_000_000
 
 
 def env_rank():
@@ -292,6 +293,36 @@ def run_product(args):
     interp_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
     assert np.array_equal(out_np[0], d_e[0].cpu().numpy())
 
+    # ================= reciprocal-space Ewald + fused energy_points (A9/A12), this rank's share =========
+    n_unit = len(ex["site_charge"])
+    fw = ceg.RASPASystem(ex["unit_mat"], ex["positions"][:n_unit], ["X"] * n_unit, np.ones(n_unit), ex["charges"][:n_unit], False)
+    ef = ceg.initialize_ewald(fw, device=dev)
+    qna = float(ex["probe_charge"])
+    n_rec = N_RECIP // world
+    rec_pos = torch.from_numpy(wl.random_positions(cset1.cell.mat, n_rec, 7, start=rank * n_rec)).pin_memory()
+    d_rec = rec_pos.cuda()
+    d_rec_out = torch.empty(n_rec, dtype=torch.float64, device="cuda")
+    for _ in range(W):
+        ceg._lib.ewald_reciprocal_dev(ef.handle, n_rec, np.array([qna]), d_rec.data_ptr(), 0.0, 0.0, d_rec_out.data_ptr(), stream)
+    barrier()
+    e0.record()
+    for _ in range(KI):
+        ceg._lib.ewald_reciprocal_dev(ef.handle, n_rec, np.array([qna]), d_rec.data_ptr(), 0.0, 0.0, d_rec_out.data_ptr(), stream)
+    e1.record()
+    barrier()
+    rec_ms = max_over_ranks(e0.elapsed_time(e1)) / KI
+    n_k = ef.kspace.num_kvecs
+    na_sys = ceg.RASPASystem(np.diag([np.inf] * 3), np.zeros((1, 3)), ["Na"], np.ones(1), np.array([qna]), True)
+    setup = ceg.CrystalEnergySetup(fw, na_sys, eg_c, np.array([qna]), [eg_v], [0], ef, None, ceg.BlockFile(cset1))
+    rec_np = rec_pos.numpy()[:, None, :]
+    ceg.energy_points(setup, rec_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ceg.energy_points(setup, rec_np)
+    barrier()
+    ep_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+
     # ================= CPU baseline (rank 0, N = 1 only): the oracle on the host cores ===============
     cpu = None
     cpu_i = None
@@ -320,7 +351,7 @@ def run_product(args):
                          "frac_of_register_operand_peak": my_tflops / fp64_peak_regops if fp64_peak_regops else None,
                          "algorithmic_flop_per_point": fl_pp, "pairs_in_cutoff_per_point": n_in_pp,
                          "pairs_tested_per_point": stats["pairs_tested"] / max(1, stats["n_points"]),
-                         "kernel": "grid_build_tiled_kernel<512,1,true,true>", "kernel_ms": my_ms},
+                         "kernel": "grid_build_tiled_kernel<256,1,true,true>", "kernel_ms": my_ms},
             "gpu_launches": int(build_launches),
             "clocks": clocks,
             "c1": {"workload": "C1: same framework, 0.15 Å (218x204x190 = 8,449,680 points), VdW + Coulomb grids, 1 GPU",
@@ -340,6 +371,17 @@ def run_product(args):
                        "gpu_launches": int(interp_launches), "clocks": clocks2,
                        "blocked_fraction": blocked_fraction, "checksum_K": checksum,
                        "cpu_baseline": cpu_i},
+            "ewald": {"metric": "reciprocal-space Ewald placements/sec (one Na+ per placement)",
+                      "value": n_rec * world / (rec_ms * 1e-3), "unit": "placements/s", "ms_per_step": rec_ms, "steps": KI,
+                      "config": {"workload": f"{N_RECIP} random Na+ placements in the C1 cell, k-space (8,8,8), {n_k} k-vectors "
+                                             "(compute_ewald, ewald.jl:555-577)", "parallelism": f"placements x{world}"},
+                      "roofline": {"bound": "fp64", "achieved": 15.0 * n_k * n_rec / (rec_ms * 1e-3) / 1e12, "peak": fp64_peak,
+                                   "unit": "TFLOP/s", "frac": 15.0 * n_k * n_rec / (rec_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                                   "algorithmic_flop_per_atom_k": 15, "kernel": "reciprocal_rows_kernel<1>"},
+                      "energy_points_e2e": {"value": n_rec * world / (ep_ms * 1e-3), "unit": "placements/s", "ms_per_step": ep_ms,
+                                            "note": "energy_points (grids.jl:311-327 batched): host positions in, host (vdw, coulomb) "
+                                                    "out; 2 interpolations + reciprocal term per placement",
+                                            "h2d_bytes_per_step": int(n_rec * world * 24), "d2h_bytes_per_step": int(n_rec * world * 16)}},
             "cpu_baseline": cpu,
             "gpu_launches_total": int(total_launches),
             "device": ceg._lib.device_info(dev),
