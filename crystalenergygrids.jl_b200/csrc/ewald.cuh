@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) reciprocal_rows_kernel(const Row
                 }
                 const double* kf = P.kf + rd.offset;
                 const double2* ksf = P.ksf + rd.offset;
+#pragma unroll 4
                 for (int c = 0; c < rd.count; c++) {
                     double sre = t[0].x, sim = t[0].y;
 #pragma unroll
@@ -265,10 +266,9 @@ __global__ void __launch_bounds__(ROWS_THREADS) reciprocal_rows_kernel(const Row
                     const double2 ks = ksf[c];
                     fa = fma(ks.x, sre, fma(ks.y, sim, fa));
                     if (NA > 1) aa = fma(kf[c], fma(sim, sim, sre * sre), aa);
-                    if (c + 1 < rd.count) {
+                    // unconditional (one wasted product per row): a select per k costs more issue slots
 #pragma unroll
-                        for (int a = 0; a < NA; a++) t[a] = cmul(t[a], e1x[a]);
-                    }
+                    for (int a = 0; a < NA; a++) t[a] = cmul(t[a], e1x[a]);
                 }
             }
             if (jz + 1 < nz) {
