@@ -37,6 +37,24 @@ def env_rank():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def bind_to_gpu_cpus(gpu_index: int):
+    """Run this process on the CPU cores NVML reports as local to its GPU, so that the host arrays it first
+    touches (and pins) sit on the NUMA node behind the GPU's PCIe root.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def slabs(n, parts):
     from ceg_b200.sharding import split_range
     return split_range(n, parts)
@@ -127,6 +145,7 @@ def run_product(args):
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
     dev = local_rank
+    local_cpus = bind_to_gpu_cpus(local_rank) if world > 1 else 0
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
@@ -196,9 +215,10 @@ def run_product(args):
     host = [torch.empty((8, nx, ny, nz), dtype=torch.float32).pin_memory() if world == 1 else
             torch.empty((8, nx, ny, nz), dtype=torch.float32) for _ in range(2)]
     host_np = [h.numpy() for h in host]
-    if world > 1:   # pin only this rank's slab pages is not expressible; register the whole array once
+    if world > 1:   # pin this rank's slab only: 8 contiguous runs per grid (sharding.slab_file_runs)
         for h in host_np:
-            ceg._lib.host_register(h)
+            for c in range(8):
+                ceg._lib.host_register(h[c, a:b])
     h2d_bytes = (inp.positions.nbytes + inp.types.nbytes + inp.charges.nbytes + inp.table.nbytes + 200)
     d2h_bytes = 2 * 8 * (b - a) * ny * nz * 4
 
@@ -338,14 +358,17 @@ def run_product(args):
             "ms_per_step": build_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "real CHA_1.4_3b4eeb96 framework fixture (flattened, tests/golden/cha_na.npz); "
                                      "synthetic query positions",
-            "config": {"workload": WORKLOAD_BUILD, "parallelism": f"x-slab x{world}",
+            "config": {"workload": WORKLOAD_BUILD, "parallelism": f"x-slab x{world}", "cpus_bound_per_rank": local_cpus,
                        "l2": "no L2 flush: inputs (<1 MB image list) are re-read by every tile by design; each step "
                              "writes 1.8 GB of output (> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_total),
                     "ms_per_step": e2e_ms, "note": "ceg_probe_create + ceg_grid_build into pinned host arrays + free"},
             "roofline": {"bound": "fp64", "achieved": my_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": my_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": my_tflops / fp64_peak if fp64_peak else None,
+                         # ncu --set full, C4 main launch (profiles/r01_ncu_build_v6_final.csv): 13.05 MB read +
+                         # 1781.69 MB written for 324x306x284 points = 63.74 B per point (64 B algorithmic)
+                         "traffic": 63.74 * stats["n_points"], "traffic_unit": "bytes per step (this rank), from the ncu capture",
                          "peak_source": "ceg_measure_fp64_peak (DFMA chains with uniform operands, this run); nominal 37.2",
                          "peak_register_operands": fp64_peak_regops,
                          "frac_of_register_operand_peak": my_tflops / fp64_peak_regops if fp64_peak_regops else None,
@@ -366,7 +389,10 @@ def run_product(args):
                                "note": "ceg_interpolate_multi: positions uploaded once for both grids, chunked on two streams",
                                "ms_per_step": interp_e2e_ms},
                        "roofline": {"bound": "hbm", "achieved": interp_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                    "frac": interp_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                                    "frac": interp_gbs / hbm_peak, "peak_source": hbm_src,
+                                    # ncu --set full (profiles/r01_ncu_interp_v3_final.csv): 4.294 GB read + 0.120 GB
+                                    # written per launch of 10^7 queries = 441 B per query (288 B algorithmic)
+                                    "traffic": 441.4 * nq, "traffic_unit": "bytes per launch (this rank), from the ncu capture",
                                     "algorithmic_bytes_per_query": 288, "kernel": "interpolate_kernel"},
                        "gpu_launches": int(interp_launches), "clocks": clocks2,
                        "blocked_fraction": blocked_fraction, "checksum_K": checksum,
