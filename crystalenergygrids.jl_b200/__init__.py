@@ -20,7 +20,7 @@ from .ewald import (EwaldContext, EwaldFramework, EwaldKspace, adsorbate_sums, b
 from .forcefields import (ForceField, InteractionRule, InteractionRuleSum, Kind, Mixing, UndefinedInteractionError,
                           get_atom_name, needsvdwgrid, pair_dtype, pair_table)
 from .grids import (CrystalEnergySetup, EnergyGrid, build_grids, coulomb_scaling, create_grid_coulomb,
-                    create_grid_vdw, energy_grid, energy_point, energy_points, interpolate_grid, parse_grid,
+                    create_grid_vdw, energy_grid, energy_point, energy_points, interpolate_grid, interpolate_sweep, parse_grid,
                     vdw_scaling, write_grid)
 from .probes import (ProbeInputs, ProbeSystem, compute_derivatives_ewald, compute_derivatives_vdw, probe_inputs,
                      replicate_framework)

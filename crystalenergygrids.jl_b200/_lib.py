@@ -42,7 +42,7 @@ EXPORTS = [
     "ceg_measure_fp64_peak", "ceg_measure_fp64_peak_regops", "ceg_selftest_math", "ceg_host_register",
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
-    "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
+    "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_interpolate_sweep", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
     "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
 ]
 
@@ -267,6 +267,18 @@ def interpolate_multi(handles, xyz, outs=None) -> np.ndarray:
     ptrs = (c_double_p * G)(*[_p(outs[g], C.c_double) for g in range(G)])
     _check(load().ceg_interpolate_multi(C.c_int32(G), hs, C.c_int64(n), _p(xyz, C.c_double), ptrs))
     return outs
+
+
+def interpolate_sweep(h, first: int, n: int, seed: int, mat, n_keep: int = 0):
+    """-> dict(sum, min, n_blocked, keep[n_keep], kernel_ms): energies at n device-generated positions."""
+    m = np.ascontiguousarray(np.asarray(mat, dtype=np.float64).T).ravel()     # column-major
+    s, mn, nb, ms = C.c_double(), C.c_double(), C.c_int64(), C.c_float()
+    n_keep = int(min(n_keep, n))
+    keep = np.empty(n_keep, dtype=np.float64)
+    _check(load().ceg_interpolate_sweep(h, C.c_int64(first), C.c_int64(n), C.c_uint64(seed), _p(m, C.c_double),
+                                        C.byref(s), C.byref(mn), C.byref(nb), C.c_int64(n_keep),
+                                        _p(keep, C.c_double) if n_keep else None, C.byref(ms)))
+    return {"sum": s.value, "min": mn.value, "n_blocked": nb.value, "keep": keep, "kernel_ms": ms.value}
 
 
 def interpolate_dev(h, n: int, d_xyz: int, d_out: int, stream: int = 0):

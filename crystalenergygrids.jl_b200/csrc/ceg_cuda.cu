@@ -828,6 +828,54 @@ extern "C" int ceg_interpolate_dev(ceg_grid_h h, int64_t n, const double* d_xyz,
     return 0;
 }
 
+extern "C" int ceg_interpolate_sweep(ceg_grid_h h, int64_t first, int64_t n, uint64_t seed, const double* mat,
+                                     double* sum, double* min, int64_t* n_blocked, int64_t n_keep, double* keep,
+                                     float* kernel_ms) {
+    if (!h || first < 0 || n < 0 || !mat || !sum || !min || !n_blocked || n_keep < 0 || (n_keep > 0 && !keep))
+        return fail("ceg_interpolate_sweep: bad argument");
+    *sum = 0.0; *min = INFINITY; *n_blocked = 0;
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (n == 0) return 0;
+    n_keep = std::min(n_keep, n);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    const int blocks = 148 * 8;          // fixed: the reduction order (and so the sum) does not depend on n
+    DevBuf d_mat, d_part, d_res, d_keep;
+    CEG_CK(d_mat.reserve(sizeof(double) * 9));
+    CEG_CK(d_part.reserve(sizeof(SweepPartial) * blocks));
+    CEG_CK(d_res.reserve(sizeof(SweepPartial)));
+    CEG_CK(d_keep.reserve(sizeof(double) * std::max<int64_t>(1, n_keep)));
+    cudaStream_t s = h->stream;
+    CEG_CK(cudaMemcpyAsync(d_mat.p, mat, sizeof(double) * 9, cudaMemcpyHostToDevice, s));
+    cudaEvent_t e0, e1;
+    CEG_CK(cudaEventCreate(&e0));
+    CEG_CK(cudaEventCreate(&e1));
+    cudaEventRecord(e0, s);
+    switch (h->g.layout) {
+        case LAYOUT_CELL: interpolate_sweep_kernel<LAYOUT_CELL><<<blocks, SWEEP_THREADS, 0, s>>>(h->g, first, n, seed, d_mat.as<double>(), n_keep, d_keep.as<double>(), d_part.as<SweepPartial>()); break;
+        case LAYOUT_QUAD: interpolate_sweep_kernel<LAYOUT_QUAD><<<blocks, SWEEP_THREADS, 0, s>>>(h->g, first, n, seed, d_mat.as<double>(), n_keep, d_keep.as<double>(), d_part.as<SweepPartial>()); break;
+        case LAYOUT_PAIR: interpolate_sweep_kernel<LAYOUT_PAIR><<<blocks, SWEEP_THREADS, 0, s>>>(h->g, first, n, seed, d_mat.as<double>(), n_keep, d_keep.as<double>(), d_part.as<SweepPartial>()); break;
+        default: interpolate_sweep_kernel<LAYOUT_NODE><<<blocks, SWEEP_THREADS, 0, s>>>(h->g, first, n, seed, d_mat.as<double>(), n_keep, d_keep.as<double>(), d_part.as<SweepPartial>()); break;
+    }
+    count_launch();
+    sweep_reduce_kernel<<<1, 32, 0, s>>>(blocks, d_part.as<SweepPartial>(), d_res.as<SweepPartial>());
+    count_launch();
+    cudaEventRecord(e1, s);
+    cudaError_t err = cudaGetLastError();
+    SweepPartial r{};
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&r, d_res.p, sizeof r, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess && n_keep > 0) err = cudaMemcpyAsync(keep, d_keep.p, sizeof(double) * n_keep, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+    float ms = 0.f;
+    if (err == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CEG_CK(err);
+    *sum = r.sum; *min = r.min; *n_blocked = (int64_t)r.blocked;
+    if (kernel_ms) *kernel_ms = ms;
+    return 0;
+}
+
 // Host-pointer path: queries are streamed through the device in chunks on two streams, so that the
 // upload of chunk c+1, the kernels of chunk c and the download of chunk c-1 overlap (PCIe is full
 // duplex).  Every grid of `grids` is evaluated at the same positions, which are uploaded once.

@@ -200,6 +200,76 @@ __global__ void __launch_bounds__(256) interpolate_kernel(const GridDev g, int64
     }
 }
 
+// ---- interpolation sweep over device-generated positions -------------------------------
+// Query i sits at mat * (u0, u1, u2), u_d = splitmix64(seed, 3 i + d) in [0, 1) — bit-identical to
+// workloads.random_positions (un-contracted (m0 u0 + m1 u1) + m2 u2).  The energies are reduced on the device to
+// (sum of the unblocked energies, minimum, blocked count) in a fixed order (per-thread grid-stride partials ->
+// block tree -> one partial per block, summed by sweep_reduce_kernel), so the result does not depend on timing;
+// the first n_keep energies are also written out for the parity check.
+__device__ __forceinline__ double splitmix_unit(uint64_t seed, uint64_t idx) {
+    uint64_t z = (seed * 0x9E3779B97F4A7C15ull + idx + 1ull) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct SweepPartial {
+    double sum, min;
+    unsigned long long blocked;
+    unsigned long long _pad;
+};
+
+constexpr int SWEEP_THREADS = 256;
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(SWEEP_THREADS) interpolate_sweep_kernel(const GridDev g, int64_t first, int64_t n,
+                                                                          uint64_t seed, const double* __restrict__ mat9,
+                                                                          int64_t n_keep, double* __restrict__ keep,
+                                                                          SweepPartial* __restrict__ partial) {
+    double m[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) m[c] = mat9[c];      // column-major 3x3
+    double sum = 0.0, mn = CUDART_INF;
+    unsigned long long blocked = 0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t q = (uint64_t)(first + t);
+        const double u0 = splitmix_unit(seed, 3 * q), u1 = splitmix_unit(seed, 3 * q + 1), u2 = splitmix_unit(seed, 3 * q + 2);
+        const double p[3] = {xadd(xadd(xmul(m[0], u0), xmul(m[3], u1)), xmul(m[6], u2)),
+                             xadd(xadd(xmul(m[1], u0), xmul(m[4], u1)), xmul(m[7], u2)),
+                             xadd(xadd(xmul(m[2], u0), xmul(m[5], u1)), xmul(m[8], u2))};
+        Stencil st;
+        make_stencil(g.uc, g.gs, p, st);
+        const double e = interp_one<LAYOUT>(g, st);
+        if (t < n_keep) keep[t] = e;
+        if (e == 1e100) blocked++;
+        else { sum += e; mn = fmin(mn, e); }
+    }
+    __shared__ SweepPartial s_p[SWEEP_THREADS];
+    s_p[threadIdx.x] = SweepPartial{sum, mn, blocked, 0};
+    __syncthreads();
+    for (int o = SWEEP_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_p[threadIdx.x].sum += s_p[threadIdx.x + o].sum;
+            s_p[threadIdx.x].min = fmin(s_p[threadIdx.x].min, s_p[threadIdx.x + o].min);
+            s_p[threadIdx.x].blocked += s_p[threadIdx.x + o].blocked;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = s_p[0];
+}
+
+__global__ void sweep_reduce_kernel(int n_blocks, const SweepPartial* __restrict__ partial, SweepPartial* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    SweepPartial r{0.0, CUDART_INF, 0, 0};
+    for (int b = 0; b < n_blocks; b++) {
+        r.sum += partial[b].sum;
+        r.min = fmin(r.min, partial[b].min);
+        r.blocked += partial[b].blocked;
+    }
+    *out = r;
+}
+
 // ---- blocking masks ----------------------------------------------------------------------------------
 // parse_blockfile (coordinates.jl:112-167): node (i,j,k) is blocked if it lies within `radius` of a sphere
 // centre under the reference's periodic distance (utils.jl:210-246, literal).  Node positions are

@@ -243,6 +243,17 @@ def interpolate_grid(g: EnergyGrid, point):
     return float(out[0]) if p.ndim == 1 else out
 
 
+def interpolate_sweep(g: EnergyGrid, n: int, seed: int, first: int = 0, n_keep: int = 0):
+    """interpolate_grid over `n` pseudo-random positions of the unit cell generated ON the device
+    (workloads.random_positions(mat, n, seed, first) bit for bit), reduced there to the sum and minimum of the
+    unblocked energies and the blocked count (the 10^9-query sweep).  -> dict."""
+    if math.isnan(g.ewald_precision):
+        raise ValueError("Invalid grid cannot be interpolated!")
+    if g.ewald_precision == -math.inf:
+        return {"sum": 0.0, "min": 0.0 if n else math.inf, "n_blocked": 0, "keep": np.zeros(min(n, n_keep)), "kernel_ms": 0.0}
+    return _lib.interpolate_sweep(g.handle, first, n, seed, g.csetup.cell.mat, n_keep)
+
+
 # ---- batched evaluation ------------------------------------------------------------------------
 @dataclass
 class CrystalEnergySetup:

@@ -38,7 +38,10 @@ def random_positions(mat: np.ndarray, n: int, seed: int, start: int = 0) -> np.n
     """C2: positions mat·(u1,u2,u3), u from splitmix64(seed, 3*i + d)."""
     idx = np.arange(start * 3, (start + n) * 3, dtype=np.uint64)
     u = splitmix64(seed, idx).reshape(n, 3)
-    return u @ np.asarray(mat, dtype=np.float64).T
+    m = np.asarray(mat, dtype=np.float64)
+    # (m0 u0 + m1 u1) + m2 u2 with every product and sum rounded: the device generator of
+    # ceg_interpolate_sweep produces the same bits
+    return (u[:, 0:1] * m[:, 0] + u[:, 1:2] * m[:, 1]) + u[:, 2:3] * m[:, 2]
 
 
 # ---- fixtures ------------------------------------------------------------------------------------

@@ -179,6 +179,14 @@ int ceg_interpolate_dev(ceg_grid_h h, int64_t n, const double* d_xyz, double* d_
 /* Several grids (e.g. the VdW grid of an atom and the Coulomb grid, grids.jl:316-318) at the same
  * positions: positions are uploaded once; outs[g] receives n energies of grids[g]. */
 int ceg_interpolate_multi(int32_t n_grids, const ceg_grid_h* grids, int64_t n, const double* xyz, double* const* outs);
+/* Interpolation sweep over positions generated on the device (the 10^9-query sweep of C5): query
+ * first + t (t < n) sits at mat * (u0,u1,u2), u_d = splitmix64(seed, 3 (first + t) + d) in [0,1), mat = 9 doubles
+ * column-major.  Returns the sum and the minimum of the unblocked energies and the number of blocked (1e100)
+ * queries, reduced on the device in a fixed order; keep (may be NULL) receives the first n_keep energies;
+ * kernel_ms (may be NULL) the device time of the sweep.  Replaces a loop of interpolate_grid (grids.jl:212-273)
+ * over random trial positions. */
+int ceg_interpolate_sweep(ceg_grid_h h, int64_t first, int64_t n, uint64_t seed, const double* mat,
+                          double* sum, double* min, int64_t* n_blocked, int64_t n_keep, double* keep, float* kernel_ms);
 
 /* ------------------------------------------------------------------------------------------
  * Ewald reciprocal space.  ceg_ewald_create replaces setup_Eik + ewald_main_loop! for the

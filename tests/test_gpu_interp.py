@@ -147,3 +147,38 @@ def test_c2_on_built_grids_and_goldens(cuda_lib, orc, tmp_path):
     v0 = ceg.interpolate_grid(gv, np.zeros(3))
     assert abs(v0 - gold["na_cha_origin_vdw"]) <= 1e-9 * abs(gold["na_cha_origin_vdw"])
     gv.close(); gc.close()
+
+
+def test_interpolate_sweep_device_generated_positions(cuda_lib, orc):
+    """ceg_interpolate_sweep: positions generated on the device equal workloads.random_positions bit
+    for bit, so the kept energies equal the batched ceg_interpolate of the host-generated positions exactly; the
+    device reduction (sum, min, blocked count) matches numpy; a split sweep adds up; and the oracle agrees."""
+    inp, cset, _ = wl.load_fixture("cit7_multi")          # triclinic cell
+    cs = wl.respace(cset, 0.5)
+    grid = _random_grid(cs, 5, hot_fraction=0.02)
+    n, seed = 300_000, 4
+    for is_vdw in (True, False):
+        eg = ceg.EnergyGrid(cs, (1, 1, 1), np.inf if is_vdw else 1e-6, True, grid)
+        pos = wl.random_positions(cs.cell.mat, n, seed)
+        want = ceg.interpolate_grid(eg, pos)
+        r = ceg.interpolate_sweep(eg, n, seed, n_keep=n)
+        assert np.array_equal(r["keep"], want)
+        ok = want != 1e100
+        assert r["n_blocked"] == int((~ok).sum()) and (is_vdw == bool(r["n_blocked"]))
+        assert r["min"] == want[ok].min()
+        assert abs(r["sum"] - want[ok].sum()) <= 1e-12 * np.abs(want[ok]).sum()
+        # same sweep in two pieces (how ranks shard it), and run-to-run determinism
+        a = ceg.interpolate_sweep(eg, 100_000, seed, first=0, n_keep=10)
+        b = ceg.interpolate_sweep(eg, n - 100_000, seed, first=100_000, n_keep=10)
+        assert np.array_equal(b["keep"], want[100_000:100_010])
+        assert a["n_blocked"] + b["n_blocked"] == r["n_blocked"] and min(a["min"], b["min"]) == r["min"]
+        assert abs(a["sum"] + b["sum"] - r["sum"]) <= 1e-12 * np.abs(want[ok]).sum()
+        assert ceg.interpolate_sweep(eg, n, seed)["sum"] == r["sum"]
+        # oracle on a sample
+        o = orc.interpolate(cs, grid, is_vdw, pos[:5000])
+        assert np.array_equal(o == 1e100, r["keep"][:5000] == 1e100)
+        m = o != 1e100
+        assert (np.abs(r["keep"][:5000][m] - o[m]) <= RTOL * np.maximum(np.abs(o[m]), 1.0)).all()
+        eg.close()
+    z = ceg.interpolate_sweep(ceg.EnergyGrid.zero(), 10, 1, n_keep=4)
+    assert z["sum"] == 0.0 and z["n_blocked"] == 0 and len(z["keep"]) == 4
