@@ -10,6 +10,9 @@
 #   energy_point/energy_grid  grids.jl:311-424   -> ceg_energy_points
 #   initialize_ewald (S_f) ewald.jl:264-271      -> ceg_ewald_create
 #   compute_ewald(ctx)     ewald.jl:555-577      -> ceg_ewald_reciprocal
+#   single_contribution_ewald  ewald.jl:704-738  -> ceg_ewald_single_contribution   (batched over trial placements)
+#   single_contribution_vdw    energy.jl:397-427 -> ceg_guest_energy                (batched over trial placements)
+#   parse_blockfile / BlockFile(g)  coordinates.jl:112-167, grids.jl:188-204 -> ceg_block_from_spheres / _values
 #
 # Everything else (force-field parsing, CIF loading, .grid headers, caches, Monte-Carlo) is
 # untouched Julia.  Units are stripped to Å / K / e before each `ccall`; every physical constant is
@@ -221,6 +224,82 @@ function reciprocal(h::Ptr{Cvoid}, positions::Array{Float64,3}, q::Vector{Float6
         (Ptr{Cvoid}, Int64, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}),
         h, n_pos, n_atoms, positions, q, ustrip(u"K", energy_net_charges), ustrip(u"K", static_contribution), out))
     out
+end
+
+# single_contribution_ewald (ewald.jl:704-738) for many trial placements of molecule ij:
+# rest = ewald.eframework.StoreRigidChargeFramework + ewald.sums[:,1] - ewald.sums[:,ij+1]
+function single_contributions(h::Ptr{Cvoid}, rest::Vector{ComplexF64}, positions::Array{Float64,3}, q::Vector{Float64})
+    n_atoms, n_pos = size(positions, 2), size(positions, 3)
+    out = Vector{Float64}(undef, n_pos)
+    check(ccall((:ceg_ewald_single_contribution, libceg), Cint,
+        (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+        h, reinterpret(Float64, rest), n_pos, n_atoms, positions, q, out))
+    out
+end
+
+# ---- batched energy_point (grids.jl:311-327; inner loop of energy_grid, :394-419) ------------------------------
+# positions: 3 x n_atoms x n_pos (Å).  vdw_handles[i] may be C_NULL (zero grid); coulomb / ewald / block may be C_NULL.
+function energy_points(vdw_handles::Vector{Ptr{Cvoid}}, coulomb::Ptr{Cvoid}, ewald::Ptr{Cvoid}, block::Ptr{Cvoid},
+                       atomsidx::Vector{Int}, charges::Vector{Float64}, positions::Array{Float64,3},
+                       energy_net_charges, static_contribution)
+    n_atoms, n_pos = size(positions, 2), size(positions, 3)
+    vdw = Vector{Float64}(undef, n_pos); coul = Vector{Float64}(undef, n_pos)
+    check(ccall((:ceg_energy_points, libceg), Cint,
+        (Int32, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Cdouble}, Ptr{Cdouble},
+         Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}),
+        length(vdw_handles), vdw_handles, coulomb, ewald, block, n_pos, n_atoms, Int32.(atomsidx .- 1), charges, positions,
+        ustrip(u"K", energy_net_charges), ustrip(u"K", static_contribution), vdw, coul))
+    vdw, coul
+end
+
+# ---- blocking masks ------------------------------------------------------------------------------------------------
+# BlockFile(g) (grids.jl:188-204): mask[c, b, a] (Julia order of the (a,b,c) BitArray transposed to C order)
+function block_from_values(cs::GridCoordinatesSetup, values::Array{Cfloat,3}; threshold=5f6, device=0)
+    mask = Vector{UInt8}(undef, length(values))
+    check(ccall((:ceg_block_from_values, libceg), Cint, (Int32, Ref{CegGridSpec}, Ptr{Cfloat}, Cfloat, Ptr{UInt8}),
+                device, CegGridSpec(cs), values, threshold, mask))
+    mask
+end
+# parse_blockfile (coordinates.jl:112-167): centers 3 x n (Å, already through inverse_offsetpoint(offsetpoint(.)))
+function block_from_spheres(cell::CegCell, cs::GridCoordinatesSetup, centers::Matrix{Float64}, radius2::Vector{Float64}; device=0)
+    mask = Vector{UInt8}(undef, prod(Int.(cs.dims) .+ 1))
+    check(ccall((:ceg_block_from_spheres, libceg), Cint,
+        (Int32, Ref{CegCell}, Ref{CegGridSpec}, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{UInt8}),
+        device, cell, CegGridSpec(cs), length(radius2), centers, radius2, mask))
+    mask
+end
+
+# ---- guest-guest pair energies (energy.jl:397-427) ---------------------------------------------------------------------
+struct CegPairEnergy
+    flags::Int32
+    _pad::Int32
+    hs_r::Cdouble
+    lj_eps::Cdouble; lj_sigma::Cdouble; lj_shift::Cdouble
+    buck_A::Cdouble; buck_B::Cdouble; buck_C::Cdouble; buck_shift::Cdouble
+    ewald_alpha::Cdouble; ewald_qq::Cdouble; coulomb_qq::Cdouble
+end
+# trial_xyz: 3 x n_atoms x n_trials; env_xyz: 3 x n_env; species / molecule ids 0-based Int32
+function guest_energies(cell::CegCell, cutoff2::Float64, table::Matrix{CegPairEnergy}, env_xyz::Matrix{Float64},
+                        env_species::Vector{Int32}, env_mol::Vector{Int32}, mol_species::Vector{Int32}, skip_mol::Integer,
+                        trial_xyz::Array{Float64,3}; device=0)
+    out = Vector{Float64}(undef, size(trial_xyz, 3))
+    check(ccall((:ceg_guest_energy, libceg), Cint,
+        (Int32, Ref{CegCell}, Cdouble, Int32, Ptr{CegPairEnergy}, Int64, Ptr{Cdouble}, Ptr{Int32}, Ptr{Int32}, Int64, Int32,
+         Ptr{Int32}, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
+        device, cell, cutoff2, size(table, 1), permutedims(table), size(env_xyz, 2), env_xyz, env_species, env_mol,
+        size(trial_xyz, 3), size(trial_xyz, 2), mol_species, skip_mol, trial_xyz, out))
+    out
+end
+
+# ---- interpolation sweep over device-generated positions (benchmarking / sampling) -------------------------------------
+function interpolate_sweep(g::EnergyGrid, n::Integer, seed::Integer; first=0, n_keep=0)
+    mat = collect(Float64.(ustrip.(u"Å", g.csetup.cell.mat)))            # column-major 3x3
+    s = Ref(0.0); mn = Ref(0.0); nb = Ref{Int64}(0); ms = Ref{Cfloat}(0)
+    keep = Vector{Float64}(undef, min(n, n_keep))
+    check(ccall((:ceg_interpolate_sweep, libceg), Cint,
+        (Ptr{Cvoid}, Int64, Int64, UInt64, Ptr{Cdouble}, Ref{Cdouble}, Ref{Cdouble}, Ref{Int64}, Int64, Ptr{Cdouble}, Ref{Cfloat}),
+        handle(g), first, n, seed, mat, s, mn, nb, length(keep), keep, ms))
+    (sum=s[], min=mn[], n_blocked=nb[], keep=keep, kernel_ms=ms[])
 end
 
 end # module
