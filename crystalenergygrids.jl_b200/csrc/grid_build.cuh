@@ -320,8 +320,11 @@ struct BuildParams {
 
 // <= 2 probes: 128 registers per thread whatever the CTA size (512/NT CTAs resident per SM); more probes
 // need the registers for their accumulators.
+#ifndef CEG_BUILD_MINB
+#define CEG_BUILD_MINB(NT) (512 / (NT))
+#endif
 template <int NT, int NP, bool COUL, bool POLY>
-__global__ void __launch_bounds__(NT, NP <= 2 ? 512 / NT : 1) grid_build_tiled_kernel(const BuildParams P) {
+__global__ void __launch_bounds__(NT, NP <= 2 ? CEG_BUILD_MINB(NT) : 1) grid_build_tiled_kernel(const BuildParams P) {
     constexpr int NW = NT / 32;
     const int TX = P.tile[0], TY = P.tile[1], TZ = P.tile[2];   // TX*TY*TZ == NT (8x8x8 main, flatter tail shapes)
     constexpr int NG = NP + (COUL ? 1 : 0);
