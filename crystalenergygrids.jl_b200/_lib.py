@@ -42,7 +42,7 @@ EXPORTS = [
     "ceg_measure_fp64_peak", "ceg_measure_fp64_peak_regops", "ceg_selftest_math", "ceg_host_register",
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
-    "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_interpolate_sweep", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
+    "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_interpolate_sweep", "ceg_energy_lattice", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
     "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
 ]
 
@@ -402,3 +402,24 @@ def energy_points(vdw_handles, coulomb, ewald, block, atomsidx, charges, xyz, en
                                     C.c_double(energy_net_charges), C.c_double(static_contribution),
                                     _p(out_v, C.c_double), _p(out_c, C.c_double)))
     return out_v, out_c
+
+
+def energy_lattice(vdw_handles, coulomb, ewald, block, nums, steps, rotpos, atomsidx, charges, energy_net_charges,
+                   static_contribution) -> np.ndarray:
+    """(n_rot, numA, numB, numC) vdw + coulomb on the lattice of energy_grid, generated on the device."""
+    atomsidx = np.ascontiguousarray(atomsidx, dtype=np.int32)
+    na = atomsidx.shape[0]
+    charges = _f64(charges, (na,))
+    rotpos = _f64(rotpos, (-1, na, 3))
+    nums = np.ascontiguousarray(nums, dtype=np.int32)
+    steps = _f64(steps, (3, 3))
+    nv = len(vdw_handles)
+    arr = (C.c_void_p * max(nv, 1))(*[h if h is not None else C.c_void_p(0) for h in vdw_handles])
+    out = np.empty((rotpos.shape[0], int(nums[0]), int(nums[1]), int(nums[2])), dtype=np.float64)
+    _check(load().ceg_energy_lattice(C.c_int32(nv), arr, coulomb if coulomb is not None else C.c_void_p(0),
+                                     ewald if ewald is not None else C.c_void_p(0),
+                                     block if block is not None else C.c_void_p(0), _p(nums, C.c_int32),
+                                     _p(steps, C.c_double), C.c_int32(rotpos.shape[0]), C.c_int32(na),
+                                     _p(rotpos, C.c_double), _p(atomsidx, C.c_int32), _p(charges, C.c_double),
+                                     C.c_double(energy_net_charges), C.c_double(static_contribution), _p(out, C.c_double)))
+    return out

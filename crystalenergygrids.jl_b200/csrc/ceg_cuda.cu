@@ -1249,28 +1249,21 @@ extern "C" int ceg_block_free(ceg_block_h h) {
     return 0;
 }
 
-extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, ceg_ewald_h ewald,
-                                 ceg_block_h block, int64_t n_pos, int32_t n_atoms, const int32_t* atomsidx,
-                                 const double* charges, const double* xyz, double energy_net_charges,
-                                 double static_contribution, double* out_vdw, double* out_coulomb) {
-    if (n_pos < 0 || n_atoms <= 0 || !atomsidx || !charges || (n_pos > 0 && (!xyz || !out_vdw || !out_coulomb)))
-        return fail("ceg_energy_points: bad argument");
+// Shared front end of ceg_energy_points / ceg_energy_lattice: validates the handles and fills the grid part of
+// the kernel parameters.  Returns -1 when nothing is resident (all grids are zero grids), 0 on success, 1 on error.
+static int energy_points_setup(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, ceg_ewald_h ewald,
+                               ceg_block_h block, int32_t n_atoms, const int32_t* atomsidx, EnergyPointsParams& P) {
     if (n_vdw < 0 || n_vdw > EP_MAX_VDW) return fail("ceg_energy_points: too many distinct VdW grids");
-    if (n_pos == 0) return 0;
     int device = -1;
     for (int g = 0; g < n_vdw; g++)
         if (vdw && vdw[g]) device = vdw[g]->device;
     if (coulomb) device = coulomb->device;
     if (ewald) device = ewald->device;
     if (block) device = block->device;
-    if (device < 0) {   // nothing resident: all grids are zero grids
-        for (int64_t i = 0; i < n_pos; i++) { out_vdw[i] = 0.0; out_coulomb[i] = 0.0; }
-        return 0;
-    }
+    if (device < 0) return -1;
     for (int a = 0; a < n_atoms; a++)
         if (atomsidx[a] < 0 || atomsidx[a] >= std::max(1, n_vdw)) return fail("ceg_energy_points: atomsidx out of range");
     if (use_device(device)) return 1;
-    EnergyPointsParams P;
     memset(&P, 0, sizeof P);
     P.n_vdw = n_vdw;
     for (int g = 0; g < n_vdw; g++) {
@@ -1285,7 +1278,44 @@ extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_
     P.has_block = block ? 1 : 0;
     if (block) P.block = block->b;
     P.n_atoms = n_atoms;
+    return 0;
+}
+
+// Device part shared by both entry points: positions already on the device (d_xyz, n_pos x n_atoms x 3);
+// d_v / d_c receive the VdW and Coulomb energies.  Everything is enqueued on `s`.
+static int energy_points_enqueue(EnergyPointsParams P, ceg_ewald_h ewald, bool has_coulomb, int64_t n_pos, int32_t n_atoms,
+                                 const double* d_xyz, double enc, double stat, double* d_v, double* d_c, uint8_t* d_blk,
+                                 cudaStream_t s) {
     P.n_pos = n_pos;
+    P.xyz = d_xyz;
+    P.out_vdw = d_v;
+    P.out_coulomb = d_c;
+    P.blocked = d_blk;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_pos + 127) / 128, 148 * 32));
+    energy_points_kernel<<<blocks, 128, 0, s>>>(P);
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    if (has_coulomb && ewald && ewald->n_k > 0) {
+        std::lock_guard<std::mutex> lk(ewald->mu);
+        if (launch_reciprocal(ewald, n_pos, n_atoms, d_xyz, P.charges, enc, stat, d_c, d_blk, 1, s)) return 1;
+    }
+    return 0;
+}
+
+extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, ceg_ewald_h ewald,
+                                 ceg_block_h block, int64_t n_pos, int32_t n_atoms, const int32_t* atomsidx,
+                                 const double* charges, const double* xyz, double energy_net_charges,
+                                 double static_contribution, double* out_vdw, double* out_coulomb) {
+    if (n_pos < 0 || n_atoms <= 0 || !atomsidx || !charges || (n_pos > 0 && (!xyz || !out_vdw || !out_coulomb)))
+        return fail("ceg_energy_points: bad argument");
+    if (n_pos == 0) return 0;
+    EnergyPointsParams P;
+    const int st = energy_points_setup(n_vdw, vdw, coulomb, ewald, block, n_atoms, atomsidx, P);
+    if (st > 0) return 1;
+    if (st < 0) {   // nothing resident: all grids are zero grids
+        for (int64_t i = 0; i < n_pos; i++) { out_vdw[i] = 0.0; out_coulomb[i] = 0.0; }
+        return 0;
+    }
     cudaStream_t s;
     CEG_CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     DevBuf d_idx, d_q, d_xyz, d_v, d_c, d_blk;
@@ -1303,22 +1333,70 @@ extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_
         CK2(cudaMemcpyAsync(d_xyz.p, xyz, sizeof(double) * 3 * n_atoms * n_pos, cudaMemcpyHostToDevice, s));
         P.atomsidx = d_idx.as<int>();
         P.charges = d_q.as<double>();
-        P.xyz = d_xyz.as<double>();
-        P.out_vdw = d_v.as<double>();
-        P.out_coulomb = d_c.as<double>();
-        P.blocked = d_blk.as<uint8_t>();
-        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_pos + 127) / 128, 148 * 32));
-        energy_points_kernel<<<blocks, 128, 0, s>>>(P);
-        count_launch();
-        CK2(cudaGetLastError());
-        if (coulomb && ewald && ewald->n_k > 0) {
-            std::lock_guard<std::mutex> lk(ewald->mu);
-            if (launch_reciprocal(ewald, n_pos, n_atoms, P.xyz, P.charges, energy_net_charges, static_contribution,
-                                  P.out_coulomb, P.blocked, 1, s)) { rc = 1; break; }
-        }
+        if (energy_points_enqueue(P, ewald, coulomb != nullptr, n_pos, n_atoms, d_xyz.as<double>(), energy_net_charges,
+                                  static_contribution, d_v.as<double>(), d_c.as<double>(), d_blk.as<uint8_t>(), s)) { rc = 1; break; }
         CK2(cudaMemcpyAsync(out_vdw, d_v.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, s));
         CK2(cudaMemcpyAsync(out_coulomb, d_c.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, s));
         CK2(cudaStreamSynchronize(s));
+    } while (0);
+    cudaStreamDestroy(s);
+    return rc;
+}
+
+// energy_grid (grids.jl:346-424) with the lattice generated on the device: point (iA, iB, iC) of rotation r has its
+// atoms at (iA stepA + iB stepB) + iC stepC + rotpos[r][a] (the reference's left-to-right sum, grids.jl:396, each
+// product and sum rounded).  out[r][iA][iB][iC] = vdw + coulomb of energy_point (1e100 when blocked).
+extern "C" int ceg_energy_lattice(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, ceg_ewald_h ewald,
+                                  ceg_block_h block, const int32_t* nums, const double* steps, int32_t n_rot,
+                                  int32_t n_atoms, const double* rotpos, const int32_t* atomsidx, const double* charges,
+                                  double energy_net_charges, double static_contribution, double* out) {
+    if (!nums || !steps || n_rot <= 0 || n_atoms <= 0 || !rotpos || !atomsidx || !charges || !out)
+        return fail("ceg_energy_lattice: bad argument");
+    if (nums[0] <= 0 || nums[1] <= 0 || nums[2] <= 0) return fail("ceg_energy_lattice: empty lattice");
+    const int64_t n_lat = (int64_t)nums[0] * nums[1] * nums[2];
+    EnergyPointsParams P;
+    const int st = energy_points_setup(n_vdw, vdw, coulomb, ewald, block, n_atoms, atomsidx, P);
+    if (st > 0) return 1;
+    if (st < 0) {
+        for (int64_t i = 0; i < n_lat * n_rot; i++) out[i] = 0.0;
+        return 0;
+    }
+    cudaStream_t s;
+    CEG_CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    DevBuf d_idx, d_q, d_rot, d_xyz, d_v, d_c, d_blk;
+    int rc = 0;
+    do {
+        CK2(d_idx.reserve(sizeof(int) * n_atoms));
+        CK2(d_q.reserve(sizeof(double) * n_atoms));
+        CK2(d_rot.reserve(sizeof(double) * 3 * n_atoms * n_rot));
+        CK2(d_xyz.reserve(sizeof(double) * 3 * n_atoms * n_lat));
+        CK2(d_v.reserve(sizeof(double) * n_lat));
+        CK2(d_c.reserve(sizeof(double) * n_lat));
+        CK2(d_blk.reserve(n_lat));
+        CK2(cudaMemcpyAsync(d_idx.p, atomsidx, sizeof(int) * n_atoms, cudaMemcpyHostToDevice, s));
+        CK2(cudaMemcpyAsync(d_q.p, charges, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, s));
+        CK2(cudaMemcpyAsync(d_rot.p, rotpos, sizeof(double) * 3 * n_atoms * n_rot, cudaMemcpyHostToDevice, s));
+        P.atomsidx = d_idx.as<int>();
+        P.charges = d_q.as<double>();
+        LatticeParams L;
+        for (int d = 0; d < 3; d++) L.nums[d] = nums[d];
+        for (int d = 0; d < 9; d++) L.steps[d] = steps[d];
+        L.n_atoms = n_atoms;
+        L.n_lat = n_lat;
+        const int blocks = (int)std::min<int64_t>((n_lat + 255) / 256, 148 * 32);
+        for (int r = 0; r < n_rot && !rc; r++) {      // one rotation per pass bounds the scratch to one lattice
+            L.rotpos = d_rot.as<double>() + (size_t)3 * n_atoms * r;
+            lattice_positions_kernel<<<blocks, 256, 0, s>>>(L, d_xyz.as<double>());
+            count_launch();
+            CK2(cudaGetLastError());
+            if (energy_points_enqueue(P, ewald, coulomb != nullptr, n_lat, n_atoms, d_xyz.as<double>(), energy_net_charges,
+                                      static_contribution, d_v.as<double>(), d_c.as<double>(), d_blk.as<uint8_t>(), s)) { rc = 1; break; }
+            add_energies_kernel<<<blocks, 256, 0, s>>>(n_lat, d_v.as<double>(), d_c.as<double>());
+            count_launch();
+            CK2(cudaGetLastError());
+            CK2(cudaMemcpyAsync(out + (size_t)n_lat * r, d_v.p, sizeof(double) * n_lat, cudaMemcpyDeviceToHost, s));
+        }
+        if (!rc) CK2(cudaStreamSynchronize(s));
 #undef CK2
     } while (0);
     cudaStreamDestroy(s);

@@ -319,6 +319,38 @@ __global__ void __launch_bounds__(256) block_from_values_kernel(const float* __r
     }
 }
 
+// ---- lattice of energy_grid (grids.jl:346-424) ---------------------------------------------------------
+// Point l = (iA * numB + iB) * numC + iC; atom a of the probe sits at ((iA stepA + iB stepB) + iC stepC) + rotpos[a],
+// every product and sum rounded (the reference's left-to-right sum, grids.jl:396).
+struct LatticeParams {
+    int nums[3];
+    int n_atoms;
+    double steps[9];        // steps[3 d + c]: component c of the step along cell axis d
+    int64_t n_lat;
+    const double* rotpos;   // n_atoms x 3 (device): molecule offsets of the current rotation
+};
+
+__global__ void __launch_bounds__(256) lattice_positions_kernel(const LatticeParams L, double* __restrict__ xyz) {
+    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < L.n_lat; l += (int64_t)gridDim.x * blockDim.x) {
+        int64_t n = l;
+        const double iC = (double)(n % L.nums[2]); n /= L.nums[2];
+        const double iB = (double)(n % L.nums[1]);
+        const double iA = (double)(n / L.nums[1]);
+        double o[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            o[c] = xadd(xadd(xmul(iA, L.steps[c]), xmul(iB, L.steps[3 + c])), xmul(iC, L.steps[6 + c]));
+        for (int a = 0; a < L.n_atoms; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) xyz[(l * L.n_atoms + a) * 3 + c] = xadd(o[c], L.rotpos[3 * a + c]);
+    }
+}
+
+__global__ void __launch_bounds__(256) add_energies_kernel(int64_t n, double* __restrict__ v, const double* __restrict__ c) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] = xadd(v[i], c[i]);
+}
+
 // ---- fused energy_point (grids.jl:311-318): block test + VdW and Coulomb interpolation ------------
 constexpr int EP_MAX_VDW = 8;
 struct EnergyPointsParams {

@@ -293,12 +293,7 @@ class CrystalEnergySetup:
                 pass
 
 
-def energy_points(setup: CrystalEnergySetup, positions, reciprocal: bool = True):
-    """Batched energy_point: positions (n_pos, n_atoms, 3) -> (vdw[n_pos], coulomb[n_pos]).
-    With reciprocal=False the Coulomb part is only the interpolated real-space grid term, i.e.
-    framework_interactions of the Monte-Carlo loop (montecarlo.jl:490-504)."""
-    na = len(setup.atomsidx)
-    pos = np.asarray(positions, dtype=np.float64).reshape(-1, na, 3)
+def _energy_args(setup: CrystalEnergySetup, reciprocal: bool):
     for g in setup.grids:
         if math.isnan(g.ewald_precision):
             raise ValueError("Invalid grid cannot be interpolated!")
@@ -309,7 +304,17 @@ def energy_points(setup: CrystalEnergySetup, positions, reciprocal: bool = True)
     if has_coulomb and reciprocal and setup.ewald.alpha != 0:
         ctx = setup.ewald_ctx()
         ew, enc, static = setup.ewald.handle, ctx.energy_net_charges, ctx.static_contribution
-    return _lib.energy_points(vdw_handles, coul, ew, setup.block_handle(), setup.atomsidx, setup.charges, pos, enc, static)
+    return vdw_handles, coul, ew, setup.block_handle(), enc, static
+
+
+def energy_points(setup: CrystalEnergySetup, positions, reciprocal: bool = True):
+    """Batched energy_point: positions (n_pos, n_atoms, 3) -> (vdw[n_pos], coulomb[n_pos]).
+    With reciprocal=False the Coulomb part is only the interpolated real-space grid term, i.e.
+    framework_interactions of the Monte-Carlo loop (montecarlo.jl:490-504)."""
+    na = len(setup.atomsidx)
+    pos = np.asarray(positions, dtype=np.float64).reshape(-1, na, 3)
+    vdw_handles, coul, ew, blk, enc, static = _energy_args(setup, reciprocal)
+    return _lib.energy_points(vdw_handles, coul, ew, blk, setup.atomsidx, setup.charges, pos, enc, static)
 
 
 def energy_point(setup: CrystalEnergySetup, positions, ctx=None):
@@ -318,7 +323,7 @@ def energy_point(setup: CrystalEnergySetup, positions, ctx=None):
     return float(v[0]), float(c[0])
 
 
-def energy_grid(setup: CrystalEnergySetup, step: float, num_rotate: int = 40, rotations=None, chunk: int = 1 << 20):
+def energy_grid(setup: CrystalEnergySetup, step: float, num_rotate: int = 40, rotations=None):
     """grids.jl:346-424 — energies on a numA x numB x numC lattice along the CELL axes.
 
     Returns float64 array (n_rot, numA, numB, numC) with vdw+coulomb in K.  The reference draws
@@ -335,16 +340,8 @@ def energy_grid(setup: CrystalEnergySetup, step: float, num_rotate: int = 40, ro
         rotpos = [mol_pos]
     else:
         rotpos = [mol_pos @ np.asarray(r, dtype=np.float64).T for r in rotations]
-    numA, numB, numC = nums
-    iA, iB, iC = np.meshgrid(np.arange(numA), np.arange(numB), np.arange(numC), indexing="ij")
-    # thisofs = (iA-1)*stepA + (iB-1)*stepB + (iC-1)*stepC, summed left to right (grids.jl:396)
-    ofs = (iA[..., None] * steps[0] + iB[..., None] * steps[1]) + iC[..., None] * steps[2]
-    ofs = ofs.reshape(-1, 3)
-    allvals = np.empty((len(rotpos), numA * numB * numC), dtype=np.float64)
-    for k, pos in enumerate(rotpos):
-        for s in range(0, ofs.shape[0], chunk):
-            o = ofs[s:s + chunk]
-            buf = o[:, None, :] + pos[None, :, :]
-            v, c = energy_points(setup, buf)
-            allvals[k, s:s + chunk] = v + c
-    return allvals.reshape(len(rotpos), numA, numB, numC)
+    # thisofs = (iA-1)*stepA + (iB-1)*stepB + (iC-1)*stepC, summed left to right (grids.jl:396): generated on the
+    # device together with the evaluation (ceg_energy_lattice)
+    vdw_handles, coul, ew, blk, enc, static = _energy_args(setup, True)
+    return _lib.energy_lattice(vdw_handles, coul, ew, blk, nums, np.array(steps), np.array(rotpos), setup.atomsidx,
+                               setup.charges, enc, static)

@@ -253,6 +253,14 @@ int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, 
                       const double* charges /* n_atoms */, const double* xyz /* n_pos x n_atoms x 3 */,
                       double energy_net_charges, double static_contribution,
                       double* out_vdw /* n_pos */, double* out_coulomb /* n_pos */);
+/* energy_grid (grids.jl:346-424) with the lattice generated on the device: nums = (numA, numB, numC), steps[3 d + c] =
+ * component c of axis_d / num_d, rotpos = n_rot x n_atoms x 3 rotated molecule offsets.  Point (iA, iB, iC) of rotation
+ * r: atoms at (iA stepA + iB stepB) + iC stepC + rotpos[r][a] (grids.jl:396).  out[r][iA][iB][iC] = vdw + coulomb of
+ * energy_point at that placement (1e100 when blocked).  Other arguments as ceg_energy_points. */
+int ceg_energy_lattice(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, ceg_ewald_h ewald, ceg_block_h block,
+                       const int32_t* nums, const double* steps, int32_t n_rot, int32_t n_atoms, const double* rotpos,
+                       const int32_t* atomsidx, const double* charges, double energy_net_charges,
+                       double static_contribution, double* out /* n_rot x numA x numB x numC */);
 
 #ifdef __cplusplus
 }

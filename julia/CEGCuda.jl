@@ -252,6 +252,21 @@ function energy_points(vdw_handles::Vector{Ptr{Cvoid}}, coulomb::Ptr{Cvoid}, ewa
     vdw, coul
 end
 
+# energy_grid (grids.jl:346-424): the lattice (iA-1)stepA + (iB-1)stepB + (iC-1)stepC + rotpos is generated on the
+# device.  steps: 3 x 3 (column d = axis_d / num_d, Å); rotpos: 3 x n_atoms x n_rot.  Returns (numC, numB, numA, n_rot)
+# in Julia's column-major order, i.e. permutedims(., (4,3,2,1)) of the reference's allvals.
+function energy_lattice(vdw_handles::Vector{Ptr{Cvoid}}, coulomb::Ptr{Cvoid}, ewald::Ptr{Cvoid}, block::Ptr{Cvoid},
+                        nums::NTuple{3,Int}, steps::Matrix{Float64}, rotpos::Array{Float64,3}, atomsidx::Vector{Int},
+                        charges::Vector{Float64}, energy_net_charges, static_contribution)
+    out = Array{Float64,4}(undef, nums[3], nums[2], nums[1], size(rotpos, 3))
+    check(ccall((:ceg_energy_lattice, libceg), Cint,
+        (Int32, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Cdouble}, Int32, Int32, Ptr{Cdouble},
+         Ptr{Int32}, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cdouble}),
+        length(vdw_handles), vdw_handles, coulomb, ewald, block, Int32[nums...], steps, size(rotpos, 3), size(rotpos, 2), rotpos,
+        Int32.(atomsidx .- 1), charges, ustrip(u"K", energy_net_charges), ustrip(u"K", static_contribution), out))
+    out
+end
+
 # ---- blocking masks ------------------------------------------------------------------------------------------------
 # BlockFile(g) (grids.jl:188-204): mask[c, b, a] (Julia order of the (a,b,c) BitArray transposed to C order)
 function block_from_values(cs::GridCoordinatesSetup, values::Array{Cfloat,3}; threshold=5f6, device=0)

@@ -162,3 +162,17 @@ def test_setup_raspa_co2_fused_grids_and_cache(cuda_lib, orc, tmp_path):
     assert np.abs(rec - wrec).max() <= 1e-9 * np.abs(wrec).max()
     wgg = orc.guest_energy(env, setup.atomsidx, pos[:500], 0)
     assert np.abs(wgg).max() > 0 and (np.abs(gg - wgg) <= 1e-9 * np.abs(wgg) + 1e-6).all()
+    # energy_grid (grids.jl:346-424): lattice generated on the device == energy_point over the host-built lattice
+    th = 0.7
+    rots = [np.eye(3), np.array([[1, 0, 0], [0, np.cos(th), -np.sin(th)], [0, np.sin(th), np.cos(th)]])]
+    eg = ceg.energy_grid(setup, 1.1, num_rotate=2, rotations=rots)
+    m = np.asarray(fw.mat, dtype=np.float64)
+    nums = [int(np.floor(np.linalg.norm(m[:, d]) / 1.1)) + 1 for d in range(3)]
+    steps = [m[:, d] / nums[d] for d in range(3)]
+    assert eg.shape == (2, *nums)
+    iA, iB, iC = np.meshgrid(*[np.arange(k) for k in nums], indexing="ij")
+    ofs = ((iA[..., None] * steps[0] + iB[..., None] * steps[1]) + iC[..., None] * steps[2]).reshape(-1, 3)
+    for k, R in enumerate(rots):
+        v2, c2 = ceg.energy_points(setup, ofs[:, None, :] + (mol @ R.T)[None, :, :])
+        assert np.array_equal(eg[k].ravel(), v2 + c2)
+    assert (eg == 1e100).any() and (eg < 0).any()
