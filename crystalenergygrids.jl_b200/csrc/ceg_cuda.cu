@@ -497,7 +497,10 @@ struct TileShape { int tx, ty, tz; };
 #ifndef CEG_BUILD_NT
 #define CEG_BUILD_NT 256       // threads per CTA of the <= 2 probe variants
 #endif
-static int build_nt(int n_probes) { return n_probes <= 2 ? CEG_BUILD_NT : 256; }
+#ifndef CEG_BUILD_NT_MANY
+#define CEG_BUILD_NT_MANY 256  // threads per CTA of the 3 and 4 probe variants
+#endif
+static int build_nt(int n_probes) { return n_probes <= 2 ? CEG_BUILD_NT : CEG_BUILD_NT_MANY; }
 static int main_tx(int n_probes) { return build_nt(n_probes) / 64; }
 // tx x 8 x 8 nodes, the remaining factor of the thread count going to z and y alternately:
 // 512 threads: {8,8,8} {4,8,16} {2,16,16} {1,16,32};  256: {4,8,8} {2,8,16} {1,16,16};  128: {2,8,8} {1,8,16}
@@ -515,7 +518,7 @@ static double tile_radius(const TileShape& t, const double* delta) {
 
 template <int NP, bool COUL>
 static cudaError_t dispatch_np(const BuildParams& P, int n_tiles, cudaStream_t s) {
-    constexpr int NT = NP <= 2 ? CEG_BUILD_NT : 256;
+    constexpr int NT = NP <= 2 ? CEG_BUILD_NT : CEG_BUILD_NT_MANY;
     if (COUL && P.poly_erfcx) return launch_tiled<NT, NP, COUL, true>(P, n_tiles, s);
     return launch_tiled<NT, NP, COUL, false>(P, n_tiles, s);
 }

@@ -318,13 +318,16 @@ struct BuildParams {
     unsigned long long* stats; // [0] pairs tested, [1] pairs in cutoff
 };
 
-// <= 2 probes: 128 registers per thread whatever the CTA size (512/NT CTAs resident per SM); more probes
-// need the registers for their accumulators.
+// 128 registers per thread whatever the CTA size (512/NT CTAs, 16 warps resident per SM).  The 3 and 4 probe
+// variants would like ~200 registers for their 32-40 accumulators, but at 8 resident warps per SM the FP64 pipe
+// idles on dependency stalls: capped at 128 (a few hundred bytes of spills) they run 21 % faster (C3: 11.4 -> 9.1 ms).
+// With fewer registers still (96 or 80, more CTAs) every variant gets slower.
 #ifndef CEG_BUILD_MINB
 #define CEG_BUILD_MINB(NT) (512 / (NT))
 #endif
 template <int NT, int NP, bool COUL, bool POLY>
-__global__ void __launch_bounds__(NT, NP <= 2 ? CEG_BUILD_MINB(NT) : 1) grid_build_tiled_kernel(const BuildParams P) {
+__global__ void __launch_bounds__(NT, CEG_BUILD_MINB(NT))
+grid_build_tiled_kernel(const BuildParams P) {
     constexpr int NW = NT / 32;
     const int TX = P.tile[0], TY = P.tile[1], TZ = P.tile[2];   // TX*TY*TZ == NT (8x8x8 main, flatter tail shapes)
     constexpr int NG = NP + (COUL ? 1 : 0);
