@@ -390,10 +390,10 @@ def run_product(args):
                                "ms_per_step": interp_e2e_ms},
                        "roofline": {"bound": "hbm", "achieved": interp_gbs, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": interp_gbs / hbm_peak, "peak_source": hbm_src,
-                                    # ncu --set full (profiles/r01_ncu_interp_v3_final.csv): 4.294 GB read + 0.120 GB
-                                    # written per launch of 10^7 queries = 441 B per query (288 B algorithmic)
-                                    "traffic": 441.4 * nq, "traffic_unit": "bytes per launch (this rank), from the ncu capture",
-                                    "algorithmic_bytes_per_query": 288, "kernel": "interpolate_kernel"},
+                                    # ncu --set full (profiles/r01_ncu_interp_v4_block.csv): 3.903 GB read + 0.121 GB
+                                    # written per launch of 10^7 queries = 402 B per query (288 B algorithmic)
+                                    "traffic": 402.4 * nq, "traffic_unit": "bytes per launch (this rank), from the ncu capture",
+                                    "algorithmic_bytes_per_query": 288, "kernel": "interpolate_kernel<BLOCK>"},
                        "gpu_launches": int(interp_launches), "clocks": clocks2,
                        "blocked_fraction": blocked_fraction, "checksum_K": checksum,
                        "cpu_baseline": cpu_i},

@@ -746,7 +746,7 @@ extern "C" int ceg_probe_last_stats(ceg_probe_h h, int64_t* n_points, int64_t* p
 static std::atomic<int> g_interp_layout{-1};   // -1 = automatic
 
 extern "C" int ceg_set_interp_layout(int32_t layout) {
-    if (layout < -1 || layout > LAYOUT_PAIR) return fail("ceg_set_interp_layout: layout must be -1 (default), 0, 1, 2 or 3");
+    if (layout < -1 || layout > LAYOUT_BLOCK) return fail("ceg_set_interp_layout: layout must be -1 (default), 0, 1, 2, 3 or 4");
     g_interp_layout.store(layout);
     return 0;
 }
@@ -772,11 +772,14 @@ extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const
     const int64_t npts = (int64_t)nx * ny * nz;
     const size_t node_bytes = sizeof(float) * 8 * (size_t)npts;
     CEG_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    // layout: node records unless the caller asked otherwise.  Measured on B200 (10^7 random queries,
-    // 218x204x190 grid): NODE 0.70 ms, QUAD 1.42 ms, CELL 1.57 ms — the 4x/8x footprints (1-2 GB) fall
-    // out of TLB reach and of the L2, which costs more than the over-fetch they remove.
+    // layout unless the caller asked otherwise: 2x2x2-node bricks once the grid no longer fits the L2, plain node
+    // records below.  Measured on B200 (10^7 random queries): 34 MB grid NODE 0.384 / BLOCK 0.396 ms; 270 MB grid
+    // NODE 0.700 / BLOCK 0.627 / PAIR 1.12 / QUAD 1.42 / CELL 1.57 ms; 907 MB grid NODE 1.359 / BLOCK 1.356 ms; 4 GB
+    // grid (10^9-query sweep) NODE 174 / BLOCK 184 ms.  The
+    // duplicating layouts lose to their own footprint; the bricks remove half of the 64-byte-granularity over-fetch
+    // of a z pair without growing the grid.
     int layout = g_interp_layout.load();
-    if (layout < 0) layout = LAYOUT_NODE;
+    if (layout < 0) layout = (node_bytes > ((size_t)96 << 20) && node_bytes < ((size_t)1536 << 20)) ? LAYOUT_BLOCK : LAYOUT_NODE;
     {
         DevBuf tmp, nodes;
         DevBuf& node_dst = (layout == LAYOUT_NODE) ? h->d_nodes : nodes;
@@ -787,7 +790,13 @@ extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const
         relayout_nodes_kernel<<<blocks, 256, 0, h->stream>>>(tmp.as<float>(), node_dst.as<Rec8>(), npts);
         count_launch();
         CEG_CK(cudaGetLastError());
-        if (layout != LAYOUT_NODE) {
+        if (layout == LAYOUT_BLOCK) {
+            const size_t bricks = (size_t)((nx + 1) / 2) * ((ny + 1) / 2) * ((nz + 1) / 2);
+            CEG_CK(h->d_nodes.reserve(sizeof(Rec8) * 8 * bricks));
+            block_records_kernel<<<148 * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz);
+            count_launch();
+            CEG_CK(cudaGetLastError());
+        } else if (layout != LAYOUT_NODE) {
             const int corners = (layout == LAYOUT_PAIR) ? 2 : (layout == LAYOUT_QUAD) ? 4 : 8;
             CEG_CK(h->d_nodes.reserve(node_bytes * corners));
             expand_records_kernel<<<148 * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz, corners);
@@ -817,6 +826,7 @@ static cudaError_t launch_interpolate(const GridDev& g, int64_t n, const double*
         case LAYOUT_CELL: interpolate_kernel<LAYOUT_CELL><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
         case LAYOUT_QUAD: interpolate_kernel<LAYOUT_QUAD><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
         case LAYOUT_PAIR: interpolate_kernel<LAYOUT_PAIR><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
+        case LAYOUT_BLOCK: interpolate_kernel<LAYOUT_BLOCK><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
         default: interpolate_kernel<LAYOUT_NODE><<<blocks, 256, 0, s>>>(g, n, d_xyz, d_out); break;
     }
     count_launch();
@@ -858,6 +868,7 @@ extern "C" int ceg_interpolate_sweep(ceg_grid_h h, int64_t first, int64_t n, uin
         case LAYOUT_CELL: interpolate_sweep_kernel<LAYOUT_CELL><<<blocks, SWEEP_THREADS, 0, s>>>(h->g, first, n, seed, d_mat.as<double>(), n_keep, d_keep.as<double>(), d_part.as<SweepPartial>()); break;
         case LAYOUT_QUAD: interpolate_sweep_kernel<LAYOUT_QUAD><<<blocks, SWEEP_THREADS, 0, s>>>(h->g, first, n, seed, d_mat.as<double>(), n_keep, d_keep.as<double>(), d_part.as<SweepPartial>()); break;
         case LAYOUT_PAIR: interpolate_sweep_kernel<LAYOUT_PAIR><<<blocks, SWEEP_THREADS, 0, s>>>(h->g, first, n, seed, d_mat.as<double>(), n_keep, d_keep.as<double>(), d_part.as<SweepPartial>()); break;
+        case LAYOUT_BLOCK: interpolate_sweep_kernel<LAYOUT_BLOCK><<<blocks, SWEEP_THREADS, 0, s>>>(h->g, first, n, seed, d_mat.as<double>(), n_keep, d_keep.as<double>(), d_part.as<SweepPartial>()); break;
         default: interpolate_sweep_kernel<LAYOUT_NODE><<<blocks, SWEEP_THREADS, 0, s>>>(h->g, first, n, seed, d_mat.as<double>(), n_keep, d_keep.as<double>(), d_part.as<SweepPartial>()); break;
     }
     count_launch();

@@ -11,7 +11,10 @@
 //   PAIR  [x][y][z0]           64 B records = nodes (z0),(z0+1), 2x memory: 4 aligned 64 B fetches;
 //   QUAD  [x][y0][z0]         128 B records = nodes (y0,z0),(y0,z1),(y1,z0),(y1,z1), 4x memory:
 //                              2 aligned 128 B lines per query;
-//   CELL  [x0][y0][z0]        256 B records = all 8 corners, 8x memory: one aligned 256 B block.
+//   CELL  [x0][y0][z0]        256 B records = all 8 corners, 8x memory: one aligned 256 B block;
+//   BLOCK [x/2][y/2][z/2]     256 B bricks of 2x2x2 nodes (no duplication, 1x memory): a z-pair, a (y,z) quad or
+//                              the whole stencil share one aligned 64 / 128 / 256 B unit whenever the lower corner
+//                              is even along those axes.
 // ncu on the NODE layout (round 1) showed 595 B of DRAM traffic per query for 288 algorithmic bytes:
 // the L2 fetches whole 64/128 B neighbourhoods of every 32 B sector.  QUAD/CELL make every fetched
 // byte useful.  Each record is read with one 256-bit load per corner (LDG.E.256).
@@ -26,7 +29,7 @@
 
 namespace ceg {
 
-enum { LAYOUT_NODE = 0, LAYOUT_QUAD = 1, LAYOUT_CELL = 2, LAYOUT_PAIR = 3 };
+enum { LAYOUT_NODE = 0, LAYOUT_QUAD = 1, LAYOUT_CELL = 2, LAYOUT_PAIR = 3, LAYOUT_BLOCK = 4 };
 
 struct GridDev {
     CellDev uc;
@@ -74,6 +77,23 @@ __global__ void __launch_bounds__(256) expand_records_kernel(const Rec8* __restr
     }
 }
 
+// NODE -> BLOCK: brick (bx,by,bz) holds nodes (2bx+ix, 2by+iy, 2bz+iz) at slot (ix*2+iy)*2+iz; bricks on the upper
+// faces of an odd-sized grid are padded with copies of the last node (never read).
+__global__ void __launch_bounds__(256) block_records_kernel(const Rec8* __restrict__ nodes, Rec8* __restrict__ dst,
+                                                            int nx, int ny, int nz) {
+    const int nby = (ny + 1) / 2, nbz = (nz + 1) / 2, nbx = (nx + 1) / 2;
+    const int64_t total = (int64_t)nbx * nby * nbz * 8;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t & 7);
+        int64_t b = t >> 3;
+        const int bz = (int)(b % nbz); b /= nbz;
+        const int by = (int)(b % nby);
+        const int bx = (int)(b / nby);
+        const int x = min(2 * bx + ((c >> 2) & 1), nx - 1), y = min(2 * by + ((c >> 1) & 1), ny - 1), z = min(2 * bz + (c & 1), nz - 1);
+        dst[t] = nodes[((int64_t)x * ny + y) * nz + z];
+    }
+}
+
 __device__ __forceinline__ void ld_rec(const float* p, float4& lo, float4& hi) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
@@ -117,7 +137,22 @@ __device__ __forceinline__ double interp_one(const GridDev& g, const Stencil& st
     float4 lo[8], hi[8];
     const int64_t ny = g.gs.n[1], nz = g.gs.n[2];
     const int64_t base = ((int64_t)st.p0[0] * ny + st.p0[1]) * nz + st.p0[2];
-    if (LAYOUT == LAYOUT_CELL) {
+    if (LAYOUT == LAYOUT_BLOCK) {
+        const int64_t nby = (ny + 1) >> 1, nbz = (nz + 1) >> 1;
+#pragma unroll
+        for (int ix = 0; ix < 2; ix++)
+#pragma unroll
+            for (int iy = 0; iy < 2; iy++)
+#pragma unroll
+                for (int iz = 0; iz < 2; iz++) {
+                    const int x = st.p0[0] + (ix ? st.step[0] : 0), y = st.p0[1] + (iy ? st.step[1] : 0),
+                              z = st.p0[2] + (iz ? st.step[2] : 0);
+                    const int64_t rec = ((((int64_t)(x >> 1) * nby + (y >> 1)) * nbz + (z >> 1)) << 3) +
+                                        (((x & 1) * 2 + (y & 1)) * 2 + (z & 1));
+                    const int n = (ix * 2 + iy) * 2 + iz;
+                    ld_rec(g.data + rec * 8, lo[n], hi[n]);
+                }
+    } else if (LAYOUT == LAYOUT_CELL) {
         const float* rec = g.data + base * 64;
 #pragma unroll
         for (int n = 0; n < 8; n++) ld_rec(rec + 8 * n, lo[n], hi[n]);
@@ -185,6 +220,7 @@ __device__ __forceinline__ double interp_any(const GridDev& g, const Stencil& st
         case LAYOUT_CELL: return interp_one<LAYOUT_CELL>(g, st);
         case LAYOUT_QUAD: return interp_one<LAYOUT_QUAD>(g, st);
         case LAYOUT_PAIR: return interp_one<LAYOUT_PAIR>(g, st);
+        case LAYOUT_BLOCK: return interp_one<LAYOUT_BLOCK>(g, st);
         default: return interp_one<LAYOUT_NODE>(g, st);
     }
 }

@@ -171,7 +171,8 @@ int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridsp
 int ceg_grid_free(ceg_grid_h h);
 /* Device record layout used by subsequent ceg_grid_upload calls: 0 = node records (1x memory),
  * 1 = (y,z) quads (4x), 2 = whole 8-corner cells (8x, one aligned 256 B block per query),
- * -1 = default (node records: measured fastest on B200 once the grid exceeds the L2). */
+ * 3 = z pairs (2x), 4 = 2x2x2-node bricks of 256 B (1x memory),
+ * -1 = default (bricks for grids between 96 MB and 1.5 GB, node records otherwise: the fastest measured on B200). */
 int ceg_set_interp_layout(int32_t layout);
 int ceg_grid_layout(ceg_grid_h h, int32_t* layout);
 int ceg_interpolate(ceg_grid_h h, int64_t n, const double* xyz /* n x 3 Cartesian Å */, double* out /* n, K */);

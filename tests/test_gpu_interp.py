@@ -35,7 +35,7 @@ def _check(orc, cset, grid, is_vdw, pos, what):
     return blocked.mean()
 
 
-@pytest.fixture(params=[0, 1, 2, 3], ids=["node", "quad", "cell", "pair"])
+@pytest.fixture(params=[0, 1, 2, 3, 4], ids=["node", "quad", "cell", "pair", "block"])
 def layout(request, cuda_lib):
     """Every device record layout (include/ceg_cuda.h: ceg_set_interp_layout) must give the same answers."""
     ceg._lib.set_interp_layout(request.param)
