@@ -124,6 +124,7 @@ def test_c2_on_built_grids_and_goldens(cuda_lib, orc, tmp_path):
     p = (51 * mat[:, 0] / nums[0] + 49 * mat[:, 1] / nums[1]) + 90 * mat[:, 2] / nums[2]
     e = ceg.interpolate_grid(eg, p)
     assert abs(e - gold["ar_chana_min"]) <= 1e-9 * abs(gold["ar_chana_min"]), (e, gold["ar_chana_min"])
+    assert ceg._lib.grid_layout(eg.handle) == 4        # 270 MB grid: 2x2x2-node bricks by default
     pos = wl.random_positions(mat, 200000, 1)
     got = ceg.interpolate_grid(eg, pos)
     want = orc.interpolate(eg.csetup, eg.grid, True, pos)
