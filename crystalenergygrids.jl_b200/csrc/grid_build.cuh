@@ -11,7 +11,7 @@
 //    (min-image search of utils.jl:210-246 for every supercell atom, division-based formulas).
 //    Backs ceg_compute_derivatives; its device functions are also the "exact" path of the tiled
 //    kernel.
-//  * grid_build_tiled_kernel — the production kernel.  One CTA owns a TXxTYxTZ tile (8x8x8) of grid
+//  * grid_build_tiled_kernel — the production kernel.  One CTA owns a TXxTYxTZ tile (4x8x8) of grid
 //    nodes; it scans the pre-expanded list of periodic atom IMAGES (atom-major order, built on the
 //    host for the slab's bounding region), keeps those within cutoff + tile radius of the tile
 //    centre with an ORDERED compaction into shared memory, and every thread (one node each) walks
@@ -329,7 +329,7 @@ template <int NT, int NP, bool COUL, bool POLY>
 __global__ void __launch_bounds__(NT, CEG_BUILD_MINB(NT))
 grid_build_tiled_kernel(const BuildParams P) {
     constexpr int NW = NT / 32;
-    const int TX = P.tile[0], TY = P.tile[1], TZ = P.tile[2];   // TX*TY*TZ == NT (8x8x8 main, flatter tail shapes)
+    const int TX = P.tile[0], TY = P.tile[1], TZ = P.tile[2];   // TX*TY*TZ == NT (4x8x8 main, flatter tail shapes)
     constexpr int NG = NP + (COUL ? 1 : 0);
     __shared__ ExtAtom s_atom[LIST_CAP];
     __shared__ ExtMeta s_meta[LIST_CAP];
