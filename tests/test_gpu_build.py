@@ -186,3 +186,37 @@ def test_error_paths(cuda_lib):
     with pytest.raises(ceg.CegError):
         ceg._lib.grid_build(ps.handle, gs, 0, 1, 1, 1, 1, 1, [None, None], None)
     ps.close()
+
+
+def test_registered_host_output_and_cache_trim(cuda_lib):
+    """ceg_host_register pins a caller-owned output array (what a multi-process driver does with its slab runs);
+    the build into it gives the same bytes; ceg_trim_device_cache releases the pooled device scratch and the next
+    call simply re-allocates."""
+    inp, cset, _ = wl.load_fixture("cha_na")
+    cs = wl.respace(cset, 0.6)
+    nx, ny, nz = cs.nodes
+    gs = ceg._lib.make_gridspec(cs)
+    lam_v, thr_v = ceg.vdw_scaling()
+    lam_c, thr_c = ceg.coulomb_scaling()
+    ps = _probe(inp)
+    plain = [np.zeros((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
+    ceg._lib.grid_build(ps.handle, gs, 0, nx, lam_v, thr_v, lam_c, thr_c, plain, None)
+    pinned = [np.zeros((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
+    for p in pinned:
+        for c in range(8):
+            ceg._lib.host_register(p[c, 3:nx - 2])          # the 8 runs of an x-slab
+    n0 = ceg._lib.kernel_launch_count()
+    ceg._lib.grid_build(ps.handle, gs, 3, nx - 2, lam_v, thr_v, lam_c, thr_c, pinned, None)
+    assert ceg._lib.kernel_launch_count() > n0
+    for p in pinned:
+        for c in range(8):
+            ceg._lib.host_unregister(p[c, 3:nx - 2])
+    for g in range(2):
+        assert np.array_equal(pinned[g][:, 3:nx - 2], plain[g][:, 3:nx - 2]) and not pinned[g][:, :3].any()
+    ceg._lib.trim_device_cache()
+    again = [np.zeros((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
+    ceg._lib.grid_build(ps.handle, gs, 0, nx, lam_v, thr_v, lam_c, thr_c, again, None)
+    assert np.array_equal(again[0], plain[0]) and np.array_equal(again[1], plain[1])
+    ps.close()
+    info = ceg._lib.device_info(0)
+    assert info["sm_count"] > 0 and info["mem_bytes"] > 0

@@ -241,3 +241,27 @@ def test_restart_baseline_co2_in_cha_na(cuda_lib, orc):
     assert abs(total - gold["restart_baseline_co2"]) <= 1e-6 * abs(total), total
     for g in grids + [gc]:
         g.close()
+
+
+def test_reciprocal_with_a_k_list_that_is_not_made_of_rows(cuda_lib, orc):
+    """ceg_ewald_create accepts any k-list.  A shuffled one cannot be walked row by row, so the reciprocal term falls
+    back to the warp-per-placement kernel; the energies equal those of the ordered list (same terms, other order)."""
+    inp, cset, ex = wl.load_fixture("cha_na")
+    fw = _framework_from_fixture(ex)
+    ef = ceg.initialize_ewald(fw)
+    frac, charge = ceg.framework_sites(fw, tuple(int(x) for x in ex["supercell"]))
+    kvec = ef.kspace.kvec_array()
+    perm = np.random.default_rng(5).permutation(len(kvec))
+    from ceg_b200.cell import flat
+    h2, S2 = ceg._lib.ewald_create(0, flat(ef.invmat), np.array(ef.kspace.ks, dtype=np.int32), kvec[perm], ef.kfactors[perm],
+                                   frac, charge)
+    scale = np.abs(ef.StoreRigidChargeFramework).max()
+    assert np.abs(S2 - ef.StoreRigidChargeFramework[perm]).max() <= 1e-11 * scale
+    pos = wl.random_positions(fw.mat, 2000, 77)
+    q = np.array([-0.3256, 0.6512, -0.3256])
+    geom = np.array([[0, 0, 1.149], [0, 0, 0.0], [0, 0, -1.149]])
+    for qq, p in ((np.array([0.9094]), pos[:, None, :]), (q, pos[:, None, :] + geom[None])):
+        a = ceg._lib.ewald_reciprocal(ef.handle, p, qq, 3.0, -1.5)
+        b = ceg._lib.ewald_reciprocal(h2, p, qq, 3.0, -1.5)
+        assert np.abs(a - b).max() <= 1e-10 * np.abs(a).max()
+    ceg._lib.ewald_free(h2)
