@@ -35,7 +35,7 @@ namespace {
 struct PoolEntry { void* p; size_t bytes; int device; };
 std::mutex g_pool_mu;
 std::vector<PoolEntry> g_pool;
-constexpr size_t POOL_MIN = 1u << 20;
+constexpr size_t POOL_MIN = 4096;          // smaller buffers go straight to cudaMalloc/cudaFree
 constexpr size_t POOL_CAP = 4ull << 30;      // at most 4 GiB parked per process
 size_t g_pool_bytes = 0;
 }  // namespace
@@ -670,12 +670,19 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
     bool any_out = false;
     for (int g = 0; g < ng; g++) any_out |= (out_f32 && out_f32[g]);
     // Device scratch is a ring of RING x-chunks (not the whole slab): chunk c is computed on s_compute into
-    // slot c % RING while earlier chunks drain to the host on s_copy, so the footprint stays ~150 MB for any
-    // grid size and no large allocation is made or freed per call.
+    // slot c % RING while earlier chunks drain to the host on s_copy, so the footprint stays bounded (3 x 192 MB at
+    // most) for any grid size and no large allocation is made or freed per call.  Large slabs start with big chunks
+    // (few launches, small launch tails) and finish with small ones (only the last chunk's copy is not overlapped).
     constexpr int RING = 3;
     const int mtx = main_tx(h->n_probes);
-    const int chunk = std::max(mtx, ((int)((48ll << 20) / (plane * 8 * 4 * ng)) / mtx) * mtx);
-    const int64_t chunk_slab = (int64_t)chunk * plane;
+    const int small = std::max(mtx, ((int)((48ll << 20) / (plane * 8 * 4 * ng)) / mtx) * mtx);
+    const int big = (i1 - i0 >= 16 * small) ? 4 * small : small;
+    auto next_chunk = [&](int remaining) {
+        if (remaining >= big + small) return big;
+        if (remaining > 2 * small) return std::max(small, (remaining / 2) / mtx * mtx);
+        return std::min(remaining, small);
+    };
+    const int64_t chunk_slab = (int64_t)big * plane;
     if (any_out) CEG_CK(h->d_out.reserve(sizeof(float) * 8 * chunk_slab * ng * RING));
     if (raw_f64) CEG_CK(h->d_raw.reserve(sizeof(double) * 8 * slab * ng));
     CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), h->s_compute));
@@ -685,8 +692,8 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
         CEG_CK(cudaEventCreateWithFlags(&ev_free[r], cudaEventDisableTiming));
     }
     int rc = 0, c = 0;
-    for (int a = i0; a < i1 && !rc; a += chunk, c++) {
-        const int b = std::min(i1, a + chunk);
+    for (int a = i0, b = i0; a < i1 && !rc; a = b, c++) {
+        b = a + next_chunk(i1 - a);
         const int slot = c % RING;
         float* base = any_out ? h->d_out.as<float>() + (int64_t)slot * 8 * chunk_slab * ng : nullptr;
         const int64_t cslab = (int64_t)(b - a) * plane;       // the kernel indexes outputs relative to [P.i0, P.i1)
