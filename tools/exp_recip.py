@@ -36,7 +36,6 @@ for na in (1, 3):
 
 # ---- fused energy_points / energy_grid through the host API (grids.jl:311-424), wall clock -----------------
 import time
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 nx, ny, nz = cset.nodes
 ps = ceg.ProbeSystem(None, None, inputs=inp)
 outs = [np.empty((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
