@@ -121,6 +121,9 @@ struct ceg_probe_s {
     int n_ext = 0;
     double ext_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool ext_valid = false;
+    // last slab whose image list was too long to be scanned by every tile: remembered so that repeated builds of
+    // the same slab go straight to its x windows (list_windows)
+    int split_i0 = -1, split_i1 = -1, split_dims[3] = {0, 0, 0};
     // scratch for host-facing builds
     DevBuf d_out, d_raw, d_pos, d_der;
     int64_t last_points = 0;
@@ -641,18 +644,54 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     return 0;
 }
 
+// Every tile scans the image list of the range it belongs to, and that list grows with the range's bounding box:
+// C1-C5 slabs give <= 8k images (the scan hides behind the co-resident CTA's pair phase), a 512-plane slab of an 85 Å
+// cell 60k (15 % slower, tools/exp_stress.py).  Thick slabs of large cells are therefore processed as x windows of
+// about 64 planes, each with its own list.
+constexpr int EXT_SPLIT_MIN = 12000;
+constexpr int LIST_WINDOW_PLANES = 64;
+static int list_windows(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i1, double lam_v, double thr_v, double lam_c,
+                        double thr_c, std::vector<std::pair<int, int>>& win) {
+    win.clear();
+    const int planes = i1 - i0;
+    bool split = (h->split_i0 == i0 && h->split_i1 == i1 && gs && memcmp(h->split_dims, gs->dims, sizeof h->split_dims) == 0);
+    if (!split && planes > 2 * LIST_WINDOW_PLANES) {
+        BuildParams P;
+        if (prepare_build(h, gs, i0, i1, lam_v, thr_v, lam_c, thr_c, P)) return 1;
+        split = P.n_ext > EXT_SPLIT_MIN;
+        if (split) {
+            h->split_i0 = i0; h->split_i1 = i1;
+            memcpy(h->split_dims, gs->dims, sizeof h->split_dims);
+        }
+    }
+    if (!split) {
+        win.push_back({i0, i1});
+        return 0;
+    }
+    const int mtx = main_tx(h->n_probes);
+    const int n_win = (planes + LIST_WINDOW_PLANES - 1) / LIST_WINDOW_PLANES;
+    const int w = ((planes + n_win - 1) / n_win + mtx - 1) / mtx * mtx;
+    for (int a = i0; a < i1; a += w) win.push_back({a, std::min(i1, a + w)});
+    return 0;
+}
+
 extern "C" int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
                                   double thr_vdw, double lambda_coul, double thr_coul, float* const* d_out, void* stream) {
     if (!h || !d_out) return fail("ceg_grid_build_dev: null argument");
     std::lock_guard<std::mutex> lk(h->mu);
     if (use_device(h->device)) return 1;
-    BuildParams P;
-    if (prepare_build(h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, P)) return 1;
+    std::vector<std::pair<int, int>> win;
+    if (list_windows(h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, win)) return 1;
     const int ng = h->n_probes + h->want_coulomb;
-    for (int g = 0; g < ng; g++) P.out[g] = d_out[g];
     cudaStream_t s = (cudaStream_t)stream;
     CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), s));
-    CEG_CK(launch_planes(h, P, gs, std::sqrt(h->cutoff2), i0, i1, s));
+    for (const auto& w : win) {
+        BuildParams P;
+        if (prepare_build(h, gs, w.first, w.second, lambda_vdw, thr_vdw, lambda_coul, thr_coul, P)) return 1;
+        P.i0 = i0; P.i1 = i1;                       // the output buffers hold the caller's whole slab
+        for (int g = 0; g < ng; g++) P.out[g] = d_out[g];
+        CEG_CK(launch_planes(h, P, gs, std::sqrt(h->cutoff2), w.first, w.second, s));
+    }
     h->last_points = (int64_t)(i1 - i0) * (gs->dims[1] + 1) * (gs->dims[2] + 1);
     return 0;
 }
@@ -662,8 +701,8 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
     if (!h) return fail("ceg_grid_build: null handle");
     std::lock_guard<std::mutex> lk(h->mu);
     if (use_device(h->device)) return 1;
-    BuildParams P;
-    if (prepare_build(h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, P)) return 1;
+    std::vector<std::pair<int, int>> win;
+    if (list_windows(h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, win)) return 1;
     const int ng = h->n_probes + h->want_coulomb;
     const int64_t ny = gs->dims[1] + 1, nz = gs->dims[2] + 1, nx = gs->dims[0] + 1;
     const int64_t plane = ny * nz, slab = (int64_t)(i1 - i0) * plane, npts = nx * plane;
@@ -692,8 +731,12 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
         CEG_CK(cudaEventCreateWithFlags(&ev_free[r], cudaEventDisableTiming));
     }
     int rc = 0, c = 0;
-    for (int a = i0, b = i0; a < i1 && !rc; a = b, c++) {
-        b = a + next_chunk(i1 - a);
+    for (size_t wi = 0; wi < win.size() && !rc; wi++) {
+    BuildParams P;   // image list of this window (prepare_build drains the device before replacing the list)
+    if (prepare_build(h, gs, win[wi].first, win[wi].second, lambda_vdw, thr_vdw, lambda_coul, thr_coul, P)) { rc = 1; break; }
+    const int w1 = win[wi].second;
+    for (int a = win[wi].first, b = a; a < w1 && !rc; a = b, c++) {
+        b = a + next_chunk(w1 - a);
         const int slot = c % RING;
         float* base = any_out ? h->d_out.as<float>() + (int64_t)slot * 8 * chunk_slab * ng : nullptr;
         const int64_t cslab = (int64_t)(b - a) * plane;       // the kernel indexes outputs relative to [P.i0, P.i1)
@@ -723,6 +766,7 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
             }
             cudaEventRecord(ev_free[slot], h->s_copy);
         }
+    }
     }
     cudaError_t e1 = cudaStreamSynchronize(h->s_compute);
     cudaError_t e2 = cudaStreamSynchronize(h->s_copy);

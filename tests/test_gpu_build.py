@@ -220,3 +220,25 @@ def test_registered_host_output_and_cache_trim(cuda_lib):
     ps.close()
     info = ceg._lib.device_info(0)
     assert info["sm_count"] > 0 and info["mem_bytes"] > 0
+
+
+def test_thick_slab_of_a_large_cell_uses_x_windows(cuda_lib):
+    """A 50 Å cell with 5000 atoms at 0.25 Å: the image list of the whole 201-plane grid (> 12k images) is replaced
+    by per-window lists (ceg_cuda.cu: list_windows).  Same bytes as the planes built as separate thin slabs."""
+    inp, cset, fw = wl.synthetic_inputs("mof", 0.25, ("C_ch4",), True)
+    nx, ny, nz = cset.nodes
+    assert nx > 128
+    gs = ceg._lib.make_gridspec(cset)
+    lam_v, thr_v = ceg.vdw_scaling()
+    lam_c, thr_c = ceg.coulomb_scaling()
+    ps = _probe(inp)
+    full = [np.zeros((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
+    ceg._lib.grid_build(ps.handle, gs, 0, nx, lam_v, thr_v, lam_c, thr_c, full, None)
+    st = ceg._lib.probe_last_stats(ps.handle)
+    assert st["n_points"] == nx * ny * nz
+    for (a, b) in [(0, 5), (60, 70), (126, 133), (nx - 3, nx)]:
+        thin = [np.zeros((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
+        ceg._lib.grid_build(ps.handle, gs, a, b, lam_v, thr_v, lam_c, thr_c, thin, None)
+        for g in range(2):
+            assert np.array_equal(thin[g][:, a:b], full[g][:, a:b]), (g, a, b)
+    ps.close()
