@@ -41,7 +41,7 @@ EXPORTS = [
     "ceg_last_error", "ceg_abi_version", "ceg_device_count", "ceg_device_info", "ceg_trim_device_cache", "ceg_kernel_launch_count",
     "ceg_measure_fp64_peak", "ceg_measure_fp64_peak_regops", "ceg_selftest_math", "ceg_host_register",
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
-    "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_free",
+    "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_upload_dev", "ceg_grid_free",
     "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_interpolate_sweep", "ceg_energy_lattice", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
     "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
 ]
@@ -231,6 +231,14 @@ def grid_upload(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, grid: np.ndar
     h = C.c_void_p()
     _check(load().ceg_grid_upload(C.c_int32(device), C.byref(cell), C.byref(gs), _p(grid, C.c_float),
                                   C.c_int32(int(is_vdw)), C.byref(h)))
+    return h
+
+
+def grid_upload_dev(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, d_grid: int, scale: float, is_vdw: bool):
+    """Device-resident [8][nx][ny][nz] f32 grid -> grid handle; values become Float32(value * scale)."""
+    h = C.c_void_p()
+    _check(load().ceg_grid_upload_dev(C.c_int32(device), C.byref(cell), C.byref(gs), C.c_void_p(int(d_grid)),
+                                      C.c_double(scale), C.c_int32(int(is_vdw)), C.byref(h)))
     return h
 
 

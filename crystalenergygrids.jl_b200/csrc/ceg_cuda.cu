@@ -808,8 +808,9 @@ extern "C" int ceg_grid_layout(ceg_grid_h h, int32_t* layout) {
     return 0;
 }
 
-extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* grid,
-                               int32_t is_vdw, ceg_grid_h* out) {
+// grid: host pointer (from_device = false) or device pointer on `device` (true), [8][nx][ny][nz]
+static int grid_upload_impl(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* grid,
+                            bool from_device, double scale, int32_t is_vdw, ceg_grid_h* out) {
     if (!unitcell || !gs || !grid || !out) return fail("ceg_grid_upload: null argument");
     for (int d = 0; d < 3; d++)
         if (gs->dims[d] < 1) return fail("ceg_grid_upload: bad dims");
@@ -834,11 +835,17 @@ extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const
     {
         DevBuf tmp, nodes;
         DevBuf& node_dst = (layout == LAYOUT_NODE) ? h->d_nodes : nodes;
-        CEG_CK(tmp.reserve(node_bytes));
         CEG_CK(node_dst.reserve(node_bytes));
-        CEG_CK(cudaMemcpyAsync(tmp.p, grid, node_bytes, cudaMemcpyHostToDevice, h->stream));
+        const float* src = grid;
+        if (!from_device) {
+            CEG_CK(tmp.reserve(node_bytes));
+            CEG_CK(cudaMemcpyAsync(tmp.p, grid, node_bytes, cudaMemcpyHostToDevice, h->stream));
+            src = tmp.as<float>();
+        } else {
+            CEG_CK(cudaDeviceSynchronize());     // the caller's producer (any stream) has finished writing the grid
+        }
         const int blocks = (int)std::min<int64_t>((npts + 255) / 256, 148 * 32);
-        relayout_nodes_kernel<<<blocks, 256, 0, h->stream>>>(tmp.as<float>(), node_dst.as<Rec8>(), npts);
+        relayout_nodes_kernel<<<blocks, 256, 0, h->stream>>>(src, node_dst.as<Rec8>(), npts, scale);
         count_launch();
         CEG_CK(cudaGetLastError());
         if (layout == LAYOUT_BLOCK) {
@@ -860,6 +867,17 @@ extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const
     h->g.layout = layout;
     *out = h.release();
     return 0;
+}
+
+extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* grid,
+                               int32_t is_vdw, ceg_grid_h* out) {
+    return grid_upload_impl(device, unitcell, gs, grid, false, 1.0, is_vdw, out);
+}
+
+extern "C" int ceg_grid_upload_dev(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* d_grid,
+                                   double scale, int32_t is_vdw, ceg_grid_h* out) {
+    if (!(scale > 0.0)) return fail("ceg_grid_upload_dev: scale must be positive");
+    return grid_upload_impl(device, unitcell, gs, d_grid, true, scale, is_vdw, out);
 }
 
 extern "C" int ceg_grid_free(ceg_grid_h h) {

@@ -49,13 +49,20 @@ struct alignas(32) Rec8 {
     float4 lo, hi;         // f, fx, fy, fz | fxy, fxz, fyz, fxyz
 };
 
-// [8][npts] -> [npts][8]
+// [8][npts] -> [npts][8].  `scale` != 1 applies parse_grid's unit conversion (grids.jl:78: Float32(value * GRID_TO_KELVIN),
+// the product formed in double) to a grid that is still in `.grid` units, as left on the device by ceg_grid_build_dev.
 __global__ void __launch_bounds__(256) relayout_nodes_kernel(const float* __restrict__ src, Rec8* __restrict__ dst,
-                                                             int64_t npts) {
+                                                             int64_t npts, double scale) {
     for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < npts; n += (int64_t)gridDim.x * blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const float x = src[c * npts + n];
+            v[c] = scale == 1.0 ? x : (float)xmul((double)x, scale);
+        }
         Rec8 r;
-        r.lo.x = src[n]; r.lo.y = src[npts + n]; r.lo.z = src[2 * npts + n]; r.lo.w = src[3 * npts + n];
-        r.hi.x = src[4 * npts + n]; r.hi.y = src[5 * npts + n]; r.hi.z = src[6 * npts + n]; r.hi.w = src[7 * npts + n];
+        r.lo = make_float4(v[0], v[1], v[2], v[3]);
+        r.hi = make_float4(v[4], v[5], v[6], v[7]);
         dst[n] = r;
     }
 }

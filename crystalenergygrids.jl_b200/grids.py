@@ -71,6 +71,16 @@ class EnergyGrid:
                                             self.grid, self.is_vdw)
         return self._handle
 
+    @staticmethod
+    def from_device(csetup, num_unitcell, ewald_precision: float, d_grid: int, device: int = 0, in_kelvin: bool = False):
+        """EnergyGrid around a grid that is already on the device in `.grid` order (ceg_grid_build_dev output, or
+        slabs gathered from other GPUs): equivalent to writing the file and parse_grid-ing it (grids.jl:61-94) without
+        the trip through host memory.  `.grid` stays empty: only device-side evaluation is available."""
+        g = EnergyGrid(csetup, tuple(num_unitcell), float(ewald_precision), True, np.zeros((0, 0, 0, 0), dtype=np.float32), device)
+        g._handle = _lib.grid_upload_dev(device, unitcell_struct(csetup.cell), _lib.make_gridspec(csetup), d_grid,
+                                         1.0 if in_kelvin else GRID_TO_KELVIN, g.is_vdw)
+        return g
+
     def close(self):
         h, self._handle = self._handle, None
         if h is not None:

@@ -168,6 +168,12 @@ int ceg_probe_last_stats(ceg_probe_h h, int64_t* n_points, int64_t* pairs_tested
  * ------------------------------------------------------------------------------------------ */
 int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs,
                     const float* grid, int32_t is_vdw, ceg_grid_h* out);
+/* The same from a grid that is already on `device` (e.g. the output of ceg_grid_build_dev, or slabs gathered from
+ * other GPUs): d_grid is [8][nx][ny][nz] f32; every value is converted as Float32(value * scale) with the product in
+ * double — scale = GRID_TO_KELVIN reproduces parse_grid (grids.jl:78) on a grid still in `.grid` units, 1 leaves a
+ * grid already in K untouched.  The source may be freed once the call returns. */
+int ceg_grid_upload_dev(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* d_grid,
+                        double scale, int32_t is_vdw, ceg_grid_h* out);
 int ceg_grid_free(ceg_grid_h h);
 /* Device record layout used by subsequent ceg_grid_upload calls: 0 = node records (1x memory),
  * 1 = (y,z) quads (4x), 2 = whole 8-corner cells (8x, one aligned 256 B block per query),

@@ -183,3 +183,31 @@ def test_interpolate_sweep_device_generated_positions(cuda_lib, orc):
         eg.close()
     z = ceg.interpolate_sweep(ceg.EnergyGrid.zero(), 10, 1, n_keep=4)
     assert z["sum"] == 0.0 and z["n_blocked"] == 0 and len(z["keep"]) == 4
+
+
+def test_grid_upload_from_device_equals_file_round_trip(cuda_lib, tmp_path):
+    """ceg_grid_upload_dev: a grid left on the device by ceg_grid_build_dev becomes an interpolation handle with
+    parse_grid's unit conversion applied on the device — same energies, bit for bit, as build -> write_grid ->
+    parse_grid -> upload."""
+    import torch
+    inp, cset, _ = wl.load_fixture("cha_na")
+    cs = wl.respace(cset, 0.5)
+    nx, ny, nz = cs.nodes
+    gs = ceg._lib.make_gridspec(cs)
+    lam_v, thr_v = ceg.vdw_scaling()
+    lam_c, thr_c = ceg.coulomb_scaling()
+    ps = ceg.ProbeSystem(None, None, inputs=inp)
+    d = [torch.empty((8, nx, ny, nz), dtype=torch.float32, device="cuda") for _ in range(2)]
+    ceg._lib.grid_build_dev(ps.handle, gs, 0, nx, lam_v, thr_v, lam_c, thr_c, [t.data_ptr() for t in d],
+                            torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = [t.cpu().numpy() for t in d]
+    ps.close()
+    pos = wl.random_positions(cs.cell.mat, 50000, 3)
+    for g, (prec, coul) in enumerate([(np.inf, False), (1e-6, True)]):
+        path = str(tmp_path / f"g{g}.grid")
+        ceg.write_grid(path, cs, inp.supercell, host[g], ewald_precision=prec if coul else None)
+        via_file = ceg.parse_grid(path, coul)
+        on_dev = ceg.EnergyGrid.from_device(cs, inp.supercell, prec, d[g].data_ptr())
+        assert np.array_equal(ceg.interpolate_grid(on_dev, pos), ceg.interpolate_grid(via_file, pos))
+        on_dev.close(); via_file.close()
