@@ -189,6 +189,17 @@ function handle(g::EnergyGrid; device=0)
     end
 end
 
+# A grid that is already on the device in `.grid` order and units (ceg_grid_build_dev output, or slabs gathered from
+# other GPUs): the handle is made on the device with parse_grid's conversion (grids.jl:78), no file, no host copy.
+function handle_from_device(cs::GridCoordinatesSetup, d_grid::Ptr{Cfloat}, is_vdw::Bool; device=0, scale=GRID_TO_KELVIN)
+    cell = CegCell(SMatrix{3,3,Float64,9}(ustrip.(u"Å", cs.cell.mat)), SMatrix{3,3,Float64,9}(ustrip.(u"Å^-1", cs.cell.invmat)))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ceg_grid_upload_dev, libceg), Cint,
+        (Int32, Ref{CegCell}, Ref{CegGridSpec}, Ptr{Cfloat}, Cdouble, Int32, Ref{Ptr{Cvoid}}),
+        device, cell, CegGridSpec(cs), d_grid, scale, is_vdw, out))
+    out[]
+end
+
 # batched method of interpolate_grid (grids.jl:212-273): points is 3 x n (Å); returns K, 1e100 = blocked
 function CrystalEnergyGrids.interpolate_grid(g::EnergyGrid, points::AbstractMatrix{Float64})
     g.ewald_precision === -Inf32 && return zeros(size(points, 2))
