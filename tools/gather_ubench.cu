@@ -6,6 +6,8 @@
 //  mode 4: the tricubic stencil on a node-major [x][y][z] grid of 32-byte records (the kernel's pattern)
 //  mode 5: the same stencil on a grid stored as 4x4x4-node bricks of 2 KB (one DRAM page per brick)
 //  mode 6: the same stencil on 2x2x2-node blocks of 256 B
+//  mode 7: 8 random sectors inside one 2 MB page chosen PER WARP (all lanes of a load share the page)
+//  mode 8: the same with a 64 KB region per warp
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -22,6 +24,12 @@ __global__ void __launch_bounds__(256) k(const float* base, uint64_t n_sectors, 
             uint64_t page = (r % (n_sectors >> 16)) << 16;     // 65536 sectors = 2 MB
 #pragma unroll
             for (int i = 0; i < 8; i++) { uint64_t s = page + (mix(r + i) & 0xffff); acc += ld32(base + s * 8); }
+        } else if (mode >= 7) {
+            const uint64_t rw = mix(seed + (uint64_t)(q >> 5) * 1315423911ull);
+            const int bits = mode == 7 ? 16 : 11;                 // sectors per region: 2 MB or 64 KB
+            const uint64_t region = (rw % (n_sectors >> bits)) << bits;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { uint64_t s = region + (mix(r + i) & ((1ull << bits) - 1)); acc += ld32(base + s * 8); }
         } else if (mode >= 4) {
             // virtual grid nx x 204 x 192 nodes filling the footprint
             const uint64_t ny = 204, nz = 192, nx = n_sectors / (ny * nz);
@@ -49,9 +57,9 @@ __global__ void __launch_bounds__(256) k(const float* base, uint64_t n_sectors, 
 int main() {
     const int64_t n = 10000000;
     float* out; cudaMalloc(&out, n * 4);
-    for (size_t mb : {256, 1024, 4096}) {
+    for (size_t mb : {256, 1024, 4080}) {
         float* base; size_t bytes = mb << 20; cudaMalloc(&base, bytes); cudaMemset(base, 0, bytes);
-        for (int mode = 0; mode < 7; mode++) {
+        for (int mode : {0, 1, 7, 8, 4}) {
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
             float best = 1e9;
             for (int rep = 0; rep < 4; rep++) {
