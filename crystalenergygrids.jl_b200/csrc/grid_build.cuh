@@ -337,6 +337,7 @@ grid_build_tiled_kernel(const BuildParams P) {
     __shared__ CellDev s_cell;
     __shared__ int s_wcount[NW];
     __shared__ double s_etab[EXP_TAB];   // 2^(j/256) for exp_neg_fast
+    __shared__ unsigned char s_all_lj[TABLE_SMEM_TYPES];   // species whose rule is pure LJ for every probe
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -344,6 +345,11 @@ grid_build_tiled_kernel(const BuildParams P) {
     for (int i = tid; i < EXP_TAB; i += NT) s_etab[i] = c_exp_tab[i];
     if (NP > 0)
         for (int i = tid; i < NP * P.n_types; i += NT) s_table[i] = P.table[i];
+    if (NP > 1 && tid < P.n_types) {
+        bool all = true;
+        for (int g = 0; g < NP; g++) all &= ((P.table[g * P.n_types + tid].flags & ~CEG_PAIR_HS) == CEG_PAIR_LJ);
+        s_all_lj[tid] = all;
+    }
 
     // tile -> node indices
     int t = blockIdx.x;
@@ -416,6 +422,18 @@ grid_build_tiled_kernel(const BuildParams P) {
                             accumulate(acc[0], v, p1, p2, p3, dx, dy, dz, dxy, dxz, dyz);
                             accumulate(acc[1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                         }
+                    } else if (NP > 1 && s_all_lj[ty_]) {
+                        // every probe sees this species through a pure Lennard-Jones rule (the CH4 / CO2-site case):
+                        // one straight-line block, so that the probes' short chains and the Ewald chains interleave
+                        constexpr int NPA = NP > 0 ? NP : 1;
+                        double v[NPA], p1[NPA], p2[NPA], p3[NPA];
+#pragma unroll
+                        for (int g = 0; g < NP; g++) lj_terms(s_table[g * P.n_types + ty_], ljw, v[g], p1[g], p2[g], p3[g]);
+                        double ev = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+                        if (COUL) ewald_pair_fast<POLY>(P.alpha, P.alpha2, P.kk, a.q, geo, s_etab, ev, e1, e2, e3);
+#pragma unroll
+                        for (int g = 0; g < NP; g++) accumulate(acc[g], v[g], p1[g], p2[g], p3[g], dx, dy, dz, dxy, dxz, dyz);
+                        if (COUL) accumulate(acc[NG - 1], ev, e1, e2, e3, dx, dy, dz, dxy, dxz, dyz);
                     } else {
 #pragma unroll
                         for (int g = 0; g < NP; g++) {
