@@ -189,3 +189,34 @@ def test_oracle_min_image_search_exits(orc):
             assert abs(float(buf @ buf) - got2) > 1.0      # the vector left behind is not the measured image
         seen[kind] += 1
     assert min(seen.values()) > 20, seen
+
+
+def test_oracle_ewald_against_direct_sums(orc):
+    """The oracle's recurrence-built structure factor and reciprocal energy against plain numpy sums of
+    exp(2 pi i k.f) over the same k-list (independent of the reference's table/recurrence scheme), and the
+    periodicity of the reciprocal energy under lattice translations of the molecule."""
+    rng = np.random.default_rng(8)
+    mat = ceg.mat_from_parameters((25.0, 26.5, 24.2), (85.0, 97.0, 104.0))
+    n = 40
+    pos = (mat @ rng.random((3, n))).T
+    q = rng.standard_normal(n)
+    q -= q.mean()
+    fw = ceg.RASPASystem(mat, pos, ["X"] * n, np.ones(n), q, False)
+    oe = orc.OracleEwald(fw, (1, 1, 1))
+    kv = oe.kspace.kvec_array().astype(np.float64)
+    frac = pos @ oe.invmat.T
+    S_direct = (q[None, :] * np.exp(2j * np.pi * (kv @ frac.T))).sum(axis=1)
+    assert np.abs(oe.S - S_direct).max() <= 1e-11 * np.abs(S_direct).max()
+    # reciprocal energy of a 3-site molecule: 2 sum kf Re(S_f conj S_a) + sum kf |S_a|^2 (+ the two constants)
+    qa = np.array([-0.35, 0.70, -0.35])
+    geom = np.array([[0, 0, 1.149], [0, 0, 0.0], [0, 0, -1.149]])
+    centers = (mat @ rng.random((3, 25))).T
+    mol = centers[:, None, :] + geom[None]
+    got = oe.reciprocal(mol, qa, 1.25, -0.5)
+    fa = mol.reshape(-1, 3) @ oe.invmat.T
+    Sa = (qa[None, None, :] * np.exp(2j * np.pi * np.einsum("kd,pad->kpa", kv, fa.reshape(25, 3, 3)))).sum(axis=2)   # (n_k, 25)
+    want = 2 * ((oe.kfactors[:, None] * (oe.S[:, None] * Sa.conj()).real).sum(axis=0) + 1.25) \
+        + ((oe.kfactors[:, None] * np.abs(Sa) ** 2).sum(axis=0) - 0.5)
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+    shifted = mol + (mat @ np.array([2.0, -1.0, 3.0]))[None, None, :]
+    assert np.abs(oe.reciprocal(shifted, qa, 1.25, -0.5) - got).max() <= 1e-9 * np.abs(got).max()
