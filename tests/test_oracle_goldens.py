@@ -220,3 +220,47 @@ def test_oracle_ewald_against_direct_sums(orc):
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
     shifted = mol + (mat @ np.array([2.0, -1.0, 3.0]))[None, None, :]
     assert np.abs(oe.reciprocal(shifted, qa, 1.25, -0.5) - got).max() <= 1e-9 * np.abs(got).max()
+
+
+def test_oracle_radial_derivatives_against_mpmath(orc):
+    """derivativesGrid (interactions.jl:432-472) and derivatives_ewald (ewald.jl:299-312) return (U - shift, DU, D^2U,
+    D^3U) with D = (1/r) d/dr.  The oracle's closed forms against 40-digit numerical differentiation of U(r) itself."""
+    import ctypes as C
+
+    import mpmath as mp
+    from ceg_b200.forcefields import pair_dtype
+    mp.mp.dps = 40
+    lib = orc.lib()
+
+    def D(f):          # (1/r) d/dr
+        return lambda r: mp.diff(f, r) / r
+
+    def check(f, got, r, what):
+        want = [f(r), D(f)(r), D(D(f))(r), D(D(D(f)))(r)]
+        if what == "LJ":
+            # REFERENCE QUIRK, reproduced on purpose: interactions.jl:441 divides the third Lennard-Jones term by r^8
+            # (`/(r4*r4)`) where the derivative is 384 eps x6 (5 - 28 x6) / r^6.  The reference's own known-answer
+            # energies (runtests.jl:38, 169) are only reproduced with its formula, so oracle and kernels keep it.
+            want[3] = want[3] / (r * r)
+        for n, (g, w) in enumerate(zip(got, want)):
+            assert abs(g - float(w)) <= 1e-11 * max(abs(float(w)), 1e-300), (what, n, g, float(w))
+
+    out = np.zeros(4)
+    for r in (1.3, 2.7, 3.9, 6.5, 11.9):
+        rr = mp.mpf(r)
+        # Lennard-Jones with a shift, Buckingham, and their sum with a hard sphere outside its radius
+        p = np.zeros(1, dtype=pair_dtype)
+        p["flags"], p["lj_eps"], p["lj_sigma"], p["lj_shift"] = 2, 107.69, 3.15, -0.0664
+        lib.ceg_o_derivatives_pair(C.c_void_p(p.ctypes.data), C.c_double(r * r), out.ctypes.data_as(C.POINTER(C.c_double)))
+        check(lambda x: 4 * mp.mpf("107.69") * ((mp.mpf("3.15") / x) ** 12 - (mp.mpf("3.15") / x) ** 6) + mp.mpf("0.0664"), out, rr, "LJ")
+        p = np.zeros(1, dtype=pair_dtype)
+        p["flags"], p["hs_r"], p["buck_A"], p["buck_B"], p["buck_C"], p["buck_shift"] = 5, 1.2, 5.581e7, 3.985, 9.167e5, 0.25
+        lib.ceg_o_derivatives_pair(C.c_void_p(p.ctypes.data), C.c_double(r * r), out.ctypes.data_as(C.POINTER(C.c_double)))
+        check(lambda x: mp.mpf("5.581e7") * mp.exp(-mp.mpf("3.985") * x) - mp.mpf("9.167e5") / x ** 6 - mp.mpf("0.25"), out, rr, "Buckingham")
+        # real-space Ewald term q erfc(alpha r) / r
+        alpha, q = 0.2650583, -1.025
+        lib.ceg_o_derivatives_ewald(C.c_double(alpha), C.c_double(q), C.c_double(r * r), out.ctypes.data_as(C.POINTER(C.c_double)))
+        check(lambda x: mp.mpf(q) * mp.erfc(mp.mpf(alpha) * x) / x, out, rr, "Ewald")
+    # inside a hard sphere the value is Inf and the other terms are kept
+    lib.ceg_o_derivatives_pair(C.c_void_p(p.ctypes.data), C.c_double(1.0), out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.isinf(out[0]) and np.isfinite(out[1:]).all()
