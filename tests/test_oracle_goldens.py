@@ -264,3 +264,35 @@ def test_oracle_radial_derivatives_against_mpmath(orc):
     # inside a hard sphere the value is Inf and the other terms are kept
     lib.ceg_o_derivatives_pair(C.c_void_p(p.ctypes.data), C.c_double(1.0), out.ctypes.data_as(C.POINTER(C.c_double)))
     assert np.isinf(out[0]) and np.isfinite(out[1:]).all()
+
+
+def test_oracle_ewald_total_is_independent_of_alpha(orc):
+    """Physics invariant tying the real-space term (ewald.jl:299-312), the k-list, the k-factors, UIon and the
+    static terms (ewald.jl:475-577) together: the total electrostatic energy of a molecule in a charged framework,
+    real-space + reciprocal, does not depend on the Ewald splitting parameter.  Two precisions (alpha = 0.265 and
+    0.33 1/Å, k-spaces of different size) must agree to the accuracy of the coarser one."""
+    fw, ff, species = wl.mfi_shaped()
+    geom = np.array([[0, 0, 1.149], [0, 0, 0.0], [0, 0, -1.149]])
+    q = np.array([-0.35, 0.70, -0.35])
+    co2 = ceg.RASPASystem(np.diag([np.inf] * 3), geom, ["O_co2", "C_co2", "O_co2"], np.ones(3), q, True)
+    centers = wl.random_positions(fw.mat, 40, 21)
+    totals = []
+    for precision in (1e-6, 1e-9):
+        oe = orc.OracleEwald(fw, None, precision)
+        inp = ceg.probe_inputs(fw, ff, (), True, oe.alpha)
+        e = []
+        for c in centers:
+            pos = geom + c
+            with np.errstate(invalid="ignore"):
+                real = ceg.COULOMBIC_CONVERSION_FACTOR * float(q @ orc.compute_derivatives(inp, pos)[-1][:, 0])
+            recip = orc.compute_ewald(oe, ([co2.with_positions(pos)],))
+            e.append(real + recip)
+        totals.append(np.array(e))
+    assert ceg.ewald_parameters(1e-9)[0] > 1.2 * ceg.ewald_parameters(1e-6)[0]
+    finite = np.isfinite(totals[0]) & np.isfinite(totals[1])          # a site closer than 1 Å to an atom gives Inf
+    assert finite.sum() >= 4
+    # the coarser setting truncates the real-space sum at erfc(alpha * 12 Å) ~ 7e-6: ~0.1 K per unit-charge pair in
+    # the cutoff shell, i.e. up to ~1 K here (charges +2.05 / -1.025); any inconsistency between the two parts
+    # (k-factors, UIon, self terms) would show up at the scale of the energies themselves, 1e3-1e4 K
+    diff = np.abs(totals[0][finite] - totals[1][finite])
+    assert np.abs(totals[1][finite]).max() > 5e3 and diff.max() <= 2.0, (totals[0], totals[1])
