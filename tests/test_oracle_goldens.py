@@ -296,3 +296,32 @@ def test_oracle_ewald_total_is_independent_of_alpha(orc):
     # (k-factors, UIon, self terms) would show up at the scale of the energies themselves, 1e3-1e4 K
     diff = np.abs(totals[0][finite] - totals[1][finite])
     assert np.abs(totals[1][finite]).max() > 5e3 and diff.max() <= 2.0, (totals[0], totals[1])
+
+
+def test_oracle_derivative_channels_are_derivatives(orc):
+    """The 8 channels of a grid point are (f, f_x, f_y, f_z, f_xy, f_xz, f_yz, f_xyz) of the summed potential
+    (probes.jl:85-91: d1 = DU v, d2 = D^2U (xy, xz, yz), d3 = D^3U xyz).  Central differences of the lower channel
+    reproduce the higher one for the Buckingham VdW grid and the Ewald real-space grid of Na+ in CHA."""
+    inp, cset, _ = wl.load_fixture("cha_na")
+    rng = np.random.default_rng(4)
+    h = 2e-4
+    checked = 0
+    for p in wl.random_positions(cset.cell.mat, 400, 17):
+        d0 = orc.compute_derivatives(inp, p[None])[:, 0]                    # (2 grids, 8)
+        if not np.isfinite(d0).all() or abs(d0[0, 0]) > 5e4:                # keep clear of the repulsive cores
+            continue
+        def at(dx):
+            return orc.compute_derivatives(inp, (p + dx)[None])[:, 0]
+        ex, ey, ez = np.eye(3) * h
+        fx = (at(ex) - at(-ex)) / (2 * h)
+        fy = (at(ey) - at(-ey)) / (2 * h)
+        fz = (at(ez) - at(-ez)) / (2 * h)
+        for g in range(2):
+            s = [np.abs(d0[g, 1:4]).max(), np.abs(d0[g, 4:7]).max(), abs(d0[g, 7])]
+            assert np.allclose([fx[g, 0], fy[g, 0], fz[g, 0]], d0[g, 1:4], rtol=0, atol=2e-6 * s[0] + 1e-9)       # f_x, f_y, f_z
+            assert np.allclose([fy[g, 1], fz[g, 1], fz[g, 2]], d0[g, 4:7], rtol=0, atol=2e-6 * s[1] + 1e-9)       # f_xy, f_xz, f_yz
+            assert abs(fz[g, 4] - d0[g, 7]) <= 2e-6 * max(s[2], s[1]) + 1e-9                                        # f_xyz
+        checked += 1
+        if checked == 12:
+            break
+    assert checked == 12
