@@ -9,6 +9,14 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
+try:    # property tests: deterministic examples, no wall-clock deadlines (CI boxes are noisy)
+    from hypothesis import HealthCheck, settings
+    settings.register_profile("ceg", deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    settings.load_profile("ceg")
+except ImportError:
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
