@@ -50,6 +50,9 @@ struct PairHot {
     }
 };
 
+#ifndef CEG_COMPACT_WARPS
+#define CEG_COMPACT_WARPS 1
+#endif
 constexpr int MAX_GRIDS = 5;       // up to 4 fused VdW probes + Coulomb per pass
 constexpr int LIST_CAP = 1024;     // shared-memory image list capacity per round
 constexpr int TABLE_SMEM_TYPES = 24;
@@ -356,7 +359,19 @@ grid_build_tiled_kernel(const BuildParams P) {
     const int tz = t % P.tiles_z; t /= P.tiles_z;
     const int ty = t % P.tiles_y; t /= P.tiles_y;
     const int tx = t;
-    const int lz = tid % TZ, ly = (tid / TZ) % TY, lx = tid / (TZ * TY);
+    // thread -> node of the tile.  A warp evaluates a pair as soon as one of its lanes is inside the cutoff, so the more
+    // compact a warp's 32 nodes, the fewer lanes idle at the cutoff sphere: 2 x 4 x 4 nodes per warp where the tile allows
+    // it (CEG_COMPACT_WARPS), 1 x 4 x 8 (z fastest) otherwise.
+    int lz = tid % TZ, ly = (tid / TZ) % TY, lx = tid / (TZ * TY);
+#if CEG_COMPACT_WARPS
+    if (TX >= 2 && (TY & 3) == 0 && (TZ & 3) == 0) {
+        const int wz_n = TZ >> 2, wy_n = TY >> 2;
+        const int wz = warp % wz_n, wy = (warp / wz_n) % wy_n, wx = warp / (wz_n * wy_n);
+        lz = (wz << 2) + (lane & 3);
+        ly = (wy << 2) + ((lane >> 2) & 3);
+        lx = (wx << 1) + (lane >> 4);
+    }
+#endif
     const int i = P.a0 + tx * TX + lx, j = ty * TY + ly, k = tz * TZ + lz;
     const bool valid = (i < P.a1) && (j < P.gs.n[1]) && (k < P.gs.n[2]);
     // abc_to_xyz (coordinates.jl:72-76): multiply, divide, add — bit-identical to the oracle
