@@ -1422,6 +1422,7 @@ extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_
         CK2(cudaMemcpyAsync(out_coulomb, d_c.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, s));
         CK2(cudaStreamSynchronize(s));
     } while (0);
+    if (rc) cudaStreamSynchronize(s);   // nothing may still use the scratch buffers when they go back to the pool
     cudaStreamDestroy(s);
     return rc;
 }
@@ -1482,6 +1483,7 @@ extern "C" int ceg_energy_lattice(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid
         if (!rc) CK2(cudaStreamSynchronize(s));
 #undef CK2
     } while (0);
+    if (rc) cudaStreamSynchronize(s);   // nothing may still use the scratch buffers when they go back to the pool
     cudaStreamDestroy(s);
     return rc;
 }
