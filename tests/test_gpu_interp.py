@@ -211,3 +211,20 @@ def test_grid_upload_from_device_equals_file_round_trip(cuda_lib, tmp_path):
         on_dev = ceg.EnergyGrid.from_device(cs, inp.supercell, prec, d[g].data_ptr())
         assert np.array_equal(ceg.interpolate_grid(on_dev, pos), ceg.interpolate_grid(via_file, pos))
         on_dev.close(); via_file.close()
+
+
+def test_non_finite_positions_are_memory_safe(cuda_lib, orc, layout):
+    """NaN, infinite or astronomically large query positions must not read out of bounds or poison later calls
+    (the reference would throw an InexactError / BoundsError there; the device clamps the cell index)."""
+    cset = ceg.GridCoordinatesSetup.from_cell(ceg.mat_from_parameters((7.0, 6.0, 5.0), (80.0, 95.0, 105.0)), 0.5)
+    grid = _random_grid(cset, 3)
+    eg = ceg.EnergyGrid(cset, (1, 1, 1), 1e-6, True, grid)
+    bad = np.array([[np.nan, 0, 0], [np.inf, 1, 2], [-np.inf, np.inf, np.nan], [1e300, -1e300, 1e308], [1e19, 3.0, -2e18]])
+    good = wl.random_positions(cset.cell.mat, 1000, 2)
+    out = ceg.interpolate_grid(eg, np.concatenate([good[:500], bad, good[500:]]))
+    assert out.shape == (1005,)
+    want = orc.interpolate(cset, grid, False, good)
+    got = np.concatenate([out[:500], out[505:]])
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-9)
+    assert np.allclose(ceg.interpolate_grid(eg, good), want, rtol=1e-9, atol=1e-9)
+    eg.close()
