@@ -96,3 +96,32 @@ def test_grid_locations(raspa_dir):
     base = os.path.join(str(raspa_dir), "grids", "ToyFF", "Toy", "0.400000")
     assert coul == os.path.join(base, "2x2x3", "Toy_Electrostatics_Ewald.grid")
     assert vdw == [os.path.join(base, "Toy_O_co2_truncated.grid"), os.path.join(base, "Toy_C_co2_truncated.grid")]
+
+
+def test_guest_pair_energy_table_and_oracle_rule(raspa_dir, orc):
+    """energy.py: the (species x species) table of rule(d^2) (interactions.jl:367-409) built from the parsed force
+    field, and the oracle's pair energy against the host-side InteractionRule.__call__ (written from the same
+    reference lines, independently of the C code)."""
+    import ctypes as C
+    ff = ceg.parse_forcefield_RASPA("ToyFF")
+    names = ["O_co2", "C_co2", "Na", "Oz"]
+    tab = ceg.pair_energy_table(ff, names)
+    assert tab.shape == (4, 4) and np.array_equal(tab["flags"], tab["flags"].T)
+    na_o = tab[2, 3]
+    assert na_o["flags"] == 1 | 4 | 8 and na_o["hs_r"] == 1.5 and na_o["buck_B"] == 3.985       # HS + Buckingham + Ewald
+    assert na_o["ewald_qq"] == pytest.approx(ceg.COULOMBIC_CONVERSION_FACTOR * 1.0 * -1.025)
+    assert tab[0, 1]["flags"] == 2 | 8 and tab[0, 1]["ewald_qq"] == pytest.approx(ceg.COULOMBIC_CONVERSION_FACTOR * -0.3256 * 0.6512)
+    # oracle rule(d^2) == host rule(r) on a few distances (outside the hard sphere)
+    sd = ff.sdict
+    env = ceg.GuestEnvironment(np.diag([60.0, 60.0, 60.0]), 12.0, tab, np.zeros((1, 3)), np.array([3], dtype=np.int32),
+                               np.array([0], dtype=np.int32))
+    for (a, b) in ((2, 3), (0, 3), (1, 3)):
+        env.species[:] = b
+        rule = ff.interactions[sd[names[a]]][sd[names[b]]]
+        for r in (1.7, 2.9, 5.5, 11.0):
+            got = orc.guest_energy(env, [a], np.array([[[r, 0.0, 0.0]]]), 1)[0]
+            assert got == pytest.approx(rule(r), rel=1e-12, abs=1e-12), (names[a], names[b], r)
+    # inside the hard sphere: +Inf; beyond the cutoff: 0
+    env.species[:] = 3
+    assert np.isinf(orc.guest_energy(env, [2], np.array([[[1.2, 0.0, 0.0]]]), 1)[0])
+    assert orc.guest_energy(env, [2], np.array([[[12.5, 0.0, 0.0]]]), 1)[0] == 0.0
