@@ -1093,7 +1093,10 @@ extern "C" int ceg_ewald_free(ceg_ewald_h h) {
 static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const double* d_xyz, const double* d_q,
                              double enc, double stat, double* d_out, const uint8_t* d_skip, int accumulate,
                              cudaStream_t s, const double2* d_rest = nullptr) {
-    if (h->rows_ok && n_atoms <= ROWS_MAX_ATOMS) {
+    // Small batches (single Monte-Carlo steps) do not fill the GPU with one thread per placement, and that thread walks
+    // the whole k-list alone; the warp-per-placement kernel spreads the k-list over 32 lanes and returns sooner.
+    constexpr int64_t ROWS_MIN_PLACEMENTS = 16384;
+    if (h->rows_ok && n_atoms <= ROWS_MAX_ATOMS && n_pos >= ROWS_MIN_PLACEMENTS) {
         RowsParams R;
         memcpy(R.invmat, h->invmat, sizeof R.invmat);
         R.ky = h->kmax[1]; R.kz = h->kmax[2];
@@ -1332,6 +1335,42 @@ extern "C" int ceg_block_free(ceg_block_h h) {
     return 0;
 }
 
+// Per-thread pinned staging block and stream for small ceg_energy_points calls (one device per thread at a time).
+struct SmallStage {
+    static constexpr size_t BYTES = 1u << 20;
+    void* host = nullptr;
+    cudaStream_t stream = nullptr;
+    int device = -1;
+    bool ready(int dev) {
+        if (dev < 0) return false;
+        if (device != dev) {                       // (re)create for this device
+            if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+            if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { stream = nullptr; cudaGetLastError(); return false; }
+            device = dev;
+        }
+        if (!host && cudaHostAlloc(&host, BYTES, cudaHostAllocPortable) != cudaSuccess) { host = nullptr; cudaGetLastError(); return false; }
+        return true;
+    }
+    ~SmallStage() {                                 // thread exit; the context may already be gone: ignore errors
+        if (host) cudaFreeHost(host);
+        if (stream) cudaStreamDestroy(stream);
+        cudaGetLastError();
+    }
+};
+static SmallStage& small_stage() {
+    static thread_local SmallStage st;
+    return st;
+}
+static int P_device_of(const ceg_grid_h* vdw, int n_vdw, ceg_grid_h coulomb, ceg_ewald_h ewald, ceg_block_h block) {
+    int device = -1;
+    for (int g = 0; g < n_vdw; g++)
+        if (vdw && vdw[g]) device = vdw[g]->device;
+    if (coulomb) device = coulomb->device;
+    if (ewald) device = ewald->device;
+    if (block) device = block->device;
+    return device;
+}
+
 // Shared front end of ceg_energy_points / ceg_energy_lattice: validates the handles and fills the grid part of
 // the kernel parameters.  Returns -1 when nothing is resident (all grids are zero grids), 0 on success, 1 on error.
 static int energy_points_setup(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h coulomb, ceg_ewald_h ewald,
@@ -1399,31 +1438,67 @@ extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_
         for (int64_t i = 0; i < n_pos; i++) { out_vdw[i] = 0.0; out_coulomb[i] = 0.0; }
         return 0;
     }
-    cudaStream_t s;
-    CEG_CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    DevBuf d_idx, d_q, d_xyz, d_v, d_c, d_blk;
+    // Small batches (single Monte-Carlo steps): latency is what matters.  Inputs are packed into one pinned, thread-local
+    // staging block and uploaded with ONE copy, the two outputs come back with ONE copy, and the stream is kept per
+    // thread — 5 pageable copies and a stream create/destroy per call cost more than the kernels.
+    const size_t n_idx_d = ((size_t)n_atoms + 1) / 2;                       // int32 indices, in units of doubles
+    const size_t n_in_d = n_idx_d + (size_t)n_atoms + (size_t)3 * n_atoms * n_pos;
+    const size_t n_out_d = (size_t)2 * n_pos;
+    const bool small = (n_in_d + n_out_d) * sizeof(double) <= SmallStage::BYTES;
+    SmallStage& stage = small_stage();
+    cudaStream_t s = nullptr;
+    bool own_stream = false;
+    if (small && stage.ready(P_device_of(vdw, n_vdw, coulomb, ewald, block))) s = stage.stream;
+    if (!s) {
+        CEG_CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        own_stream = true;
+    }
+    DevBuf d_in, d_xyz, d_out, d_blk, d_idx, d_q;
     int rc = 0;
     do {
 #define CK2(call) { cudaError_t _e = (call); if (_e != cudaSuccess) { rc = fail_cuda(_e, #call, __FILE__, __LINE__); break; } }
-        CK2(d_idx.reserve(sizeof(int) * n_atoms));
-        CK2(d_q.reserve(sizeof(double) * n_atoms));
-        CK2(d_xyz.reserve(sizeof(double) * 3 * n_atoms * n_pos));
-        CK2(d_v.reserve(sizeof(double) * n_pos));
-        CK2(d_c.reserve(sizeof(double) * n_pos));
+        CK2(d_out.reserve(sizeof(double) * n_out_d));
         CK2(d_blk.reserve(n_pos));
-        CK2(cudaMemcpyAsync(d_idx.p, atomsidx, sizeof(int) * n_atoms, cudaMemcpyHostToDevice, s));
-        CK2(cudaMemcpyAsync(d_q.p, charges, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, s));
-        CK2(cudaMemcpyAsync(d_xyz.p, xyz, sizeof(double) * 3 * n_atoms * n_pos, cudaMemcpyHostToDevice, s));
-        P.atomsidx = d_idx.as<int>();
-        P.charges = d_q.as<double>();
-        if (energy_points_enqueue(P, ewald, coulomb != nullptr, n_pos, n_atoms, d_xyz.as<double>(), energy_net_charges,
-                                  static_contribution, d_v.as<double>(), d_c.as<double>(), d_blk.as<uint8_t>(), s)) { rc = 1; break; }
-        CK2(cudaMemcpyAsync(out_vdw, d_v.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, s));
-        CK2(cudaMemcpyAsync(out_coulomb, d_c.p, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, s));
-        CK2(cudaStreamSynchronize(s));
+        double* d_v = d_out.as<double>();
+        double* d_c = d_v + n_pos;
+        const double* d_pos = nullptr;
+        if (!own_stream) {
+            double* hin = static_cast<double*>(stage.host);
+            memcpy(hin, atomsidx, sizeof(int32_t) * n_atoms);
+            memcpy(hin + n_idx_d, charges, sizeof(double) * n_atoms);
+            memcpy(hin + n_idx_d + n_atoms, xyz, sizeof(double) * 3 * n_atoms * n_pos);
+            CK2(d_in.reserve(sizeof(double) * n_in_d));
+            CK2(cudaMemcpyAsync(d_in.p, hin, sizeof(double) * n_in_d, cudaMemcpyHostToDevice, s));
+            P.atomsidx = reinterpret_cast<const int*>(d_in.as<double>());
+            P.charges = d_in.as<double>() + n_idx_d;
+            d_pos = d_in.as<double>() + n_idx_d + n_atoms;
+        } else {
+            CK2(d_idx.reserve(sizeof(int) * n_atoms));
+            CK2(d_q.reserve(sizeof(double) * n_atoms));
+            CK2(d_xyz.reserve(sizeof(double) * 3 * n_atoms * n_pos));
+            CK2(cudaMemcpyAsync(d_idx.p, atomsidx, sizeof(int) * n_atoms, cudaMemcpyHostToDevice, s));
+            CK2(cudaMemcpyAsync(d_q.p, charges, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, s));
+            CK2(cudaMemcpyAsync(d_xyz.p, xyz, sizeof(double) * 3 * n_atoms * n_pos, cudaMemcpyHostToDevice, s));
+            P.atomsidx = d_idx.as<int>();
+            P.charges = d_q.as<double>();
+            d_pos = d_xyz.as<double>();
+        }
+        if (energy_points_enqueue(P, ewald, coulomb != nullptr, n_pos, n_atoms, d_pos, energy_net_charges,
+                                  static_contribution, d_v, d_c, d_blk.as<uint8_t>(), s)) { rc = 1; break; }
+        if (!own_stream) {
+            double* hout = static_cast<double*>(stage.host) + n_in_d;
+            CK2(cudaMemcpyAsync(hout, d_v, sizeof(double) * n_out_d, cudaMemcpyDeviceToHost, s));
+            CK2(cudaStreamSynchronize(s));
+            memcpy(out_vdw, hout, sizeof(double) * n_pos);
+            memcpy(out_coulomb, hout + n_pos, sizeof(double) * n_pos);
+        } else {
+            CK2(cudaMemcpyAsync(out_vdw, d_v, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, s));
+            CK2(cudaMemcpyAsync(out_coulomb, d_c, sizeof(double) * n_pos, cudaMemcpyDeviceToHost, s));
+            CK2(cudaStreamSynchronize(s));
+        }
     } while (0);
     if (rc) cudaStreamSynchronize(s);   // nothing may still use the scratch buffers when they go back to the pool
-    cudaStreamDestroy(s);
+    if (own_stream) cudaStreamDestroy(s);
     return rc;
 }
 
