@@ -37,12 +37,15 @@ def test_structure_factor_and_reciprocal_vs_oracle(cuda_lib, orc):
              (np.array([0.9094]), np.zeros((1, 3)))]
     for na in (2, 4, 5):
         cases.append((rng.standard_normal(na), rng.standard_normal((na, 3)) * 1.5))
+    # 500 placements: latency path (warp per placement for every size); 20000: throughput path (>= 16384 placements)
+    many = wl.random_positions(fw.mat, 20000, 32) * 3.0 - 20.0
     for q, offs in cases:
-        pos = centers[:, None, :] + offs[None, :, :]
-        enc, stat = 12.5, -3.25
-        got = ceg._lib.ewald_reciprocal(ef.handle, pos, q, enc, stat)
-        want = oe.reciprocal(pos, q, enc, stat)
-        assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max(), np.abs(got - want).max()
+        for ctr in (centers, many):
+            pos = ctr[:, None, :] + offs[None, :, :]
+            enc, stat = 12.5, -3.25
+            got = ceg._lib.ewald_reciprocal(ef.handle, pos, q, enc, stat)
+            want = oe.reciprocal(pos, q, enc, stat)
+            assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max(), (len(q), len(ctr), np.abs(got - want).max())
 
 
 def test_two_co2_golden(cuda_lib):
@@ -195,7 +198,7 @@ def test_single_contribution_ewald_batched(cuda_lib, orc):
     co2 = ceg.RASPASystem(np.diag([np.inf] * 3), geom, ["O_co2", "C_co2", "O_co2"], np.ones(3), q, True)
     A = co2.with_positions(geom + [1.3, 2.9, 0.0])
     B_old = geom + [4.7, 10.1, 0.0]
-    centers = wl.random_positions(fw.mat, 300, 5)
+    centers = wl.random_positions(fw.mat, 18000, 5)      # >= 16384: the thread-per-placement kernel with `rest`
     trials = centers[:, None, :] + geom[None, :, :]
     rest = ef.StoreRigidChargeFramework + ceg.adsorbate_sums(ef, q, A.position)      # framework + molecule A
     got = ceg.single_contribution_ewald(ef, rest, q, trials)
@@ -203,6 +206,8 @@ def test_single_contribution_ewald_batched(cuda_lib, orc):
     oe.S = rest
     want = oe.reciprocal(trials, q, 0.0, 0.0)
     assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    small = ceg.single_contribution_ewald(ef, rest, q, trials[:300])     # latency path: warp per placement
+    assert np.abs(small - want[:300]).max() <= 1e-9 * np.abs(want).max()
     # identity: E(A, B_new) - E(A, B_old) == single(B_new) - single(B_old)
     old = ceg.single_contribution_ewald(ef, rest, q, B_old[None])[0]
     for i in (0, 17, 123):
