@@ -43,7 +43,7 @@ EXPORTS = [
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_upload_dev", "ceg_grid_free",
     "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_interpolate_sweep", "ceg_energy_lattice", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
-    "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
+    "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_guest_env_create", "ceg_guest_env_free", "ceg_guest_env_update", "ceg_guest_env_energy", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
 ]
 
 _lib = None
@@ -345,6 +345,39 @@ def ewald_reciprocal_dev(h, n_pos: int, q, d_xyz: int, energy_net_charges, stati
 
 
 # ---- guest-guest pair energies -----------------------------------------------------------------------
+def guest_env_create(device: int, cell: ceg_cell_t, cutoff2: float, table: np.ndarray, env_xyz, env_species, env_mol):
+    table = np.ascontiguousarray(table)
+    assert table.ndim == 2 and table.shape[0] == table.shape[1] and table.dtype.itemsize == 96
+    env_xyz = _f64(env_xyz, (-1, 3))
+    env_species = np.ascontiguousarray(env_species, dtype=np.int32)
+    env_mol = np.ascontiguousarray(env_mol, dtype=np.int32)
+    h = C.c_void_p()
+    _check(load().ceg_guest_env_create(C.c_int32(device), C.byref(cell), C.c_double(cutoff2), C.c_int32(table.shape[0]),
+                                       C.c_void_p(table.ctypes.data), C.c_int64(env_xyz.shape[0]), _p(env_xyz, C.c_double),
+                                       _p(env_species, C.c_int32), _p(env_mol, C.c_int32), C.byref(h)))
+    return h
+
+
+def guest_env_free(h):
+    _check(load().ceg_guest_env_free(h))
+
+
+def guest_env_update(h, first: int, xyz):
+    xyz = _f64(xyz, (-1, 3))
+    _check(load().ceg_guest_env_update(h, C.c_int64(first), C.c_int64(xyz.shape[0]), _p(xyz, C.c_double)))
+
+
+def guest_env_energy(h, mol_species, skip_mol: int, trial_xyz) -> np.ndarray:
+    mol_species = np.ascontiguousarray(mol_species, dtype=np.int32)
+    na = mol_species.shape[0]
+    trial_xyz = _f64(trial_xyz, (-1, na, 3))
+    out = np.empty(trial_xyz.shape[0], dtype=np.float64)
+    _check(load().ceg_guest_env_energy(h, C.c_int64(trial_xyz.shape[0]), C.c_int32(na), _p(mol_species, C.c_int32),
+                                       C.c_int32(skip_mol), _p(trial_xyz, C.c_double), _p(out, C.c_double)))
+    return out
+
+
+
 def guest_energy(device: int, cell: ceg_cell_t, cutoff2: float, table: np.ndarray, env_xyz, env_species, env_mol,
                  mol_species, skip_mol: int, trial_xyz) -> np.ndarray:
     table = np.ascontiguousarray(table)

@@ -1214,21 +1214,32 @@ extern "C" int ceg_ewald_single_contribution(ceg_ewald_h h, const double* rest_r
 // ================================================================================================
 // guest-guest pair energies (energy.jl:339-427)
 // ================================================================================================
-extern "C" int ceg_guest_energy(int32_t device, const ceg_cell_t* cell, double cutoff2, int32_t n_species,
-                                const ceg_pair_energy_t* table, int64_t n_env, const double* env_xyz,
-                                const int32_t* env_species, const int32_t* env_mol, int64_t n_trials, int32_t n_atoms,
-                                const int32_t* mol_species, int32_t skip_mol, const double* trial_xyz, double* out) {
-    if (!cell || n_species <= 0 || !table || n_env < 0 || n_trials < 0 || n_atoms <= 0 || !mol_species ||
-        (n_env > 0 && (!env_xyz || !env_species || !env_mol)) || (n_trials > 0 && (!trial_xyz || !out)))
-        return fail("ceg_guest_energy: bad argument");
-    if (n_env > (1ll << 30)) return fail("ceg_guest_energy: too many environment atoms");
+// Device-resident guest environment (SimulationStep.positions / atoms of the other guests, energy.jl:43-60): created
+// once, evaluated for many batches of trial placements, updated in place after accepted moves.
+struct ceg_guest_s {
+    int device = 0;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    CellDev cell;
+    double cutoff2 = 0;
+    int n_species = 0;
+    int64_t n_env = 0;
+    DevBuf d_tab, d_exyz, d_esp, d_emol, d_msp, d_txyz, d_out;
+    ~ceg_guest_s() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+extern "C" int ceg_guest_env_create(int32_t device, const ceg_cell_t* cell, double cutoff2, int32_t n_species,
+                                    const ceg_pair_energy_t* table, int64_t n_env, const double* env_xyz,
+                                    const int32_t* env_species, const int32_t* env_mol, ceg_guest_h* out) {
+    if (!cell || n_species <= 0 || !table || n_env < 0 || !out || (n_env > 0 && (!env_xyz || !env_species || !env_mol)))
+        return fail("ceg_guest_env_create: bad argument");
+    if (n_env > (1ll << 30)) return fail("ceg_guest_env_create: too many environment atoms");
     for (int64_t i = 0; i < n_env; i++)
-        if (env_species[i] < 0 || env_species[i] >= n_species) return fail("ceg_guest_energy: species out of range");
-    for (int a = 0; a < n_atoms; a++)
-        if (mol_species[a] < 0 || mol_species[a] >= n_species) return fail("ceg_guest_energy: species out of range");
+        if (env_species[i] < 0 || env_species[i] >= n_species) return fail("ceg_guest_env_create: species out of range");
     for (int i = 0; i < n_species * n_species; i++)
         if (table[i].flags < 0) return fail("Undefined interaction");
-    if (n_trials == 0) return 0;
     if (use_device(device)) return 1;
     std::vector<PairEnergyDev> tab((size_t)n_species * n_species);
     for (size_t i = 0; i < tab.size(); i++) {
@@ -1240,32 +1251,86 @@ extern "C" int ceg_guest_energy(int32_t device, const ceg_cell_t* cell, double c
         d.bA = s.buck_A; d.bB = s.buck_B; d.bC = s.buck_C; d.b_shift = s.buck_shift;
         d.ew_alpha = s.ewald_alpha; d.ew_qq = s.ewald_qq; d.coul_qq = s.coulomb_qq;
     }
-    DevBuf d_tab, d_exyz, d_esp, d_emol, d_msp, d_txyz, d_out;
-    CEG_CK(d_tab.reserve(sizeof(PairEnergyDev) * tab.size()));
-    CEG_CK(d_exyz.reserve(sizeof(double) * 3 * std::max<int64_t>(1, n_env)));
-    CEG_CK(d_esp.reserve(sizeof(int) * std::max<int64_t>(1, n_env)));
-    CEG_CK(d_emol.reserve(sizeof(int) * std::max<int64_t>(1, n_env)));
-    CEG_CK(d_msp.reserve(sizeof(int) * n_atoms));
-    CEG_CK(d_txyz.reserve(sizeof(double) * 3 * n_atoms * n_trials));
-    CEG_CK(d_out.reserve(sizeof(double) * n_trials));
-    CEG_CK(cudaMemcpy(d_tab.p, tab.data(), sizeof(PairEnergyDev) * tab.size(), cudaMemcpyHostToDevice));
+    std::unique_ptr<ceg_guest_s> h(new ceg_guest_s);
+    h->device = device;
+    h->cell = to_dev(*cell);
+    h->cutoff2 = cutoff2;
+    h->n_species = n_species;
+    h->n_env = n_env;
+    CEG_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CEG_CK(h->d_tab.reserve(sizeof(PairEnergyDev) * tab.size()));
+    CEG_CK(h->d_exyz.reserve(sizeof(double) * 3 * std::max<int64_t>(1, n_env)));
+    CEG_CK(h->d_esp.reserve(sizeof(int) * std::max<int64_t>(1, n_env)));
+    CEG_CK(h->d_emol.reserve(sizeof(int) * std::max<int64_t>(1, n_env)));
+    CEG_CK(cudaMemcpyAsync(h->d_tab.p, tab.data(), sizeof(PairEnergyDev) * tab.size(), cudaMemcpyHostToDevice, h->stream));
     if (n_env > 0) {
-        CEG_CK(cudaMemcpy(d_exyz.p, env_xyz, sizeof(double) * 3 * n_env, cudaMemcpyHostToDevice));
-        CEG_CK(cudaMemcpy(d_esp.p, env_species, sizeof(int) * n_env, cudaMemcpyHostToDevice));
-        CEG_CK(cudaMemcpy(d_emol.p, env_mol, sizeof(int) * n_env, cudaMemcpyHostToDevice));
+        CEG_CK(cudaMemcpyAsync(h->d_exyz.p, env_xyz, sizeof(double) * 3 * n_env, cudaMemcpyHostToDevice, h->stream));
+        CEG_CK(cudaMemcpyAsync(h->d_esp.p, env_species, sizeof(int) * n_env, cudaMemcpyHostToDevice, h->stream));
+        CEG_CK(cudaMemcpyAsync(h->d_emol.p, env_mol, sizeof(int) * n_env, cudaMemcpyHostToDevice, h->stream));
     }
-    CEG_CK(cudaMemcpy(d_msp.p, mol_species, sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
-    CEG_CK(cudaMemcpy(d_txyz.p, trial_xyz, sizeof(double) * 3 * n_atoms * n_trials, cudaMemcpyHostToDevice));
+    CEG_CK(cudaStreamSynchronize(h->stream));
+    *out = h.release();
+    return 0;
+}
+
+extern "C" int ceg_guest_env_free(ceg_guest_h h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    delete h;
+    return 0;
+}
+
+// positions of environment atoms [first, first + n) after an accepted move
+extern "C" int ceg_guest_env_update(ceg_guest_h h, int64_t first, int64_t n, const double* xyz) {
+    if (!h || first < 0 || n < 0 || first + n > h->n_env || (n > 0 && !xyz)) return fail("ceg_guest_env_update: bad argument");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    CEG_CK(cudaMemcpyAsync(h->d_exyz.as<double>() + 3 * first, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    CEG_CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int ceg_guest_env_energy(ceg_guest_h h, int64_t n_trials, int32_t n_atoms, const int32_t* mol_species,
+                                    int32_t skip_mol, const double* trial_xyz, double* out) {
+    if (!h || n_trials < 0 || n_atoms <= 0 || !mol_species || (n_trials > 0 && (!trial_xyz || !out)))
+        return fail("ceg_guest_env_energy: bad argument");
+    for (int a = 0; a < n_atoms; a++)
+        if (mol_species[a] < 0 || mol_species[a] >= h->n_species) return fail("ceg_guest_env_energy: species out of range");
+    if (n_trials == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    cudaStream_t s = h->stream;
+    CEG_CK(h->d_msp.reserve(sizeof(int) * n_atoms));
+    CEG_CK(h->d_txyz.reserve(sizeof(double) * 3 * n_atoms * n_trials));
+    CEG_CK(h->d_out.reserve(sizeof(double) * n_trials));
+    CEG_CK(cudaMemcpyAsync(h->d_msp.p, mol_species, sizeof(int) * n_atoms, cudaMemcpyHostToDevice, s));
+    CEG_CK(cudaMemcpyAsync(h->d_txyz.p, trial_xyz, sizeof(double) * 3 * n_atoms * n_trials, cudaMemcpyHostToDevice, s));
     GuestParams P;
-    P.cell = to_dev(*cell); P.cutoff2 = cutoff2; P.n_species = n_species; P.table = d_tab.as<PairEnergyDev>();
-    P.n_env = (int)n_env; P.env_xyz = d_exyz.as<double>(); P.env_species = d_esp.as<int>(); P.env_mol = d_emol.as<int>();
-    P.n_trials = n_trials; P.n_atoms = n_atoms; P.mol_species = d_msp.as<int>(); P.skip_mol = skip_mol;
-    P.trial_xyz = d_txyz.as<double>(); P.out = d_out.as<double>();
-    guest_energy_kernel<<<(unsigned)((n_trials + 127) / 128), 128>>>(P);
+    P.cell = h->cell; P.cutoff2 = h->cutoff2; P.n_species = h->n_species; P.table = h->d_tab.as<PairEnergyDev>();
+    P.n_env = (int)h->n_env; P.env_xyz = h->d_exyz.as<double>(); P.env_species = h->d_esp.as<int>(); P.env_mol = h->d_emol.as<int>();
+    P.n_trials = n_trials; P.n_atoms = n_atoms; P.mol_species = h->d_msp.as<int>(); P.skip_mol = skip_mol;
+    P.trial_xyz = h->d_txyz.as<double>(); P.out = h->d_out.as<double>();
+    guest_energy_kernel<<<(unsigned)((n_trials + 127) / 128), 128, 0, s>>>(P);
     count_launch();
     CEG_CK(cudaGetLastError());
-    CEG_CK(cudaMemcpy(out, d_out.p, sizeof(double) * n_trials, cudaMemcpyDeviceToHost));
+    CEG_CK(cudaMemcpyAsync(out, h->d_out.p, sizeof(double) * n_trials, cudaMemcpyDeviceToHost, s));
+    CEG_CK(cudaStreamSynchronize(s));
     return 0;
+}
+
+// Stateless form: environment uploaded, evaluated and released in one call.
+extern "C" int ceg_guest_energy(int32_t device, const ceg_cell_t* cell, double cutoff2, int32_t n_species,
+                                const ceg_pair_energy_t* table, int64_t n_env, const double* env_xyz,
+                                const int32_t* env_species, const int32_t* env_mol, int64_t n_trials, int32_t n_atoms,
+                                const int32_t* mol_species, int32_t skip_mol, const double* trial_xyz, double* out) {
+    if (n_trials < 0 || n_atoms <= 0 || !mol_species || (n_trials > 0 && (!trial_xyz || !out)))
+        return fail("ceg_guest_energy: bad argument");
+    ceg_guest_h h = nullptr;
+    if (ceg_guest_env_create(device, cell, cutoff2, n_species, table, n_env, env_xyz, env_species, env_mol, &h)) return 1;
+    const int rc = ceg_guest_env_energy(h, n_trials, n_atoms, mol_species, skip_mol, trial_xyz, out);
+    ceg_guest_env_free(h);
+    return rc;
 }
 
 // ================================================================================================

@@ -10,7 +10,7 @@ energy_intra of flexible molecules requires an infinite cutoff, energy.jl:309-32
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 
 import numpy as np
 
@@ -90,12 +90,41 @@ class GuestEnvironment:
         ortho, safemin = prepare_periodic_distance_computations(m)
         return _lib.make_cell(flat(m), flat(inv3(m)), ortho, safemin * safemin)
 
+    # device-resident copy (ceg_guest_env_create), made on first use; never copied by dataclasses.replace
+    _handle: object = field(default=None, init=False, repr=False, compare=False)
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            self._handle = _lib.guest_env_create(self.device, self.cell_struct(), float(self.cutoff) ** 2, self.table,
+                                                 self.positions, self.species, self.molecule)
+        return self._handle
+
+    def move(self, first: int, positions) -> None:
+        """Accepted move: atoms [first, first + len(positions)) take new positions, on the host copy and on the device."""
+        pos = np.asarray(positions, dtype=np.float64).reshape(-1, 3)
+        self.positions = np.array(self.positions, dtype=np.float64)
+        self.positions[first:first + len(pos)] = pos
+        if self._handle is not None:
+            _lib.guest_env_update(self._handle, first, pos)
+
+    def close(self):
+        h, self._handle = self._handle, None
+        if h is not None:
+            _lib.guest_env_free(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
 
 def single_contribution_vdw(env: GuestEnvironment, mol_species, trial_positions, skip_molecule: int = -1) -> np.ndarray:
     """energy.jl:407-427, batched: energy of a rigid molecule (species indices `mol_species`) at each trial
-    placement (n_trials, n_atoms, 3) with every environment atom not belonging to `skip_molecule`."""
-    return _lib.guest_energy(env.device, env.cell_struct(), float(env.cutoff) ** 2, env.table, env.positions, env.species,
-                             env.molecule, mol_species, skip_molecule, trial_positions)
+    placement (n_trials, n_atoms, 3) with every environment atom not belonging to `skip_molecule`.  The environment
+    stays on the device between calls (GuestEnvironment.handle / .move)."""
+    return _lib.guest_env_energy(env.handle, mol_species, skip_molecule, trial_positions)
 
 
 def compute_vdw(env: GuestEnvironment) -> float:

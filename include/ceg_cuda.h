@@ -87,6 +87,7 @@ typedef struct ceg_probe_s* ceg_probe_h;   /* ProbeSystem(s)            probes.j
 typedef struct ceg_grid_s*  ceg_grid_h;    /* device-resident EnergyGrid grids.jl:10-16   */
 typedef struct ceg_ewald_s* ceg_ewald_h;   /* EwaldFramework            ewald.jl:40-50    */
 typedef struct ceg_block_s* ceg_block_h;   /* BlockFile                 coordinates.jl:83 */
+typedef struct ceg_guest_s* ceg_guest_h;   /* guests of a SimulationStep energy.jl:43-60  */
 
 const char* ceg_last_error(void);
 int ceg_abi_version(void);
@@ -231,6 +232,16 @@ int ceg_ewald_reciprocal_dev(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, cons
  * grids) and ceg_ewald_single_contribution (reciprocal part) this evaluates movement_energy
  * (montecarlo.jl:563-606) for a batch of trial moves.
  * ------------------------------------------------------------------------------------------ */
+/* The same with the environment resident on the device: create once per simulation, evaluate batches of trial
+ * placements (ceg_guest_env_energy = the arguments of ceg_guest_energy after the environment), move atoms
+ * [first, first + n) after an accepted step (ceg_guest_env_update). */
+int ceg_guest_env_create(int32_t device, const ceg_cell_t* cell, double cutoff2, int32_t n_species,
+                         const ceg_pair_energy_t* table, int64_t n_env, const double* env_xyz,
+                         const int32_t* env_species, const int32_t* env_mol, ceg_guest_h* out);
+int ceg_guest_env_free(ceg_guest_h h);
+int ceg_guest_env_update(ceg_guest_h h, int64_t first, int64_t n, const double* xyz /* n x 3 */);
+int ceg_guest_env_energy(ceg_guest_h h, int64_t n_trials, int32_t n_atoms, const int32_t* mol_species, int32_t skip_mol,
+                         const double* trial_xyz, double* out);
 int ceg_guest_energy(int32_t device, const ceg_cell_t* cell, double cutoff2, int32_t n_species,
                      const ceg_pair_energy_t* table /* n_species x n_species */, int64_t n_env, const double* env_xyz,
                      const int32_t* env_species, const int32_t* env_mol, int64_t n_trials, int32_t n_atoms,

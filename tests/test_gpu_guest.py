@@ -132,3 +132,26 @@ def test_grid_vs_explicit_supercell_cit7(cuda_lib, orc):
     g.close()
     # (a repulsive site, ~2.5e5 K: the tricubic interpolant is 1.4e-3 off the exact sum there)
     assert abs(e_grid - pair_sum[0]) <= 5e-3 * abs(pair_sum[0]), (e_grid, pair_sum[0])
+
+
+def test_resident_environment_update_and_stateless_form(cuda_lib, orc):
+    """ceg_guest_env_*: the environment stays on the device, accepted moves update it in place; the stateless
+    ceg_guest_energy gives the same numbers."""
+    ff, names = _forcefield()
+    env, geom = _environment(ff, names, 45, 3)
+    rng = np.random.default_rng(9)
+    trials = (env.mat @ rng.random((3, 3000))).T[:, None, :] + geom[None]
+    e0 = ceg.single_contribution_vdw(env, [1, 0, 1], trials, skip_molecule=0)
+    stateless = ceg._lib.guest_energy(0, env.cell_struct(), 144.0, env.table, env.positions, env.species, env.molecule,
+                                      [1, 0, 1], 0, trials)
+    assert np.array_equal(e0, stateless)
+    # move molecule 3 (a CO2: atoms of molecule id 3) somewhere else and compare with a fresh environment / the oracle
+    sel = np.nonzero(env.molecule == 3)[0]
+    new_pos = env.positions[sel] + np.array([3.1, -2.2, 1.7])
+    env.move(int(sel[0]), new_pos)
+    e1 = ceg.single_contribution_vdw(env, [1, 0, 1], trials, skip_molecule=0)
+    want = orc.guest_energy(env, [1, 0, 1], trials, 0)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isinf(e1), np.isinf(want)) and (np.abs(e1[fin] - want[fin]) <= 1e-9 * np.abs(want[fin]) + 1e-6).all()
+    assert not np.array_equal(e0, e1)
+    env.close()
