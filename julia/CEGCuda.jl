@@ -317,6 +317,28 @@ function guest_energies(cell::CegCell, cutoff2::Float64, table::Matrix{CegPairEn
     out
 end
 
+# The environment resident on the device: create once per simulation, evaluate batches, move atoms after accepted steps.
+mutable struct GuestEnv
+    ptr::Ptr{Cvoid}
+    function GuestEnv(cell::CegCell, cutoff2::Float64, table::Matrix{CegPairEnergy}, env_xyz::Matrix{Float64},
+                      env_species::Vector{Int32}, env_mol::Vector{Int32}; device=0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ceg_guest_env_create, libceg), Cint,
+            (Int32, Ref{CegCell}, Cdouble, Int32, Ptr{CegPairEnergy}, Int64, Ptr{Cdouble}, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+            device, cell, cutoff2, size(table, 1), permutedims(table), size(env_xyz, 2), env_xyz, env_species, env_mol, out))
+        h = new(out[])
+        finalizer(x -> ccall((:ceg_guest_env_free, libceg), Cint, (Ptr{Cvoid},), x.ptr), h)
+    end
+end
+function guest_energies(env::GuestEnv, mol_species::Vector{Int32}, skip_mol::Integer, trial_xyz::Array{Float64,3})
+    out = Vector{Float64}(undef, size(trial_xyz, 3))
+    check(ccall((:ceg_guest_env_energy, libceg), Cint, (Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Int32, Ptr{Cdouble}, Ptr{Cdouble}),
+                env.ptr, size(trial_xyz, 3), size(trial_xyz, 2), mol_species, skip_mol, trial_xyz, out))
+    out
+end
+move!(env::GuestEnv, first::Integer, xyz::Matrix{Float64}) =      # atoms first..first+n-1 (1-based) take the columns of xyz
+    check(ccall((:ceg_guest_env_update, libceg), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), env.ptr, first - 1, size(xyz, 2), xyz))
+
 # ---- interpolation sweep over device-generated positions (benchmarking / sampling) -------------------------------------
 function interpolate_sweep(g::EnergyGrid, n::Integer, seed::Integer; first=0, n_keep=0)
     mat = collect(Float64.(ustrip.(u"Å", g.csetup.cell.mat)))            # column-major 3x3
