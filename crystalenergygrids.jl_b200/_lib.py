@@ -141,7 +141,7 @@ def measure_fp64_peak_regops(device: int = 0) -> float:
 
 def selftest_math(x, device: int = 0) -> np.ndarray:
     x = _f64(x, (-1,))
-    out = np.empty((x.shape[0], 4), dtype=np.float64)
+    out = np.empty((x.shape[0], 6), dtype=np.float64)
     _check(load().ceg_selftest_math(C.c_int32(device), C.c_int64(x.shape[0]), _p(x, C.c_double), _p(out, C.c_double)))
     return out
 

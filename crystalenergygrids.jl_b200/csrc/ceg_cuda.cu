@@ -96,6 +96,53 @@ static int use_device(int dev) {
     return 0;
 }
 
+// Streams are recycled across handles (creating and destroying a pair per ceg_probe_create / ceg_probe_free cycle is
+// part of the fixed cost of a create_grid_* call).
+namespace {
+std::mutex g_stream_mu;
+std::vector<std::pair<int, cudaStream_t>> g_streams;
+}  // namespace
+cudaError_t acquire_stream(cudaStream_t* out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_stream_mu);
+        for (size_t i = 0; i < g_streams.size(); i++)
+            if (g_streams[i].first == dev) {
+                *out = g_streams[i].second;
+                g_streams.erase(g_streams.begin() + i);
+                return cudaSuccess;
+            }
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+void release_stream(cudaStream_t s) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    if (g_streams.size() < 64) g_streams.push_back({dev, s});
+    else cudaStreamDestroy(s);
+}
+
+// multiprocessor count per device (launch sizes are multiples of it)
+int sm_count_of(int dev) {
+    static std::mutex mu;
+    static std::vector<int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)cache.size() <= dev) cache.resize(dev + 1, 0);
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+static int sm_count_here() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return sm_count_of(dev);
+}
+
 }  // namespace ceg
 
 using namespace ceg;
@@ -117,10 +164,17 @@ struct ceg_probe_s {
     double min_perp_width = 0;
     DevBuf d_xyz, d_type, d_q, d_table, d_stats;
     // cached expanded image list
-    DevBuf d_ext, d_ext_meta;
+    DevBuf d_ext, d_ext_meta, d_ext_range;
     int n_ext = 0;
+    int ext_plane0 = 0, ext_planes = 0;
     double ext_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int ext_key_planes[2] = {-1, -1};
     bool ext_valid = false;
+    int sm_count = 148;
+    // events of the write-back ring of ceg_grid_build, created once per handle
+    cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr}, ev_free[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_time[3] = {nullptr, nullptr, nullptr};   // first launch, last launch done, last copy done
+    double last_timing[4] = {0, 0, 0, 0};                   // image list (host) ms, kernel span ms, copy tail ms, whole call ms
     // last slab whose image list was too long to be scanned by every tile: remembered so that repeated builds of
     // the same slab go straight to its x windows (list_windows)
     int split_i0 = -1, split_i1 = -1, split_dims[3] = {0, 0, 0};
@@ -128,8 +182,13 @@ struct ceg_probe_s {
     DevBuf d_out, d_raw, d_pos, d_der;
     int64_t last_points = 0;
     ~ceg_probe_s() {
-        if (s_compute) cudaStreamDestroy(s_compute);
-        if (s_copy) cudaStreamDestroy(s_copy);
+        for (int r = 0; r < 3; r++) {
+            if (ev_done[r]) cudaEventDestroy(ev_done[r]);
+            if (ev_free[r]) cudaEventDestroy(ev_free[r]);
+            if (ev_time[r]) cudaEventDestroy(ev_time[r]);
+        }
+        if (s_compute) release_stream(s_compute);
+        if (s_copy) release_stream(s_copy);
     }
 };
 
@@ -280,16 +339,15 @@ extern "C" int ceg_measure_fp64_peak_regops(int32_t device, double* tflops) {
 
 namespace ceg {
 __global__ void selftest_math_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ out) {
-    __shared__ double s_etab[EXP_TAB];
-    for (int i = threadIdx.x; i < EXP_TAB; i += blockDim.x) s_etab[i] = c_exp_tab[i];
-    __syncthreads();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
-    out[4 * i] = exp_neg_fast(-v, s_etab);
-    out[4 * i + 1] = erfcx_fast(v);
-    out[4 * i + 2] = rsqrt_fast(v);
-    out[4 * i + 3] = rcp_fast(v);
+    out[6 * i] = exp_fast(-v);
+    out[6 * i + 1] = erfcx_fast(v);
+    out[6 * i + 2] = rsqrt_fast(v);
+    out[6 * i + 3] = rcp_fast(v);
+    out[6 * i + 4] = exp_acc(-v);
+    out[6 * i + 5] = exp_fast(v);
 }
 }  // namespace ceg
 
@@ -299,12 +357,12 @@ extern "C" int ceg_selftest_math(int32_t device, int64_t n, const double* x, dou
     if (use_device(device)) return 1;
     DevBuf dx, dout;
     CEG_CK(dx.reserve(sizeof(double) * n));
-    CEG_CK(dout.reserve(sizeof(double) * 4 * n));
+    CEG_CK(dout.reserve(sizeof(double) * 6 * n));
     CEG_CK(cudaMemcpy(dx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice));
     selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256>>>(n, dx.as<double>(), dout.as<double>());
     count_launch();
     CEG_CK(cudaGetLastError());
-    CEG_CK(cudaMemcpy(out, dout.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
+    CEG_CK(cudaMemcpy(out, dout.p, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -370,9 +428,13 @@ extern "C" int ceg_probe_create(int32_t device, const ceg_cell_t* supercell, int
         h->h_type[i] = dense[t];
     }
     const int n_present = std::max<int>(1, (int)present.size());
-    if (n_probes > 0 && n_present > TABLE_SMEM_TYPES)
-        return fail("ceg_probe_create: more than 24 distinct framework species in one probe system");
+    // the kernels stage the (probe x present species) table in shared memory; 64 KB hold 744 entries (round 1
+    // stopped at 24 species)
+    if (n_probes > 0 && build_table_bytes(n_probes, n_present) > TABLE_SMEM_MAX)
+        return fail("ceg_probe_create: the (probe x framework species) pair table exceeds 64 KB of shared memory: fuse fewer "
+                    "probes per handle");
     h->n_types = n_present;
+    h->sm_count = sm_count_of(device);
     std::vector<PairDev> tab((size_t)std::max(1, n_probes * n_present));
     memset(tab.data(), 0, sizeof(PairDev) * tab.size());
     for (int p = 0; p < n_probes; p++)
@@ -385,22 +447,29 @@ extern "C" int ceg_probe_create(int32_t device, const ceg_cell_t* supercell, int
             { const double s6 = d.lj_sig2 * d.lj_sig2 * d.lj_sig2; d.lj_c6 = 4.0 * s.lj_eps * s6; d.lj_c12 = d.lj_c6 * s6; }
             d.bA = s.buck_A; d.bB = s.buck_B; d.bC = s.buck_C; d.b_shift = s.buck_shift;
             d.bB2 = s.buck_B * s.buck_B;
+            d.b_lnA = 0.0;
+            if ((s.flags & CEG_PAIR_BUCK) && s.buck_A > 0.0 && std::isfinite(s.buck_A)) {
+                const double l = std::log(s.buck_A);
+                if (std::fabs(l) < 500.0) { d.b_lnA = l; d.flags |= CEG_PAIRHOT_LNA; }
+            }
             if (s.flags & CEG_PAIR_HS) h->max_hs_r2 = std::max(h->max_hs_r2, d.hs_r2);
         }
-    CEG_CK(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
-    CEG_CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CEG_CK(acquire_stream(&h->s_compute));
+    CEG_CK(acquire_stream(&h->s_copy));
     CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * std::max<int64_t>(1, n_atoms)));
     CEG_CK(h->d_type.reserve(sizeof(int) * std::max<int64_t>(1, n_atoms)));
     CEG_CK(h->d_q.reserve(sizeof(double) * std::max<int64_t>(1, n_atoms)));
     CEG_CK(h->d_table.reserve(sizeof(PairDev) * tab.size()));
     CEG_CK(h->d_stats.reserve(2 * sizeof(unsigned long long)));
+    // one stream, one synchronisation (the sources are pageable: each copy is staged before the call returns)
     if (n_atoms > 0) {
-        CEG_CK(cudaMemcpy(h->d_xyz.p, h->h_xyz.data(), sizeof(double) * 3 * n_atoms, cudaMemcpyHostToDevice));
-        CEG_CK(cudaMemcpy(h->d_type.p, h->h_type.data(), sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
-        CEG_CK(cudaMemcpy(h->d_q.p, h->h_q.data(), sizeof(double) * n_atoms, cudaMemcpyHostToDevice));
+        CEG_CK(cudaMemcpyAsync(h->d_xyz.p, h->h_xyz.data(), sizeof(double) * 3 * n_atoms, cudaMemcpyHostToDevice, h->s_compute));
+        CEG_CK(cudaMemcpyAsync(h->d_type.p, h->h_type.data(), sizeof(int) * n_atoms, cudaMemcpyHostToDevice, h->s_compute));
+        CEG_CK(cudaMemcpyAsync(h->d_q.p, h->h_q.data(), sizeof(double) * n_atoms, cudaMemcpyHostToDevice, h->s_compute));
     }
-    CEG_CK(cudaMemcpy(h->d_table.p, tab.data(), sizeof(PairDev) * tab.size(), cudaMemcpyHostToDevice));
-    CEG_CK(cudaMemset(h->d_stats.p, 0, 2 * sizeof(unsigned long long)));
+    CEG_CK(cudaMemcpyAsync(h->d_table.p, tab.data(), sizeof(PairDev) * tab.size(), cudaMemcpyHostToDevice, h->s_compute));
+    CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), h->s_compute));
+    CEG_CK(cudaStreamSynchronize(h->s_compute));
     *out = h.release();
     return 0;
 }
@@ -434,7 +503,7 @@ extern "C" int ceg_compute_derivatives(ceg_probe_h h, int64_t n_pos, const doubl
     P.table = h->d_table.as<PairDev>();
     P.n_types = h->n_types; P.n_probes = h->n_probes; P.want_coulomb = h->want_coulomb;
     P.pos = h->d_pos.as<double>(); P.out = h->d_der.as<double>();
-    const int blocks = (int)std::min<int64_t>((n_pos + 127) / 128, 148 * 16);
+    const int blocks = (int)std::min<int64_t>((n_pos + 127) / 128, (int64_t)h->sm_count * 16);
     derivatives_literal_kernel<<<blocks, 128, 0, h->s_compute>>>(P);
     count_launch();
     CEG_CK(cudaGetLastError());
@@ -445,7 +514,8 @@ extern "C" int ceg_compute_derivatives(ceg_probe_h h, int64_t n_pos, const doubl
 
 // ---- expanded image list ----------------------------------------------------------------------------
 // All periodic images a + n1*A + n2*B + n3*C (A,B,C = supercell vectors) lying inside the box
-// [lo - reach, hi + reach], emitted atom by atom (the reference's summation order, probes.jl:80).
+// [lo - reach, hi + reach], sorted along x (ties: atom order), so that a tile only scans the images its x planes
+// can reach (prepare_build tabulates that index range per plane).
 static void build_ext_list(const ceg_probe_s* h, const double lo[3], const double hi[3], double reach,
                            std::vector<ExtAtom>& ext, std::vector<ExtMeta>& meta) {
     const double* m = h->cell.mat;
@@ -484,11 +554,46 @@ static void build_ext_list(const ceg_probe_s* h, const double lo[3], const doubl
                     meta.push_back(ExtMeta{h->h_type[a], (int)a});
                 }
     }
+    std::vector<int> order(ext.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ext[a].x < ext[b].x; });
+    std::vector<ExtAtom> ext2(ext.size());
+    std::vector<ExtMeta> meta2(meta.size());
+    for (size_t i = 0; i < order.size(); i++) { ext2[i] = ext[order[i]]; meta2[i] = meta[order[i]]; }
+    ext.swap(ext2);
+    meta.swap(meta2);
+}
+
+// Shared memory per CTA.  Coulomb passes carry TX + TY + TZ Gaussian factors per image: the list capacity is chosen so
+// that two CTAs still fit an SM (2 x ~104 KB of the 227 KB), which holds the whole list of a tile in one round for
+// frameworks up to ~530 images within reach (CHA: ~420); VdW-only passes keep 1024 entries (40 KB).
+constexpr size_t BUILD_SMEM_TARGET = 104 << 10;
+static int build_list_cap(int nt, int n_axes, bool coul, int n_probes, int n_types) {
+    if (!build_uses_gtable(n_probes, coul)) return LIST_CAP_MAX;
+    const size_t per = sizeof(ExtAtom) + sizeof(ListMeta) + sizeof(int) + sizeof(double) * n_axes;
+    const size_t tab = build_table_bytes(n_probes, n_types);
+    int cap = tab + per < BUILD_SMEM_TARGET ? (int)((BUILD_SMEM_TARGET - tab - per) / per) : 0;
+    cap = std::min(cap, LIST_CAP_MAX) & ~3;
+    return std::max(cap, nt);          // a scan chunk (one image per thread) must always fit
 }
 
 template <int NT, int NP, bool COUL, bool POLY>
 static cudaError_t launch_tiled(const BuildParams& P, int n_tiles, cudaStream_t s) {
-    grid_build_tiled_kernel<NT, NP, COUL, POLY><<<n_tiles, NT, 0, s>>>(P);
+    static std::mutex mu;
+    static size_t granted[64] = {0};     // per device: dynamic shared memory already opted in for this instantiation
+    const size_t smem = build_smem_bytes(P.list_cap, P.tile[0] + P.tile[1] + P.tile[2], build_uses_gtable(NP, COUL), NP, P.n_types);
+    if (smem > (48u << 10)) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 64 && granted[dev] < smem) {
+            cudaError_t e = cudaFuncSetAttribute(grid_build_tiled_kernel<NT, NP, COUL, POLY>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)(200u << 10)));
+            if (e != cudaSuccess) return e;
+            granted[dev] = std::max(smem, (size_t)(200u << 10));
+        }
+    }
+    grid_build_tiled_kernel<NT, NP, COUL, POLY><<<n_tiles, NT, smem, s>>>(P);
     count_launch();
     return cudaGetLastError();
 }
@@ -552,6 +657,7 @@ static cudaError_t launch_planes(const ceg_probe_s* h, BuildParams P, const ceg_
         const double reach = cutoff + tile_radius(t, gs->delta) + 1e-6;
         P.reach2 = reach * reach;
         P.tile[0] = t.tx; P.tile[1] = t.ty; P.tile[2] = t.tz;
+        P.list_cap = build_list_cap(build_nt(h->n_probes), t.tx + t.ty + t.tz, h->want_coulomb != 0, h->n_probes, h->n_types);
         P.a0 = a; P.a1 = a + rows * tx;
         P.tiles_x = rows;
         P.tiles_y = (gs->dims[1] + 1 + t.ty - 1) / t.ty;
@@ -582,6 +688,8 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     P.kk[0] = 2.0 * h->alpha / std::sqrt(M_PI);
     P.kk[1] = 2.0 * P.alpha2 * P.kk[0];
     P.kk[2] = 4.0 * P.alpha2 * P.alpha2 * P.kk[0];
+    P.alpha_p = h->alpha * ERFCX_P;
+    for (int d = 0; d < 3; d++) P.gauss_step[d] = std::exp(-2.0 * P.alpha2 * gs->delta[d] * gs->delta[d]);
     P.cut_hi = h->cutoff2 + GUARD_BAND;
     // fast path window: away from every mask threshold (hard spheres, the 1 Å rule, the cutoff, the
     // entry of the reference's non-orthogonal image search) and from r -> 0
@@ -599,7 +707,8 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
         const int top = hiword(P.fast_hi);          // exclusive
         P.hi_fast_span = top > P.hi_fast_lo ? (unsigned)(top - P.hi_fast_lo) : 0u;
     }
-    P.poly_erfcx = (h->alpha * cutoff <= ERFCX_XMAX && h->alpha >= 0) ? 1 : 0;
+    P.poly_erfcx = (h->alpha * cutoff <= ERFCX_XMAX && h->alpha * std::sqrt(P.fast_lo) >= ERFCX_XMIN) ? 1 : 0;
+    P.list_cap = LIST_CAP_MAX;                       // per launch: launch_planes
     double rmax = 0.0;
     for (int tx = main_tx(h->n_probes); tx >= 1; tx >>= 1)
         rmax = std::max(rmax, tile_radius(tile_shape_for(h->n_probes, tx), gs->delta));
@@ -623,24 +732,42 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     hi[0] = (i1 - 1) * gs->size[0] / gs->dims[0] + gs->shift[0];
     for (int d = 1; d < 3; d++) { lo[d] = gs->shift[d]; hi[d] = gs->shift[d] + gs->size[d]; }
     double key[8] = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], cutoff, reach};
-    if (!h->ext_valid || memcmp(key, h->ext_key, sizeof key) != 0) {
+    if (!h->ext_valid || memcmp(key, h->ext_key, sizeof key) != 0 || h->ext_key_planes[0] != i0 || h->ext_key_planes[1] != i1) {
         std::vector<ExtAtom> ext;
         std::vector<ExtMeta> meta;
         build_ext_list(h, lo, hi, reach + 1e-6, ext, meta);
+        // per plane: the index range of the images within the cutoff along x (list sorted by x)
+        const int planes = i1 - i0;
+        std::vector<int> range(2 * (size_t)planes);
+        const double xcut = std::sqrt(P.cut_hi) + 1e-9;
+        auto xless = [](const ExtAtom& a, double v) { return a.x < v; };
+        auto xgreater = [](double v, const ExtAtom& a) { return v < a.x; };
+        for (int i = 0; i < planes; i++) {
+            const double x = (double)(i0 + i) * gs->size[0] / gs->dims[0] + gs->shift[0];
+            range[i] = (int)(std::lower_bound(ext.begin(), ext.end(), x - xcut, xless) - ext.begin());
+            range[planes + i] = (int)(std::upper_bound(ext.begin(), ext.end(), x + xcut, xgreater) - ext.begin());
+        }
         CEG_CK(cudaDeviceSynchronize());   // an earlier asynchronous build may still be reading the old list
         h->n_ext = (int)ext.size();
         CEG_CK(h->d_ext.reserve(sizeof(ExtAtom) * std::max<size_t>(1, ext.size())));
         CEG_CK(h->d_ext_meta.reserve(sizeof(ExtMeta) * std::max<size_t>(1, meta.size())));
+        CEG_CK(h->d_ext_range.reserve(sizeof(int) * range.size()));
         if (!ext.empty()) {
             CEG_CK(cudaMemcpy(h->d_ext.p, ext.data(), sizeof(ExtAtom) * ext.size(), cudaMemcpyHostToDevice));
             CEG_CK(cudaMemcpy(h->d_ext_meta.p, meta.data(), sizeof(ExtMeta) * meta.size(), cudaMemcpyHostToDevice));
         }
+        CEG_CK(cudaMemcpy(h->d_ext_range.p, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
         memcpy(h->ext_key, key, sizeof key);
+        h->ext_key_planes[0] = i0; h->ext_key_planes[1] = i1;
+        h->ext_plane0 = i0; h->ext_planes = planes;
         h->ext_valid = true;
     }
     P.ext = h->d_ext.as<ExtAtom>();
     P.ext_meta = h->d_ext_meta.as<ExtMeta>();
     P.n_ext = h->n_ext;
+    P.ext_lo = h->d_ext_range.as<int>();
+    P.ext_hi = h->d_ext_range.as<int>() + h->ext_planes;
+    P.ext_plane0 = h->ext_plane0;
     return 0;
 }
 
@@ -844,20 +971,20 @@ static int grid_upload_impl(int32_t device, const ceg_cell_t* unitcell, const ce
         } else {
             CEG_CK(cudaDeviceSynchronize());     // the caller's producer (any stream) has finished writing the grid
         }
-        const int blocks = (int)std::min<int64_t>((npts + 255) / 256, 148 * 32);
+        const int blocks = (int)std::min<int64_t>((npts + 255) / 256, sm_count_here() * 32);
         relayout_nodes_kernel<<<blocks, 256, 0, h->stream>>>(src, node_dst.as<Rec8>(), npts, scale);
         count_launch();
         CEG_CK(cudaGetLastError());
         if (layout == LAYOUT_BLOCK) {
             const size_t bricks = (size_t)((nx + 1) / 2) * ((ny + 1) / 2) * ((nz + 1) / 2);
             CEG_CK(h->d_nodes.reserve(sizeof(Rec8) * 8 * bricks));
-            block_records_kernel<<<148 * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz);
+            block_records_kernel<<<sm_count_here() * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz);
             count_launch();
             CEG_CK(cudaGetLastError());
         } else if (layout != LAYOUT_NODE) {
             const int corners = (layout == LAYOUT_PAIR) ? 2 : (layout == LAYOUT_QUAD) ? 4 : 8;
             CEG_CK(h->d_nodes.reserve(node_bytes * corners));
-            expand_records_kernel<<<148 * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz, corners);
+            expand_records_kernel<<<sm_count_here() * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz, corners);
             count_launch();
             CEG_CK(cudaGetLastError());
         }
@@ -887,7 +1014,7 @@ extern "C" int ceg_grid_free(ceg_grid_h h) {
     return 0;
 }
 
-static int interp_blocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 64)); }
+static int interp_blocks(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, sm_count_here() * 64)); }
 
 static cudaError_t launch_interpolate(const GridDev& g, int64_t n, const double* d_xyz, double* d_out, cudaStream_t s) {
     const int blocks = interp_blocks(n);
@@ -921,7 +1048,7 @@ extern "C" int ceg_interpolate_sweep(ceg_grid_h h, int64_t first, int64_t n, uin
     n_keep = std::min(n_keep, n);
     std::lock_guard<std::mutex> lk(h->mu);
     if (use_device(h->device)) return 1;
-    const int blocks = 148 * 8;          // fixed: the reduction order (and so the sum) does not depend on n
+    const int blocks = SWEEP_BLOCKS;    // fixed: the reduction order (and so the sum) depends neither on n nor on the device
     DevBuf d_mat, d_part, d_res, d_keep;
     CEG_CK(d_mat.reserve(sizeof(double) * 9));
     CEG_CK(d_part.reserve(sizeof(SweepPartial) * blocks));
@@ -1141,7 +1268,7 @@ static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const d
     if (smem > 200 * 1024) return fail("ceg_ewald_reciprocal: molecule too large for the shared-memory phase tables");
     if (smem > 48 * 1024)
         CEG_CK(cudaFuncSetAttribute(reciprocal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_pos + RECIP_WARPS - 1) / RECIP_WARPS, 148 * 16));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_pos + RECIP_WARPS - 1) / RECIP_WARPS, sm_count_here() * 16));
     reciprocal_kernel<<<blocks, RECIP_WARPS * 32, smem, s>>>(P);
     count_launch();
     CEG_CK(cudaGetLastError());
@@ -1367,7 +1494,7 @@ extern "C" int ceg_block_from_spheres(int32_t device, const ceg_cell_t* unitcell
         CEG_CK(cudaMemcpy(d_c.p, centers, sizeof(double) * 3 * n_spheres, cudaMemcpyHostToDevice));
         CEG_CK(cudaMemcpy(d_r.p, radius2, sizeof(double) * n_spheres, cudaMemcpyHostToDevice));
     }
-    block_spheres_kernel<<<148 * 8, 256>>>(to_dev(*unitcell), to_dev(*gs), n_spheres, d_c.as<double>(), d_r.as<double>(),
+    block_spheres_kernel<<<sm_count_here() * 8, 256>>>(to_dev(*unitcell), to_dev(*gs), n_spheres, d_c.as<double>(), d_r.as<double>(),
                                           d_m.as<uint8_t>());
     count_launch();
     CEG_CK(cudaGetLastError());
@@ -1386,7 +1513,7 @@ extern "C" int ceg_block_from_values(int32_t device, const ceg_gridspec_t* gs, c
     CEG_CK(d_v.reserve(sizeof(float) * npts));
     CEG_CK(d_m.reserve(npts));
     CEG_CK(cudaMemcpy(d_v.p, values, sizeof(float) * npts, cudaMemcpyHostToDevice));
-    block_from_values_kernel<<<148 * 8, 256>>>(d_v.as<float>(), threshold, nx, ny, nz, d_m.as<uint8_t>());
+    block_from_values_kernel<<<sm_count_here() * 8, 256>>>(d_v.as<float>(), threshold, nx, ny, nz, d_m.as<uint8_t>());
     count_launch();
     CEG_CK(cudaGetLastError());
     CEG_CK(cudaMemcpy(mask, d_m.p, npts, cudaMemcpyDeviceToHost));
@@ -1478,7 +1605,7 @@ static int energy_points_enqueue(EnergyPointsParams P, ceg_ewald_h ewald, bool h
     P.out_vdw = d_v;
     P.out_coulomb = d_c;
     P.blocked = d_blk;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_pos + 127) / 128, 148 * 32));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_pos + 127) / 128, sm_count_here() * 32));
     energy_points_kernel<<<blocks, 128, 0, s>>>(P);
     count_launch();
     CEG_CK(cudaGetLastError());
@@ -1607,7 +1734,7 @@ extern "C" int ceg_energy_lattice(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid
         for (int d = 0; d < 9; d++) L.steps[d] = steps[d];
         L.n_atoms = n_atoms;
         L.n_lat = n_lat;
-        const int blocks = (int)std::min<int64_t>((n_lat + 255) / 256, 148 * 32);
+        const int blocks = (int)std::min<int64_t>((n_lat + 255) / 256, sm_count_here() * 32);
         for (int r = 0; r < n_rot && !rc; r++) {      // one rotation per pass bounds the scratch to one lattice
             L.rotpos = d_rot.as<double>() + (size_t)3 * n_atoms * r;
             lattice_positions_kernel<<<blocks, 256, 0, s>>>(L, d_xyz.as<double>());

@@ -264,6 +264,7 @@ struct SweepPartial {
 };
 
 constexpr int SWEEP_THREADS = 256;
+constexpr int SWEEP_BLOCKS = 148 * 8;   // 8 CTAs per SM of a B200; a constant so that the reduction order is device-independent
 
 template <int LAYOUT>
 __global__ void __launch_bounds__(SWEEP_THREADS) interpolate_sweep_kernel(const GridDev g, int64_t first, int64_t n,

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CEG_ABI_VERSION 1
+#define CEG_ABI_VERSION 2
 
 /* Periodic cell used for minimum-image distances (utils.jl:146-155, 210-246).
  * `ortho` and `safemin2` are the outputs of prepare_periodic_distance_computations. */
@@ -109,7 +109,7 @@ int ceg_measure_fp64_peak(int32_t device, double* tflops);
 int ceg_measure_fp64_peak_regops(int32_t device, double* tflops);
 
 /* Self-test hook for the branch-free device math of the construction kernels (fastmath.cuh):
- * out[4*i..] = exp_neg_fast(-x[i]), erfcx_fast(x[i]), rsqrt_fast(x[i]), rcp_fast(x[i]), x[i] > 0. */
+ * out[6*i..] = exp_fast(-x[i]), erfcx_fast(x[i]), rsqrt_fast(x[i]), rcp_fast(x[i]), exp_acc(-x[i]), exp_fast(x[i]), x[i] > 0. */
 int ceg_selftest_math(int32_t device, int64_t n, const double* x, double* out);
 
 /* Pin / unpin a caller-owned host buffer so that slab write-back and query upload overlap compute. */

@@ -473,3 +473,13 @@ int ceg_o_num_threads(void) {
     return 1;
 #endif
 }
+
+/* bench.py's reference arm runs under torch.distributed.run, which exports OMP_NUM_THREADS=1 to its workers:
+ * the timing harness sets the team size explicitly (all cores of the process' affinity mask). */
+void ceg_o_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

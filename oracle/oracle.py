@@ -71,6 +71,13 @@ def num_threads() -> int:
     return int(lib().ceg_o_num_threads())
 
 
+def use_all_cores() -> int:
+    """Size the OpenMP team to the cores this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().ceg_o_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 # ---- tricubic matrix from its definition (constants.jl:24-89 is its tabulated form) ---------------
 def tricubic_coeff() -> np.ndarray:
     """The 64x64 Lekien–Marsden matrix: inverse of the corner-constraint matrix B, where row

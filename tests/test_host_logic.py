@@ -158,7 +158,7 @@ def test_cabi_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(ceg.LIB_PATH)          # must load without a GPU
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ceg_abi_version() == 1
+    assert lib.ceg_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():

@@ -1,0 +1,11 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+L=gpurun_out/r2_run4.log
+( timeout 900 python -m pytest tests/test_gpu_build.py tests/test_gpu_setup_raspa.py -m gpu -x -q 2>&1 | tail -5 ) > $L 2>&1
+for v in d0 gt2; do
+  export CEG_LIB_PATH=$PWD/tools/variants/$v.so
+  echo "== $v" >> $L
+  timeout 300 python tools/exp_build.py 0.10 5 >> $L 2>&1
+  timeout 600 python tools/exp_configs.py 2>&1 | grep -v generat >> $L
+done
