@@ -5,9 +5,14 @@
     python bench.py --gpus N --steps K --warmup W            # product arm (CUDA, C ABI)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
 
-One JSON line on stdout (rank 0).  Under torchrun (N > 1) one rank per GPU; the C4 grid is sharded
-into contiguous x-slabs (no data-path collective) and interpolation queries are
-sharded by index.  Timings are device-side (CUDA events on the launching stream), max over ranks.
+One JSON line on stdout (rank 0).  Under torchrun (N > 1) one rank per GPU; the grids are sharded into
+contiguous x-slabs (no data-path collective) and interpolation queries by index.  Timings are
+device-side (CUDA events on the launching stream), max over ranks; end-to-end figures use the host clock around
+the reference-facing call.
+
+Top-level keys: C4 (BASELINE configs[3]) grid construction.  Sibling blocks: `e2e_device` (grid pair built,
+gathered over NVLink and interpolable on every GPU), `c1`, `interp` (C2), `ewald`, `c3`, `c5` (configs[2] and
+configs[4]), `latency_us`, `guest`.
 """
 from __future__ import annotations
 
@@ -29,12 +34,31 @@ WORKLOAD_BUILD = ("C4: CHA_1.4_3b4eeb96 (972 framework atoms, rhombohedral 28.37
                   "(326x306x284 = 28,330,704 points), 12 Å cutoff, x-slab sharded")
 WORKLOAD_INTERP = ("C2: tricubic interpolation of 10^7 random positions (splitmix64 seed 1) on the C1 Na+ VdW and "
                    "Coulomb grids (0.15 Å, 218x204x190 nodes, 270 MB each)")
+WORKLOAD_C3 = ("C3: synthetic MFI-shaped framework (288 atoms, 20.022x19.899x13.383 Å, supercell 2x2x2 = 2304 atoms), CH4, C_co2 "
+               "and O_co2 Lennard-Jones probes + Ewald real-space grid fused in one pass, 0.15 Å (134x134x90 nodes x 4 grids)")
+WORKLOAD_C5 = ("C5: synthetic MOF-shaped framework (5000 atoms, 50 Å cubic cell), CH4 Lennard-Jones + Ewald real-space grids "
+               "at 0.10 Å (502^3 = 126.5 M points x 2 grids, 4.05 GB each), x-slab sharded, then 10^9 device-generated "
+               "interpolation queries on both grids, sharded by query")
 N_QUERIES = 10_000_000
 N_RECIP = 1_000_000
+N_SWEEP = 1_000_000_000
 
 
 def env_rank():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    aff = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return {"cpu_model": model, "cpus_online": os.cpu_count(), "cpus_in_affinity_mask": aff}
 
 
 def bind_to_gpu_cpus(gpu_index: int):
@@ -115,6 +139,35 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def csrc_digest() -> str:
+    """Digest of the kernel sources the loaded library was built from (tools/ncu_extract.py stores the same digest next
+    to every DRAM-traffic figure it extracts from an ncu capture)."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "crystalenergygrids.jl_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:12]
+
+
+def profiled_traffic(key: str, regs_loaded: int):
+    """DRAM bytes per unit of the dominant kernel from the committed ncu capture (profiles/traffic.json, written by
+    tools/ncu_extract.py traffic): quoted only if the capture was taken on the kernel that is loaded now (same source
+    digest, same register count) — a stale capture yields null instead of a wrong number."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(p):
+        return None, "no ncu capture committed"
+    d = json.load(open(p)).get(key)
+    if not d:
+        return None, "no ncu capture for this kernel"
+    if int(d.get("registers", -1)) != int(regs_loaded):
+        return None, f"ncu capture is of a {d.get('registers')}-register build, the loaded kernel uses {regs_loaded}: stale"
+    if d.get("csrc_digest") != csrc_digest():
+        return None, f"kernel sources changed since the ncu capture ({d.get('csrc_digest')} -> {csrc_digest()}): stale"
+    return float(d["dram_bytes_per_unit"]), d.get("source", "profiles/")
+
+
 # ---------------------------------------------------------------------------------------------------
 def flops_per_point(inp, stats):
     """per in-cutoff pair 8 (distance) + 64 (Ewald real-space) for every atom + 59
@@ -133,6 +186,10 @@ def flops_per_point(inp, stats):
     return n_in * per_pair, n_in
 
 
+class Ctx:
+    pass
+
+
 def run_product(args):
     import torch
     import torch.distributed as dist
@@ -149,7 +206,7 @@ def run_product(args):
     if world > 1:
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
-                                timeout=datetime.timedelta(seconds=180))
+                                timeout=datetime.timedelta(seconds=300))
 
     def barrier():
         torch.cuda.synchronize()
@@ -171,10 +228,16 @@ def run_product(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def min_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
     K, W = args.steps, args.warmup
     stream = torch.cuda.current_stream().cuda_stream
-    inp, cset1, ex = wl.load_fixture("cha_na")
-    cset4 = wl.respace(cset1, 0.10)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lam_v, thr_v = ceg.vdw_scaling()
     lam_c, thr_c = ceg.coulomb_scaling()
     launches0 = ceg._lib.kernel_launch_count()
@@ -182,36 +245,60 @@ def run_product(args):
     fp64_peak_regops = ceg._lib.measure_fp64_peak_regops(dev)
     hbm_peak, hbm_src = measured_peaks()
 
-    # ================= construction: kernel-only, outputs resident in HBM ===========================
+    def timed_build(ps, gs, a, b, ptrs, reps, warm):
+        for _ in range(warm):
+            ceg._lib.grid_build_dev(ps.handle, gs, a, b, lam_v, thr_v, lam_c, thr_c, ptrs, stream)
+        barrier()
+        l0 = ceg._lib.kernel_launch_count()
+        ev0.record()
+        for _ in range(reps):
+            ceg._lib.grid_build_dev(ps.handle, gs, a, b, lam_v, thr_v, lam_c, thr_c, ptrs, stream)
+        ev1.record()
+        barrier()
+        mine = ev0.elapsed_time(ev1) / reps
+        return mine, max_over_ranks(mine), ceg._lib.kernel_launch_count() - l0
+
+    def gather_full(mine_slabs, sl, shape_full):
+        """x-slabs [8][planes][ny][nz] of every rank -> full [8][nx][ny][nz] grid on every rank (NCCL over NVLink)."""
+        full = torch.empty(shape_full, dtype=torch.float32, device="cuda")
+        if world == 1:
+            full.copy_(mine_slabs)
+            return full
+        pmax = max(e - s for s, e in sl)
+        a, b = sl[rank]
+        send = mine_slabs
+        if b - a != pmax:
+            send = torch.zeros((8, pmax) + tuple(shape_full[2:]), dtype=torch.float32, device="cuda")
+            send[:, :b - a] = mine_slabs
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send)
+        for (s, e), p in zip(sl, parts):
+            full[:, s:e] = p[:, :e - s]
+        return full
+
+    # ================= C4 construction: kernel-only, outputs resident in HBM ===========================
+    inp, cset1, ex = wl.load_fixture("cha_na")
+    cset4 = wl.respace(cset1, 0.10)
     nx, ny, nz = cset4.nodes
-    a, b = slabs(nx, world)[rank]
+    sl4 = slabs(nx, world)
+    a, b = sl4[rank]
     gs4 = ceg._lib.make_gridspec(cset4)
     ps = ceg.ProbeSystem(None, None, inputs=inp, device=dev)
     d_out = [torch.empty((8, b - a, ny, nz), dtype=torch.float32, device="cuda") for _ in range(2)]
     ptrs = [t.data_ptr() for t in d_out]
-    for _ in range(W):
-        ceg._lib.grid_build_dev(ps.handle, gs4, a, b, lam_v, thr_v, lam_c, thr_c, ptrs, stream)
-    barrier()
     sampler = ClockSampler(dev)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = ceg._lib.kernel_launch_count()
-    e0.record()
-    for _ in range(K):
-        ceg._lib.grid_build_dev(ps.handle, gs4, a, b, lam_v, thr_v, lam_c, thr_c, ptrs, stream)
-    e1.record()
-    barrier()
-    build_ms = max_over_ranks(e0.elapsed_time(e1)) / K
-    build_launches = ceg._lib.kernel_launch_count() - l0
+    my_ms, build_ms, build_launches = timed_build(ps, gs4, a, b, ptrs, K, W)
     clocks = sampler.stop()
     stats = ceg._lib.probe_last_stats(ps.handle)
     fl_pp, n_in_pp = flops_per_point(inp, stats)
-    my_ms = e0.elapsed_time(e1) / K
     my_tflops = fl_pp * stats["n_points"] / (my_ms * 1e-3) / 1e12
     total_points = nx * ny * nz
     build_value = total_points / (build_ms * 1e-3)
+    build_regs = ceg._lib.kernel_registers(0, dev)
+    tr_b, tr_b_src = profiled_traffic("build", build_regs)
 
-    # ================= construction: end to end through the host C ABI ==============================
+    # ================= C4 end to end, (1): through the host C ABI into pinned host arrays ==============
     host = [torch.empty((8, nx, ny, nz), dtype=torch.float32).pin_memory() if world == 1 else
             torch.empty((8, nx, ny, nz), dtype=torch.float32) for _ in range(2)]
     host_np = [h.numpy() for h in host]
@@ -221,21 +308,74 @@ def run_product(args):
                 ceg._lib.host_register(h[c, a:b])
     h2d_bytes = (inp.positions.nbytes + inp.types.nbytes + inp.charges.nbytes + inp.table.nbytes + 200)
     d2h_bytes = 2 * 8 * (b - a) * ny * nz * 4
+    phases = {"probe_create_ms": [], "image_list_host_ms": [], "kernel_span_ms": [], "copy_tail_ms": [], "build_call_ms": [],
+              "probe_free_ms": []}
 
-    def e2e_step():
+    def e2e_step(record=False):
+        t0 = time.perf_counter()
         p2 = ceg.ProbeSystem(None, None, inputs=inp, device=dev)
+        t1 = time.perf_counter()
         ceg._lib.grid_build(p2.handle, gs4, a, b, lam_v, thr_v, lam_c, thr_c, host_np, None)
+        t2 = time.perf_counter()
+        tm = ceg._lib.probe_last_timing(p2.handle)
         p2.close()
+        t3 = time.perf_counter()
+        if record:
+            phases["probe_create_ms"].append((t1 - t0) * 1e3)
+            phases["build_call_ms"].append((t2 - t1) * 1e3)
+            phases["probe_free_ms"].append((t3 - t2) * 1e3)
+            for k in ("image_list_host_ms", "kernel_span_ms", "copy_tail_ms"):
+                phases[k].append(tm[k])
 
-    for _ in range(max(1, W // 2)):
+    n_e2e = max(2, K // 2)
+    for _ in range(max(2, W // 2)):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(max(1, K // 2)):
-        e2e_step()
+    for _ in range(n_e2e):
+        e2e_step(True)
     barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / max(1, K // 2)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_e2e
     e2e_value = total_points / (e2e_ms * 1e-3)
+    breakdown = {k: float(np.mean(v)) for k, v in phases.items()}
+    breakdown["note"] = ("rank 0, mean per call: ceg_probe_create (uploads, streams from the library's pool) / host time "
+                         "building image lists (cached on the handle: a fresh handle per call builds it once) / device span "
+                         "first-to-last kernel / tail between the last kernel and the last slab copy / whole "
+                         "ceg_grid_build call / ceg_probe_free")
+    del host, host_np
+
+    # ================= C4 end to end, (2): grid pair resident and interpolable on EVERY GPU =============
+    # build_dev (x-slab) -> all-gather over NVLink -> ceg_grid_upload_dev (parse_grid's conversion on the device):
+    # the hand-off the reference makes through `.grid` files (raspa.jl:430-438), without host memory in the path.
+    def device_resident_step():
+        ceg._lib.grid_build_dev(ps.handle, gs4, a, b, lam_v, thr_v, lam_c, thr_c, ptrs, stream)
+        egs = []
+        for g, prec in enumerate((np.inf, 1e-6)):
+            full = gather_full(d_out[g], sl4, (8, nx, ny, nz))
+            egs.append(ceg.EnergyGrid.from_device(cset4, inp.supercell, prec, full.data_ptr(), device=dev))
+            del full
+        return egs
+
+    for eg in device_resident_step():
+        eg.close()
+    barrier()
+    n_dr = max(2, K // 3)
+    t0 = time.perf_counter()
+    for i in range(n_dr):
+        egs = device_resident_step()
+        torch.cuda.synchronize()
+        if i < n_dr - 1:
+            for eg in egs:
+                eg.close()
+    barrier()
+    dr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_dr
+    # proof of use: the same 1000 queries on every rank's replica
+    chk_pos = wl.random_positions(cset4.cell.mat, 1000, 5)
+    chk = float(np.where(ceg.interpolate_grid(egs[0], chk_pos) == 1e100, 0.0, ceg.interpolate_grid(egs[0], chk_pos)).sum())
+    chk_same = (min_over_ranks(chk) == max_over_ranks(chk))
+    for eg in egs:
+        eg.close()
+    del d_out
 
     # ================= C1 (0.15 Å) on this GPU: the "< 1 s" headline, and the grids for C2 ============
     nx1, ny1, nz1 = cset1.nodes
@@ -249,15 +389,8 @@ def run_product(args):
     c1_e2e_ms = (time.perf_counter() - t0) * 1e3
     d1 = [torch.empty((8, nx1, ny1, nz1), dtype=torch.float32, device="cuda") for _ in range(2)]
     p1 = [t.data_ptr() for t in d1]
-    ceg._lib.grid_build_dev(ps.handle, gs1, 0, nx1, lam_v, thr_v, lam_c, thr_c, p1, stream)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(3):
-        ceg._lib.grid_build_dev(ps.handle, gs1, 0, nx1, lam_v, thr_v, lam_c, thr_c, p1, stream)
-    e1.record()
-    torch.cuda.synchronize()
-    c1_kernel_ms = e0.elapsed_time(e1) / 3
-    del d1, d_out
+    c1_kernel_ms, _, _ = timed_build(ps, gs1, 0, nx1, p1, 3, 1)
+    del d1
     ps.close()
 
     # ================= interpolation (C2) ============================================================
@@ -266,44 +399,62 @@ def run_product(args):
     eg_v = ceg.EnergyGrid(cset1, (1, 1, 1), float("inf"), True, gK[0], dev)
     eg_c = ceg.EnergyGrid(cset1, (1, 1, 1), 1e-6, True, gK[1], dev)
     hv, hc = eg_v.handle, eg_c.handle
+    hp = eg_v.pair_with(eg_c)
     qa, qb = slabs(N_QUERIES, world)[rank]
     nq = qb - qa
     pos_host = torch.from_numpy(wl.random_positions(cset1.cell.mat, nq, 1, start=qa)).pin_memory()
     d_pos = pos_host.cuda()
-    d_e = [torch.empty(nq, dtype=torch.float64, device="cuda") for _ in range(2)]
+    d_e = [torch.empty(nq, dtype=torch.float64, device="cuda") for _ in range(4)]
+    KI = max(K, 20)
 
-    def interp_step():
+    def timed(fn, reps):
+        for _ in range(W):
+            fn()
+        barrier()
+        l0 = ceg._lib.kernel_launch_count()
+        ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record()
+        barrier()
+        mine = ev0.elapsed_time(ev1) / reps
+        return mine, max_over_ranks(mine), ceg._lib.kernel_launch_count() - l0
+
+    def interp_separate():
         ceg._lib.interpolate_dev(hv, nq, d_pos.data_ptr(), d_e[0].data_ptr(), stream)
         ceg._lib.interpolate_dev(hc, nq, d_pos.data_ptr(), d_e[1].data_ptr(), stream)
 
-    for _ in range(W):
-        interp_step()
-    barrier()
+    def interp_pair():
+        ceg._lib.interpolate_pair_dev(hp, nq, d_pos.data_ptr(), d_e[2].data_ptr(), d_e[3].data_ptr(), stream)
+
+    sep_mine, sep_ms, _ = timed(interp_separate, KI)
     sampler2 = ClockSampler(dev)
     sampler2.start()
-    l0 = ceg._lib.kernel_launch_count()
-    KI = max(K, 20)
-    e0.record()
-    for _ in range(KI):
-        interp_step()
-    e1.record()
-    barrier()
-    interp_ms = max_over_ranks(e0.elapsed_time(e1)) / KI
-    interp_launches = ceg._lib.kernel_launch_count() - l0
+    pair_mine, pair_ms, interp_launches = timed(interp_pair, KI)
     clocks2 = sampler2.stop()
-    interp_value = 2 * N_QUERIES / (interp_ms * 1e-3)
-    my_interp_ms = e0.elapsed_time(e1) / KI
-    interp_gbs = 2 * nq * 288.0 / (my_interp_ms * 1e-3) / 1e9
-    blocked_fraction = float((d_e[0] == 1e100).double().mean().item())
-    checksum = float(torch.where(d_e[0] == 1e100, torch.zeros_like(d_e[0]), d_e[0]).sum().item())
-    # e2e: pinned host positions in, host energies out, through ceg_interpolate
+    assert torch.equal(d_e[0], d_e[2]) and torch.equal(d_e[1], d_e[3]), "fused pair records differ from the separate lookups"
+    # headline = the faster of the two device paths (the fused records double the working set of a launch: on these
+    # 270 MB grids it crosses the ~500 MB footprint beyond which the B200's random-sector rate collapses)
+    use_pair = pair_ms < sep_ms
+    best_ms = pair_ms if use_pair else sep_ms
+    interp_value = 2 * N_QUERIES / (best_ms * 1e-3)
+    pair_gbs = nq * 552.0 / (pair_mine * 1e-3) / 1e9
+    sep_gbs = 2 * nq * 288.0 / (sep_mine * 1e-3) / 1e9
+    blocked_fraction = float((d_e[2] == 1e100).double().mean().item())
+    checksum = float(torch.where(d_e[2] == 1e100, torch.zeros_like(d_e[2]), d_e[2]).sum().item())
+    pair_regs = ceg._lib.kernel_registers(2, dev)
+    sep_regs = ceg._lib.kernel_registers(1, dev)
+    tr_i, tr_i_src = profiled_traffic("interp_pair" if use_pair else "interp", pair_regs if use_pair else sep_regs)
+    # e2e: pinned host positions in, host energies out, through the reference-facing batched call
     out_host = torch.empty((2, nq), dtype=torch.float64).pin_memory()
     pos_np = pos_host.numpy()
     out_np = out_host.numpy()
 
-    def interp_e2e():
-        # the reference-facing call: host positions in, host energies out, both grids (grids.jl:316-318)
-        ceg._lib.interpolate_multi([hv, hc], pos_np, out_np)
+    def interp_e2e():     # both grids at the same positions (grids.jl:316-318), host arrays in and out
+        if use_pair:
+            ceg._lib.interpolate_pair(hp, pos_np, out_np)
+        else:
+            ceg._lib.interpolate_multi([hv, hc], pos_np, out_np)
     interp_e2e()
     barrier()
     t0 = time.perf_counter()
@@ -311,7 +462,7 @@ def run_product(args):
         interp_e2e()
     barrier()
     interp_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
-    assert np.array_equal(out_np[0], d_e[0].cpu().numpy())
+    assert np.array_equal(out_np[0], d_e[2].cpu().numpy())
 
     # ================= reciprocal-space Ewald + fused energy_points (A9/A12), this rank's share =========
     n_unit = len(ex["site_charge"])
@@ -322,18 +473,15 @@ def run_product(args):
     rec_pos = torch.from_numpy(wl.random_positions(cset1.cell.mat, n_rec, 7, start=rank * n_rec)).pin_memory()
     d_rec = rec_pos.cuda()
     d_rec_out = torch.empty(n_rec, dtype=torch.float64, device="cuda")
-    for _ in range(W):
-        ceg._lib.ewald_reciprocal_dev(ef.handle, n_rec, np.array([qna]), d_rec.data_ptr(), 0.0, 0.0, d_rec_out.data_ptr(), stream)
-    barrier()
-    e0.record()
-    for _ in range(KI):
-        ceg._lib.ewald_reciprocal_dev(ef.handle, n_rec, np.array([qna]), d_rec.data_ptr(), 0.0, 0.0, d_rec_out.data_ptr(), stream)
-    e1.record()
-    barrier()
-    rec_ms = max_over_ranks(e0.elapsed_time(e1)) / KI
+    qarr = np.array([qna])
+    _, rec_ms, _ = timed(lambda: ceg._lib.ewald_reciprocal_dev(ef.handle, n_rec, qarr, d_rec.data_ptr(), 0.0, 0.0,
+                                                               d_rec_out.data_ptr(), stream), KI)
     n_k = ef.kspace.num_kvecs
     na_sys = ceg.RASPASystem(np.diag([np.inf] * 3), np.zeros((1, 3)), ["Na"], np.ones(1), np.array([qna]), True)
     setup = ceg.CrystalEnergySetup(fw, na_sys, eg_c, np.array([qna]), [eg_v], [0], ef, None, ceg.BlockFile(cset1))
+    if not use_pair:
+        eg_v.unpair()      # the library evaluates through the fused records for as long as they are registered
+    setup.fused_pairs = use_pair
     rec_np = rec_pos.numpy()[:, None, :]
     ceg.energy_points(setup, rec_np)
     barrier()
@@ -342,6 +490,147 @@ def run_product(args):
         ceg.energy_points(setup, rec_np)
     barrier()
     ep_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+
+    # ================= latency of single Monte-Carlo steps (montecarlo.jl:490-504 consumer), rank 0 ===========
+    latency = None
+    if rank == 0:
+        def med_us(fn, n=300):
+            for _ in range(20):
+                fn()
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return float(np.median(ts) * 1e6)
+        one = rec_np[:1]
+        p64 = rec_np[:64]
+        from ceg_b200.grids import _energy_args
+        vh, ch, eh, bh, enc_, stat_ = _energy_args(setup, True)
+        call1, ov1, oc1 = ceg._lib.energy_points_prepared(vh, ch, eh, bh, setup.atomsidx, setup.charges, one, enc_, stat_)
+        call64, _, _ = ceg._lib.energy_points_prepared(vh, ch, eh, bh, setup.atomsidx, setup.charges, p64, enc_, stat_)
+        callf, _, _ = ceg._lib.energy_points_prepared(vh, ch, None, bh, setup.atomsidx, setup.charges, one, 0.0, 0.0)
+        call1()
+        v_ref, c_ref = ceg.energy_points(setup, rec_np[:20000])
+        assert ov1[0] == v_ref[0] and abs(oc1[0] - c_ref[0]) <= 1e-9 * abs(c_ref[0]) + 1e-6
+        latency = {
+            "c_abi_energy_point_1_placement": med_us(call1, 2000),
+            "c_abi_energy_points_64_placements": med_us(call64, 1000),
+            "c_abi_framework_interactions_1_placement": med_us(callf, 2000),
+            "c_abi_note": "ceg_energy_points re-issued on prepared argument buffers (no Python marshalling): what a compiled "
+                          "host — the Julia shim's ccall — pays per call; one kernel launch, mapped pinned I/O, flag wait",
+            "energy_point_1_placement": med_us(lambda: ceg.energy_points(setup, one)),
+            "energy_points_64_placements": med_us(lambda: ceg.energy_points(setup, p64)),
+            "framework_interactions_1_placement": med_us(lambda: ceg.energy_points(setup, one, reciprocal=False)),
+            "interpolate_grid_1_point": med_us(lambda: ceg._lib.interpolate(hv, one[0])),
+            "ewald_reciprocal_1_placement": med_us(lambda: ceg._lib.ewald_reciprocal(ef.handle, one, qarr, 0.0, 0.0)),
+            "unit": "us per call through the host API (median of 300), host positions in, host energies out",
+            "note": "the reference's CPU call is ~1-2 us: a serial Markov chain should keep single-point interpolate_grid on the "
+                    "CPU and hand batches of trial placements to this path",
+        }
+    eg_v.close()
+    eg_c.close()
+    del d_e, d_pos, d_rec, d_rec_out
+
+    # ================= C3 (BASELINE configs[2]): 3 LJ probes + Coulomb fused, x-slab sharded ==================
+    inp3, cs3, _ = wl.synthetic_inputs("mfi", 0.15, ("C_ch4", "C_co2", "O_co2"), True)
+    nx3, ny3, nz3 = cs3.nodes
+    a3, b3 = slabs(nx3, world)[rank]
+    gs3 = ceg._lib.make_gridspec(cs3)
+    ps3 = ceg.ProbeSystem(None, None, inputs=inp3, device=dev)
+    d3 = [torch.empty((8, b3 - a3, ny3, nz3), dtype=torch.float32, device="cuda") for _ in range(4)]
+    c3_mine, c3_ms, c3_launches = timed_build(ps3, gs3, a3, b3, [t.data_ptr() for t in d3], max(K, 10), W)
+    st3 = ceg._lib.probe_last_stats(ps3.handle)
+    fl3, nin3 = flops_per_point(inp3, st3)
+    c3_tflops = fl3 * st3["n_points"] / (c3_mine * 1e-3) / 1e12
+    h3 = [torch.empty((8, nx3, ny3, nz3), dtype=torch.float32).pin_memory() for _ in range(4)]
+    h3np = [t.numpy() for t in h3]
+
+    def c3_e2e():
+        p = ceg.ProbeSystem(None, None, inputs=inp3, device=dev)
+        ceg._lib.grid_build(p.handle, gs3, a3, b3, lam_v, thr_v, lam_c, thr_c, h3np, None)
+        p.close()
+    c3_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        c3_e2e()
+    barrier()
+    c3_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 5
+    pts3 = nx3 * ny3 * nz3
+    ps3.close()
+    del d3, h3, h3np
+
+    # ================= C5 (BASELINE configs[4]): 5000 atoms, 502^3 x 2 grids, then the 10^9-query sweep ========
+    c5 = None
+    if not args.no_c5:
+        inp5, cs5, _ = wl.synthetic_inputs("mof", 0.10, ("C_ch4",), True)
+        nx5, ny5, nz5 = cs5.nodes
+        sl5 = slabs(nx5, world)
+        a5, b5 = sl5[rank]
+        gs5 = ceg._lib.make_gridspec(cs5)
+        ps5 = ceg.ProbeSystem(None, None, inputs=inp5, device=dev)
+        d5 = [torch.empty((8, b5 - a5, ny5, nz5), dtype=torch.float32, device="cuda") for _ in range(2)]
+        c5_mine, c5_ms, c5_launches = timed_build(ps5, gs5, a5, b5, [t.data_ptr() for t in d5], 2, 1)
+        st5 = ceg._lib.probe_last_stats(ps5.handle)
+        fl5, nin5 = flops_per_point(inp5, st5)
+        c5_tflops = fl5 * st5["n_points"] / (c5_mine * 1e-3) / 1e12
+        ps5.close()
+        barrier()
+        t0 = time.perf_counter()
+        grids5 = []
+        for g, prec in enumerate((np.inf, 1e-6)):
+            full = gather_full(d5[g], sl5, (8, nx5, ny5, nz5))
+            grids5.append(ceg.EnergyGrid.from_device(cs5, inp5.supercell, prec, full.data_ptr(), device=dev))
+            del full
+        barrier()
+        c5_handoff_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        del d5
+        q0, q1 = slabs(N_SWEEP, world)[rank]
+        for eg in grids5:
+            ceg.interpolate_sweep(eg, 10 ** 6, 4)
+        barrier()
+        t0 = time.perf_counter()
+        res5 = [ceg.interpolate_sweep(eg, q1 - q0, 4, first=q0, n_keep=1000 if rank == 0 else 0) for eg in grids5]
+        barrier()
+        c5_sweep_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        c5_kernel_ms = max_over_ranks(sum(r["kernel_ms"] for r in res5))
+        sums = [sum_over_ranks(r["sum"]) for r in res5]
+        nblk = sum_over_ranks(float(res5[0]["n_blocked"]))
+        mins = [min_over_ranks(r["min"]) for r in res5]
+        if rank == 0:
+            pos = wl.random_positions(cs5.cell.mat, 1000, 4)
+            assert np.array_equal(ceg.interpolate_grid(grids5[0], pos), res5[0]["keep"])
+        for eg in grids5:
+            eg.close()
+        pts5 = nx5 * ny5 * nz5
+        c5 = {"workload": WORKLOAD_C5,
+              "build": {"value": pts5 / (c5_ms * 1e-3), "unit": "grid points/s", "ms_per_step": c5_ms, "steps": 2,
+                        "roofline": {"bound": "fp64", "achieved": c5_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                                     "frac": c5_tflops / fp64_peak if fp64_peak else None,
+                                     "algorithmic_flop_per_point": fl5, "pairs_in_cutoff_per_point": nin5,
+                                     "kernel": "grid_build_tiled_kernel<256,1,true,true>"},
+                        "gpu_launches": int(c5_launches)},
+              "handoff_ms": c5_handoff_ms,
+              "handoff_note": "all-gather of the 8.1 GB grid pair over NVLink + ceg_grid_upload_dev on every GPU (parse_grid on the device)",
+              "sweep": {"value": 2 * N_SWEEP / (c5_sweep_ms * 1e-3), "unit": "interpolations/s", "ms": c5_sweep_ms,
+                        "kernel_ms_max_over_ranks": c5_kernel_ms, "queries": N_SWEEP, "grids": 2,
+                        "roofline": {"bound": "hbm", "achieved": 2 * (q1 - q0) * 264.0 / (c5_kernel_ms * 1e-3) / 1e9 if c5_kernel_ms else None,
+                                     "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": 2 * (q1 - q0) * 264.0 / (c5_kernel_ms * 1e-3) / 1e9 / hbm_peak if c5_kernel_ms else None,
+                                     "algorithmic_bytes_per_query": 264,
+                                     "note": "positions generated and energies reduced on the device: 256 B stencil + 8 B; a 4 GB "
+                                             "grid is far beyond the L2, the gather runs at the memory system's random-sector rate"},
+                        "sum_vdw_K": sums[0], "sum_coulomb": sums[1], "min_vdw_K": mins[0], "blocked": int(nblk)},
+              "e2e": {"value": pts5 / ((c5_ms + c5_handoff_ms) * 1e-3), "unit": "grid points/s",
+                      "note": "grid pair built, gathered and interpolable on every GPU (build + hand-off)",
+                      "h2d_bytes_per_step": int(inp5.positions.nbytes + inp5.charges.nbytes + inp5.types.nbytes),
+                      "d2h_bytes_per_step": 0}}
+
+    # ================= guest-guest pair energies (energy.jl:397-427), rank 0 =============================
+    guest = None
+    if rank == 0:
+        guest = bench_guest(ceg, wl, dev)
 
     # ================= CPU baseline (rank 0, N = 1 only): the oracle on the host cores ===============
     cpu = None
@@ -358,56 +647,93 @@ def run_product(args):
             "ms_per_step": build_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "real CHA_1.4_3b4eeb96 framework fixture (flattened, tests/golden/cha_na.npz); "
                                      "synthetic query positions",
-            "config": {"workload": WORKLOAD_BUILD, "parallelism": f"x-slab x{world}", "cpus_bound_per_rank": local_cpus,
-                       "l2": "no L2 flush: inputs (<1 MB image list) are re-read by every tile by design; each step "
-                             "writes 1.8 GB of output (> 126 MB L2)"},
+            "config": {"workload": WORKLOAD_BUILD},
+            "parallelism": f"x-slab x{world}", "cpus_bound_per_rank": local_cpus, "host": host_info(),
+            "l2": "no L2 flush: inputs (<1 MB image list) are re-read by every tile by design; each step writes 1.8 GB of "
+                  "output (> 126 MB L2)",
             "e2e": {"value": e2e_value, "unit": "grid points/s", "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_total),
-                    "ms_per_step": e2e_ms, "note": "ceg_probe_create + ceg_grid_build into pinned host arrays + free"},
+                    "ms_per_step": e2e_ms, "note": "ceg_probe_create + ceg_grid_build into pinned host arrays + free",
+                    "breakdown_ms": breakdown},
+            "e2e_device": {"value": total_points / (dr_ms * 1e-3), "unit": "grid points/s", "ms_per_step": dr_ms,
+                           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                           "replicas_identical": bool(chk_same),
+                           "note": "per step: ceg_grid_build_dev of this rank's x-slab, all-gather of both grids over NVLink "
+                                   "(NCCL), ceg_grid_upload_dev on every GPU -> the VdW + Coulomb grid pair is resident and "
+                                   "interpolable on every GPU (the reference: .grid files, raspa.jl:430-438)"},
             "roofline": {"bound": "fp64", "achieved": my_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": my_tflops / fp64_peak if fp64_peak else None,
-                         # ncu --set full, C4 main launch (profiles/r01_ncu_build_v6_final.csv): 13.05 MB read +
-                         # 1781.69 MB written for 324x306x284 points = 63.74 B per point (64 B algorithmic)
-                         "traffic": 63.74 * stats["n_points"], "traffic_unit": "bytes per step (this rank), from the ncu capture",
+                         "traffic": tr_b * stats["n_points"] if tr_b else None, "traffic_source": tr_b_src,
+                         "traffic_unit": "DRAM bytes per step (this rank)",
                          "peak_source": "ceg_measure_fp64_peak (DFMA chains with uniform operands, this run); nominal 37.2",
                          "peak_register_operands": fp64_peak_regops,
                          "frac_of_register_operand_peak": my_tflops / fp64_peak_regops if fp64_peak_regops else None,
                          "algorithmic_flop_per_point": fl_pp, "pairs_in_cutoff_per_point": n_in_pp,
                          "pairs_tested_per_point": stats["pairs_tested"] / max(1, stats["n_points"]),
-                         "kernel": "grid_build_tiled_kernel<256,1,true,true>", "kernel_ms": my_ms},
+                         "kernel": "grid_build_tiled_kernel<256,1,true,true>", "kernel_ms": my_ms,
+                         "registers": build_regs},
             "gpu_launches": int(build_launches),
             "clocks": clocks,
             "c1": {"workload": "C1: same framework, 0.15 Å (218x204x190 = 8,449,680 points), VdW + Coulomb grids, 1 GPU",
                    "kernel_ms": c1_kernel_ms, "e2e_ms_pinned_host": c1_e2e_ms,
                    "points_per_s_kernel": 8449680 / (c1_kernel_ms * 1e-3)},
             "interp": {"metric": "tricubic interpolations/sec", "value": interp_value, "unit": "interpolations/s",
-                       "ms_per_step": interp_ms, "steps": KI,
-                       "config": {"workload": WORKLOAD_INTERP, "parallelism": f"queries x{world}",
-                                  "l2": "grids 2 x 270 MB + 240 MB of positions exceed the 126 MB L2; no flush"},
+                       "ms_per_step": best_ms, "steps": KI,
+                       "config": {"workload": WORKLOAD_INTERP},
+                       "parallelism": f"queries x{world}",
+                       "l2": "grids 2 x 270 MB (pair records: 540 MB) + 240 MB of positions exceed the 126 MB L2; no flush",
                        "e2e": {"value": 2 * N_QUERIES / (interp_e2e_ms * 1e-3), "unit": "interpolations/s",
                                "h2d_bytes_per_step": int(N_QUERIES * 24), "d2h_bytes_per_step": int(2 * N_QUERIES * 8),
-                               "note": "ceg_interpolate_multi: positions uploaded once for both grids, chunked on two streams",
+                               "note": ("ceg_interpolate_pair" if use_pair else "ceg_interpolate_multi") +
+                                       ": host positions in, both grids' energies out, chunked on two streams",
                                "ms_per_step": interp_e2e_ms},
-                       "roofline": {"bound": "hbm", "achieved": interp_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                    "frac": interp_gbs / hbm_peak, "peak_source": hbm_src,
-                                    # ncu --set full (profiles/r01_ncu_interp_v4_block.csv): 3.903 GB read + 0.121 GB
-                                    # written per launch of 10^7 queries = 402 B per query (288 B algorithmic)
-                                    "traffic": 402.4 * nq, "traffic_unit": "bytes per launch (this rank), from the ncu capture",
-                                    "algorithmic_bytes_per_query": 288, "kernel": "interpolate_kernel<BLOCK>"},
+                       "roofline": ({"bound": "hbm", "achieved": pair_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": pair_gbs / hbm_peak, "peak_source": hbm_src,
+                                     "traffic": tr_i * nq if tr_i else None, "traffic_source": tr_i_src,
+                                     "traffic_unit": "DRAM bytes per launch (this rank)",
+                                     "algorithmic_bytes_per_query": 552,
+                                     "algorithmic_note": "one launch = both interpolations of a query: 8 nodes x 64 B {VdW, Coulomb} "
+                                                         "records + 24 B position + 16 B of results (two separate lookups: 2 x 288 B)",
+                                     "kernel": "interpolate_pair_kernel", "registers": pair_regs} if use_pair else
+                                    {"bound": "hbm", "achieved": sep_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": sep_gbs / hbm_peak, "peak_source": hbm_src,
+                                     "traffic": tr_i * nq if tr_i else None, "traffic_source": tr_i_src,
+                                     "traffic_unit": "DRAM bytes per launch of 10^7/N queries on one grid (this rank)",
+                                     "algorithmic_bytes_per_query": 288, "kernel": "interpolate_kernel<BLOCK>", "registers": sep_regs}),
+                       "separate_kernels": {"value": 2 * N_QUERIES / (sep_ms * 1e-3), "ms_per_step": sep_ms,
+                                            "achieved_gbs": sep_gbs, "frac": sep_gbs / hbm_peak,
+                                            "algorithmic_bytes_per_query": 288, "kernel": "interpolate_kernel<BLOCK> x 2"},
+                       "fused_pair_kernel": {"value": 2 * N_QUERIES / (pair_ms * 1e-3), "ms_per_step": pair_ms,
+                                             "achieved_gbs": pair_gbs, "frac": pair_gbs / hbm_peak,
+                                             "algorithmic_bytes_per_query": 552, "kernel": "interpolate_pair_kernel",
+                                             "footprint_bytes": int(2 * 8 * 4 * nx1 * ny1 * nz1)},
                        "gpu_launches": int(interp_launches), "clocks": clocks2,
                        "blocked_fraction": blocked_fraction, "checksum_K": checksum,
                        "cpu_baseline": cpu_i},
             "ewald": {"metric": "reciprocal-space Ewald placements/sec (one Na+ per placement)",
                       "value": n_rec * world / (rec_ms * 1e-3), "unit": "placements/s", "ms_per_step": rec_ms, "steps": KI,
                       "config": {"workload": f"{N_RECIP} random Na+ placements in the C1 cell, k-space (8,8,8), {n_k} k-vectors "
-                                             "(compute_ewald, ewald.jl:555-577)", "parallelism": f"placements x{world}"},
+                                             "(compute_ewald, ewald.jl:555-577)"},
                       "roofline": {"bound": "fp64", "achieved": 15.0 * n_k * n_rec / (rec_ms * 1e-3) / 1e12, "peak": fp64_peak,
                                    "unit": "TFLOP/s", "frac": 15.0 * n_k * n_rec / (rec_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                                    "algorithmic_flop_per_atom_k": 15, "kernel": "reciprocal_rows_kernel<1>"},
                       "energy_points_e2e": {"value": n_rec * world / (ep_ms * 1e-3), "unit": "placements/s", "ms_per_step": ep_ms,
                                             "note": "energy_points (grids.jl:311-327 batched): host positions in, host (vdw, coulomb) "
-                                                    "out; 2 interpolations + reciprocal term per placement",
+                                                    "out; fused pair interpolation + reciprocal term per placement",
                                             "h2d_bytes_per_step": int(n_rec * world * 24), "d2h_bytes_per_step": int(n_rec * world * 16)}},
+            "c3": {"workload": WORKLOAD_C3, "value": 4 * pts3 / (c3_ms * 1e-3), "unit": "grid points/s (x 4 grids)",
+                   "ms_per_step": c3_ms, "points_per_s_per_pass": pts3 / (c3_ms * 1e-3),
+                   "e2e": {"value": 4 * pts3 / (c3_e2e_ms * 1e-3), "unit": "grid points/s (x 4 grids)", "ms_per_step": c3_e2e_ms,
+                           "h2d_bytes_per_step": int(inp3.positions.nbytes + inp3.charges.nbytes + inp3.types.nbytes + inp3.table.nbytes),
+                           "d2h_bytes_per_step": int(4 * 8 * pts3 * 4),
+                           "note": "ceg_probe_create + ceg_grid_build of the 4 grids into pinned host arrays + free"},
+                   "roofline": {"bound": "fp64", "achieved": c3_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                                "frac": c3_tflops / fp64_peak if fp64_peak else None, "algorithmic_flop_per_point": fl3,
+                                "pairs_in_cutoff_per_point": nin3, "kernel": "grid_build_tiled_kernel<256,3,true,true>"},
+                   "gpu_launches": int(c3_launches)},
+            "c5": c5,
+            "latency_us": latency,
+            "guest": guest,
             "cpu_baseline": cpu,
             "gpu_launches_total": int(total_launches),
             "device": ceg._lib.device_info(dev),
@@ -415,18 +741,46 @@ def run_product(args):
         if args.headline == "interp":
             # same measurements, the interpolation half promoted to the top-level keys
             top = dict(line["interp"])
-            build = {k: line[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "roofline", "gpu_launches",
-                                          "clocks", "cpu_baseline", "c1")}
+            build = {k: line[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "e2e_device", "roofline",
+                                          "gpu_launches", "clocks", "cpu_baseline", "c1")}
             line = {"metric": top.pop("metric"), "value": top.pop("value"), "unit": top.pop("unit"), "n_gpus": world,
                     "steps": top.pop("steps"), "warmup": W, "ms_per_step": top.pop("ms_per_step"), "higher_is_better": True,
                     "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": line["data"], **top,
-                    "build": build, "ewald": line["ewald"], "gpu_launches_total": line["gpu_launches_total"],
-                    "device": line["device"]}
+                    "build": build, "ewald": line["ewald"], "c3": line["c3"], "c5": line["c5"],
+                    "latency_us": line["latency_us"], "guest": line["guest"],
+                    "gpu_launches_total": line["gpu_launches_total"], "device": line["device"], "host": line["host"]}
         emit(line)
-    eg_v.close()
-    eg_c.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_guest(ceg, wl, dev):
+    """single_contribution_vdw for 10^5 trial CO2 placements against 10^3 CO2 guests (3000 atoms) in the C3 cell."""
+    import torch
+    fw, ff, _ = wl.mfi_shaped()
+    names = ["O_co2", "C_co2"]
+    tab = ceg.pair_energy_table(ff, names)
+    mol = np.array([[0.0, 0.0, 1.149], [0.0, 0.0, 0.0], [0.0, 0.0, -1.149]])
+    idx = np.array([0, 1, 0], dtype=np.int32)
+    n_guests, n_trials = 1000, 100_000
+    cell = np.asarray(fw.mat) * np.array([2.0, 2.0, 2.0])[None, :]
+    envc = wl.random_positions(cell, n_guests, 3)
+    env_pos = (envc[:, None, :] + mol[None, :, :]).reshape(-1, 3)
+    env = ceg.GuestEnvironment(cell, 12.0, tab, env_pos, np.tile(idx, n_guests), np.repeat(np.arange(n_guests, dtype=np.int32), 3))
+    trials = wl.random_positions(cell, n_trials, 11)[:, None, :] + mol[None, :, :]
+    ceg.single_contribution_vdw(env, idx, trials[:1000], -1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        e = ceg.single_contribution_vdw(env, idx, trials, -1)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    pairs = n_trials * 3 * 3 * n_guests
+    return {"workload": "10^5 trial CO2 placements x 10^3 CO2 guests (3000 environment atoms), LJ + real-space Ewald rules, 12 Å cutoff",
+            "ms_per_step": ms, "pair_tests_per_s": pairs / (ms * 1e-3), "placements_per_s": n_trials / (ms * 1e-3),
+            "checksum_K": float(np.where(np.isfinite(e), e, 0.0).sum()),
+            "note": "host positions in, host energies out (ceg_guest_env_energy); every (trial atom, guest atom) pair goes through "
+                    "the literal wrap-only minimum image, ~43 FP64 operations"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -436,6 +790,7 @@ def cpu_baseline(inp, cset4, cset1, gK, budget_s=20.0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     orc.build()
+    cores = orc.use_all_cores()
     nx, ny, nz = cset4.nodes
     t0 = time.perf_counter()
     orc.grid_build(inp, cset4, nx // 2, nx // 2 + 1, 1, want_f32=True)
@@ -446,8 +801,7 @@ def cpu_baseline(inp, cset4, cset1, gK, budget_s=20.0):
     orc.grid_build(inp, cset4, 0, nx, stride, want_f32=True)
     dt = time.perf_counter() - t0
     planes = len(range(0, nx, stride))
-    cores = orc.num_threads()
-    cpu = {"value": planes * ny * nz / dt, "unit": "grid points/s", "cores": cores, "kind": "port",
+    cpu = {"value": planes * ny * nz / dt, "unit": "grid points/s", "cores": cores, "kind": "port", **host_info(),
            "sample": f"{planes} of {nx} x planes (every {stride}th) of the same C4 grid, VdW + Coulomb passes, "
                      f"{dt:.1f} s on {cores} OpenMP threads"}
     cpu_i = None
@@ -474,6 +828,8 @@ def run_reference(args):
     import oracle as orc
     from ceg_b200 import workloads as wl
     orc.build()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: size the team from the affinity mask instead
+    cores = orc.use_all_cores()
     inp, cset1, _ = wl.load_fixture("cha_na")
     cset4 = wl.respace(cset1, 0.10)
     nx, ny, nz = cset4.nodes
@@ -493,15 +849,15 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     pts = sum(len(range(k % stride, nx, stride)) for k in range(K)) * ny * nz
     value = pts / dt
-    cores = orc.num_threads()
     sample = (f"each step = {planes} of {nx} x planes (every {stride}th) of the C4 grid, VdW + Coulomb passes, "
               f"{cores} OpenMP threads")
     line = {"impl": "reference", "metric": "grid points/sec (LJ+Ewald FP64)", "value": value, "unit": "grid points/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "real CHA_1.4_3b4eeb96 framework fixture (flattened, tests/golden/cha_na.npz)",
-            "config": {"workload": WORKLOAD_BUILD, "parallelism": f"OpenMP x{cores}"},
-            "cpu_baseline": {"value": value, "unit": "grid points/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD_BUILD},
+            "parallelism": f"OpenMP x{cores}", "host": host_info(),
+            "cpu_baseline": {"value": value, "unit": "grid points/s", "cores": cores, "kind": "port", "sample": sample, **host_info()},
             "e2e": {"value": value, "unit": "grid points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = CrystalEnergyGrids.jl CPU algorithm restated in C/OpenMP (oracle/ceg_oracle.c); "
                     "Julia is not installed in this image"}
@@ -529,6 +885,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ceg", choices=["ceg", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 block (2 x 4 GB grids + 10^9-query sweep)")
     ap.add_argument("--headline", default="build", choices=["build", "interp"],
                     help="which half of BASELINE.json's metric the top-level keys carry: grid construction on C4 (default) "
                          "or tricubic interpolation on C2 (configs[1]); the other half is always in the same line")

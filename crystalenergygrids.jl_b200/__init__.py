@@ -19,12 +19,13 @@ from .ewald import (EwaldContext, EwaldFramework, EwaldKspace, adsorbate_sums, b
                     ewald_context, ewald_parameters, framework_sites, initialize_ewald)
 from .forcefields import (ForceField, InteractionRule, InteractionRuleSum, Kind, Mixing, UndefinedInteractionError,
                           get_atom_name, needsvdwgrid, pair_dtype, pair_table)
-from .grids import (CrystalEnergySetup, EnergyGrid, build_grids, coulomb_scaling, create_grid_coulomb,
-                    create_grid_vdw, energy_grid, energy_point, energy_points, interpolate_grid, interpolate_sweep, parse_grid,
-                    vdw_scaling, write_grid)
+from .grids import (CrystalEnergySetup, EnergyGrid, build_grids, build_grids_device, coulomb_scaling, create_grid_coulomb,
+                    create_grid_vdw, energy_grid, energy_point, energy_points, interpolate_grid, interpolate_pair,
+                    interpolate_sweep, parse_grid, vdw_scaling, write_grid)
+from .montecarlo import MonteCarloGrids, framework_interactions, setup_montecarlo
 from .probes import (ProbeInputs, ProbeSystem, compute_derivatives_ewald, compute_derivatives_vdw, probe_inputs,
                      replicate_framework)
-from .raspa import (RASPASystem, getdir_RASPA, grid_locations, load_framework_RASPA, load_molecule_RASPA,
+from .raspa import (RASPASystem, getdir_RASPA, grid_locations, hash_forcefield, load_framework_RASPA, load_molecule_RASPA,
                     parse_forcefield_RASPA, parse_pseudoatoms_RASPA, read_cif_P1, retrieve_or_create_grid,
                     setdir_RASPA, setup_RASPA)
 

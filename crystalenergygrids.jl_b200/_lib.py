@@ -44,6 +44,9 @@ EXPORTS = [
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_upload_dev", "ceg_grid_free",
     "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_interpolate_sweep", "ceg_energy_lattice", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
     "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_guest_env_create", "ceg_guest_env_free", "ceg_guest_env_update", "ceg_guest_env_energy", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
+    "ceg_probe_last_timing", "ceg_grid_gather", "ceg_kernel_registers", "ceg_device_malloc", "ceg_device_free",
+    "ceg_device_download", "ceg_device_synchronize", "ceg_grid_pair_create", "ceg_grid_pair_free", "ceg_interpolate_pair",
+    "ceg_interpolate_pair_dev",
 ]
 
 _lib = None
@@ -225,6 +228,50 @@ def probe_last_stats(h) -> dict:
     return {"n_points": a.value, "pairs_tested": b.value, "pairs_in_cutoff": c.value}
 
 
+def probe_last_timing(h) -> dict:
+    """Phases of the last ceg_grid_build on this handle (ms)."""
+    t = (C.c_double * 4)()
+    _check(load().ceg_probe_last_timing(h, t))
+    return {"image_list_host_ms": t[0], "kernel_span_ms": t[1], "copy_tail_ms": t[2], "call_ms": t[3]}
+
+
+def kernel_registers(which: int, device: int = 0) -> int:
+    r = C.c_int32(0)
+    _check(load().ceg_kernel_registers(C.c_int32(device), C.c_int32(which), C.byref(r)))
+    return r.value
+
+
+# ---- plain device buffers (chaining the _dev entry points from the host layer) ---------------------------
+def device_malloc(device: int, nbytes: int) -> int:
+    p = C.c_void_p()
+    _check(load().ceg_device_malloc(C.c_int32(device), C.c_int64(int(nbytes)), C.byref(p)))
+    return int(p.value)
+
+
+def device_free(ptr: int):
+    _check(load().ceg_device_free(C.c_void_p(int(ptr))))
+
+
+def device_download(device: int, ptr: int, out: np.ndarray):
+    assert out.flags.c_contiguous
+    _check(load().ceg_device_download(C.c_int32(device), C.c_void_p(int(ptr)), C.c_int64(out.nbytes), C.c_void_p(out.ctypes.data)))
+
+
+def device_synchronize(device: int):
+    _check(load().ceg_device_synchronize(C.c_int32(device)))
+
+
+def grid_gather(devices, d_slabs, i0s, i1s, gs: ceg_gridspec_t, dst_device: int, d_full: int):
+    """x-slabs [8][i1-i0][ny][nz] on several devices of this process -> full [8][nx][ny][nz] grid on dst_device."""
+    n = len(devices)
+    dv = np.ascontiguousarray(devices, dtype=np.int32)
+    a = np.ascontiguousarray(i0s, dtype=np.int32)
+    b = np.ascontiguousarray(i1s, dtype=np.int32)
+    ptrs = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in d_slabs])
+    _check(load().ceg_grid_gather(C.c_int32(n), _p(dv, C.c_int32), ptrs, _p(a, C.c_int32), _p(b, C.c_int32), C.byref(gs),
+                                  C.c_int32(dst_device), C.c_void_p(int(d_full))))
+
+
 # ---- interpolation -----------------------------------------------------------------------------
 def grid_upload(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, grid: np.ndarray, is_vdw: bool):
     assert grid.dtype == np.float32 and grid.flags.c_contiguous
@@ -287,6 +334,32 @@ def interpolate_sweep(h, first: int, n: int, seed: int, mat, n_keep: int = 0):
                                         C.byref(s), C.byref(mn), C.byref(nb), C.c_int64(n_keep),
                                         _p(keep, C.c_double) if n_keep else None, C.byref(ms)))
     return {"sum": s.value, "min": mn.value, "n_blocked": nb.value, "keep": keep, "kernel_ms": ms.value}
+
+
+def grid_pair_create(vdw_handle, coulomb_handle):
+    h = C.c_void_p()
+    _check(load().ceg_grid_pair_create(vdw_handle, coulomb_handle, C.byref(h)))
+    return h
+
+
+def grid_pair_free(h):
+    _check(load().ceg_grid_pair_free(h))
+
+
+def interpolate_pair(h, xyz, outs=None) -> np.ndarray:
+    """(2, n): VdW and Coulomb grid values at the same positions through the fused pair records."""
+    xyz = _f64(xyz, (-1, 3))
+    n = xyz.shape[0]
+    if outs is None:
+        outs = np.empty((2, n), dtype=np.float64)
+    assert outs.shape == (2, n) and outs.dtype == np.float64 and outs.flags.c_contiguous
+    _check(load().ceg_interpolate_pair(h, C.c_int64(n), _p(xyz, C.c_double), _p(outs[0], C.c_double), _p(outs[1], C.c_double)))
+    return outs
+
+
+def interpolate_pair_dev(h, n: int, d_xyz: int, d_out_vdw: int, d_out_coul: int, stream: int = 0):
+    _check(load().ceg_interpolate_pair_dev(h, C.c_int64(n), C.c_void_p(int(d_xyz)), C.c_void_p(int(d_out_vdw)),
+                                           C.c_void_p(int(d_out_coul)), C.c_void_p(int(stream))))
 
 
 def interpolate_dev(h, n: int, d_xyz: int, d_out: int, stream: int = 0):
@@ -443,6 +516,33 @@ def energy_points(vdw_handles, coulomb, ewald, block, atomsidx, charges, xyz, en
                                     C.c_double(energy_net_charges), C.c_double(static_contribution),
                                     _p(out_v, C.c_double), _p(out_c, C.c_double)))
     return out_v, out_c
+
+
+def energy_points_prepared(vdw_handles, coulomb, ewald, block, atomsidx, charges, xyz, energy_net_charges, static_contribution):
+    """-> (call, out_vdw, out_coulomb): `call()` re-issues ceg_energy_points on the SAME argument buffers with no Python
+    marshalling — what a compiled host (the Julia shim's ccall) pays per call; used to time the library's latency path."""
+    atomsidx = np.ascontiguousarray(atomsidx, dtype=np.int32)
+    na = atomsidx.shape[0]
+    charges = _f64(charges, (na,))
+    xyz = _f64(xyz, (-1, na, 3))
+    n = xyz.shape[0]
+    nv = len(vdw_handles)
+    arr = (C.c_void_p * max(nv, 1))(*[h if h is not None else C.c_void_p(0) for h in vdw_handles])
+    out_v = np.empty(n, dtype=np.float64)
+    out_c = np.empty(n, dtype=np.float64)
+    f = load().ceg_energy_points
+    args = (C.c_int32(nv), arr, coulomb if coulomb is not None else C.c_void_p(0), ewald if ewald is not None else C.c_void_p(0),
+            block if block is not None else C.c_void_p(0), C.c_int64(n), C.c_int32(na), _p(atomsidx, C.c_int32),
+            _p(charges, C.c_double), _p(xyz, C.c_double), C.c_double(energy_net_charges), C.c_double(static_contribution),
+            _p(out_v, C.c_double), _p(out_c, C.c_double))
+    keep = (atomsidx, charges, xyz, arr)
+
+    def call():
+        rc = f(*args)
+        if rc:
+            _check(rc)
+        return keep and rc
+    return call, out_v, out_c
 
 
 def energy_lattice(vdw_handles, coulomb, ewald, block, nums, steps, rotpos, atomsidx, charges, energy_net_charges,

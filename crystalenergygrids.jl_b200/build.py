@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libceg_cuda.so")
 SOURCES = ["ceg_cuda.cu"]
-HEADERS = ["common.cuh", "grid_build.cuh", "interp.cuh", "ewald.cuh", "fastmath.cuh", "math_coeffs.cuh", "guest.cuh"]
+HEADERS = ["common.cuh", "grid_build.cuh", "interp.cuh", "ewald.cuh", "fastmath.cuh", "math_coeffs.cuh", "guest.cuh", "latency.cuh"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -1,6 +1,7 @@
 // libceg_cuda — C ABI implementation (include/ceg_cuda.h).  sm_100a only; no CPU fallback.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -12,6 +13,7 @@
 #include "grid_build.cuh"
 #include "guest.cuh"
 #include "interp.cuh"
+#include "latency.cuh"
 
 namespace ceg {
 
@@ -83,6 +85,10 @@ void pool_trim() {
     cudaSetDevice(cur);
 }
 
+namespace {
+std::mutex g_user_mu;
+std::vector<PoolEntry> g_user_bufs;     // buffers handed out by ceg_device_malloc
+}  // namespace
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -175,6 +181,7 @@ struct ceg_probe_s {
     cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr}, ev_free[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_time[3] = {nullptr, nullptr, nullptr};   // first launch, last launch done, last copy done
     double last_timing[4] = {0, 0, 0, 0};                   // image list (host) ms, kernel span ms, copy tail ms, whole call ms
+    double list_ms = 0.0;                                   // host time spent (re)building image lists in the current call
     // last slab whose image list was too long to be scanned by every tile: remembered so that repeated builds of
     // the same slab go straight to its x windows (list_windows)
     int split_i0 = -1, split_i1 = -1, split_dims[3] = {0, 0, 0};
@@ -192,15 +199,31 @@ struct ceg_probe_s {
     }
 };
 
+struct ceg_gridpair_s;
 struct ceg_grid_s {
     int device = 0;
     std::mutex mu;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // ping-pong pair for the pipelined host path
     GridDev g;
     DevBuf d_nodes, d_xyz[2], d_out[2];
+    ceg_gridpair_s* pair = nullptr;                     // fused {this VdW grid, a Coulomb grid} records (ceg_grid_pair_create)
     ~ceg_grid_s() {
         if (stream) cudaStreamDestroy(stream);
         if (stream2) cudaStreamDestroy(stream2);
+    }
+};
+
+struct ceg_gridpair_s {
+    int device = 0;
+    std::mutex mu;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    PairGridDev g;
+    ceg_grid_s* vdw = nullptr;
+    ceg_grid_s* coul = nullptr;
+    DevBuf d_nodes, d_xyz[2], d_out[2];
+    ~ceg_gridpair_s() {
+        if (stream) release_stream(stream);
+        if (stream2) release_stream(stream2);
     }
 };
 
@@ -733,6 +756,7 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     for (int d = 1; d < 3; d++) { lo[d] = gs->shift[d]; hi[d] = gs->shift[d] + gs->size[d]; }
     double key[8] = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], cutoff, reach};
     if (!h->ext_valid || memcmp(key, h->ext_key, sizeof key) != 0 || h->ext_key_planes[0] != i0 || h->ext_key_planes[1] != i1) {
+        const auto t_list0 = std::chrono::steady_clock::now();
         std::vector<ExtAtom> ext;
         std::vector<ExtMeta> meta;
         build_ext_list(h, lo, hi, reach + 1e-6, ext, meta);
@@ -761,6 +785,7 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
         h->ext_key_planes[0] = i0; h->ext_key_planes[1] = i1;
         h->ext_plane0 = i0; h->ext_planes = planes;
         h->ext_valid = true;
+        h->list_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_list0).count();
     }
     P.ext = h->d_ext.as<ExtAtom>();
     P.ext_meta = h->d_ext_meta.as<ExtMeta>();
@@ -802,9 +827,24 @@ static int list_windows(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i1
     return 0;
 }
 
+// argument checks shared by ceg_grid_build / ceg_grid_build_dev: nothing is dereferenced or sized before they pass
+static int check_build_args(const char* who, ceg_probe_h h, const ceg_gridspec_t* gs, int i0, int i1) {
+    if (!h) return fail(std::string(who) + ": null handle");
+    if (!gs) return fail(std::string(who) + ": null gridspec");
+    for (int d = 0; d < 3; d++)
+        if (gs->dims[d] < 1 || !(gs->size[d] > 0) || !std::isfinite(gs->size[d]) || !std::isfinite(gs->shift[d]) ||
+            !(gs->delta[d] > 0))
+            return fail(std::string(who) + ": bad grid spec");
+    if (i0 < 0 || i1 > gs->dims[0] + 1 || i0 >= i1) return fail(std::string(who) + ": bad x-slab range");
+    return 0;
+}
+
 extern "C" int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
                                   double thr_vdw, double lambda_coul, double thr_coul, float* const* d_out, void* stream) {
-    if (!h || !d_out) return fail("ceg_grid_build_dev: null argument");
+    if (check_build_args("ceg_grid_build_dev", h, gs, i0, i1)) return 1;
+    if (!d_out) return fail("ceg_grid_build_dev: null argument");
+    for (int g = 0; g < h->n_probes + h->want_coulomb; g++)
+        if (!d_out[g]) return fail("ceg_grid_build_dev: null output buffer");
     std::lock_guard<std::mutex> lk(h->mu);
     if (use_device(h->device)) return 1;
     std::vector<std::pair<int, int>> win;
@@ -825,10 +865,12 @@ extern "C" int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32
 
 extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
                               double thr_vdw, double lambda_coul, double thr_coul, float* const* out_f32, double* raw_f64) {
-    if (!h) return fail("ceg_grid_build: null handle");
+    if (check_build_args("ceg_grid_build", h, gs, i0, i1)) return 1;
     std::lock_guard<std::mutex> lk(h->mu);
     if (use_device(h->device)) return 1;
+    const auto t_call0 = std::chrono::steady_clock::now();
     std::vector<std::pair<int, int>> win;
+    h->list_ms = 0.0;
     if (list_windows(h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, win)) return 1;
     const int ng = h->n_probes + h->want_coulomb;
     const int64_t ny = gs->dims[1] + 1, nz = gs->dims[2] + 1, nx = gs->dims[0] + 1;
@@ -852,11 +894,15 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
     if (any_out) CEG_CK(h->d_out.reserve(sizeof(float) * 8 * chunk_slab * ng * RING));
     if (raw_f64) CEG_CK(h->d_raw.reserve(sizeof(double) * 8 * slab * ng));
     CEG_CK(cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), h->s_compute));
-    cudaEvent_t ev_done[RING], ev_free[RING];
-    for (int r = 0; r < RING; r++) {
-        CEG_CK(cudaEventCreateWithFlags(&ev_done[r], cudaEventDisableTiming));
-        CEG_CK(cudaEventCreateWithFlags(&ev_free[r], cudaEventDisableTiming));
+    static_assert(RING == 3, "ceg_probe_s caches three ring events");
+    for (int r = 0; r < RING; r++) {      // created once per handle
+        if (!h->ev_done[r]) CEG_CK(cudaEventCreateWithFlags(&h->ev_done[r], cudaEventDisableTiming));
+        if (!h->ev_free[r]) CEG_CK(cudaEventCreateWithFlags(&h->ev_free[r], cudaEventDisableTiming));
+        if (!h->ev_time[r]) CEG_CK(cudaEventCreate(&h->ev_time[r]));
     }
+    cudaEvent_t* ev_done = h->ev_done;
+    cudaEvent_t* ev_free = h->ev_free;
+    CEG_CK(cudaEventRecord(h->ev_time[0], h->s_compute));
     int rc = 0, c = 0;
     for (size_t wi = 0; wi < win.size() && !rc; wi++) {
     BuildParams P;   // image list of this window (prepare_build drains the device before replacing the list)
@@ -884,10 +930,11 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
             cudaStreamWaitEvent(h->s_copy, ev_done[slot], 0);
             for (int g = 0; g < ng && !rc; g++) {
                 if (!Q.out[g]) continue;
+                // one copy per channel run (a pitched 2-D copy is refused when only the runs, not the rows between them,
+                // are registered — what a multi-process driver does with its slab, sharding.slab_file_runs)
                 for (int ch = 0; ch < 8; ch++) {
-                    const float* src = Q.out[g] + (int64_t)ch * cslab;
-                    float* dst = out_f32[g] + (int64_t)ch * npts + (int64_t)a * plane;
-                    e = cudaMemcpyAsync(dst, src, sizeof(float) * cslab, cudaMemcpyDeviceToHost, h->s_copy);
+                    e = cudaMemcpyAsync(out_f32[g] + (int64_t)ch * npts + (int64_t)a * plane, Q.out[g] + (int64_t)ch * cslab,
+                                        sizeof(float) * cslab, cudaMemcpyDeviceToHost, h->s_copy);
                     if (e != cudaSuccess) { rc = fail_cuda(e, "cudaMemcpyAsync(D2H slab)", __FILE__, __LINE__); break; }
                 }
             }
@@ -895,14 +942,23 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
         }
     }
     }
+    cudaEventRecord(h->ev_time[1], h->s_compute);
+    cudaStreamWaitEvent(h->s_copy, h->ev_time[1], 0);
+    cudaEventRecord(h->ev_time[2], h->s_copy);
     cudaError_t e1 = cudaStreamSynchronize(h->s_compute);
     cudaError_t e2 = cudaStreamSynchronize(h->s_copy);
-    for (int r = 0; r < RING; r++) { cudaEventDestroy(ev_done[r]); cudaEventDestroy(ev_free[r]); }
     if (rc) return rc;
     if (e1 != cudaSuccess) return fail_cuda(e1, "grid build (compute stream)", __FILE__, __LINE__);
     if (e2 != cudaSuccess) return fail_cuda(e2, "grid build (copy stream)", __FILE__, __LINE__);
     if (raw_f64) CEG_CK(cudaMemcpy(raw_f64, h->d_raw.p, sizeof(double) * 8 * slab * ng, cudaMemcpyDeviceToHost));
     h->last_points = slab;
+    float k_ms = 0.f, t_ms = 0.f;
+    cudaEventElapsedTime(&k_ms, h->ev_time[0], h->ev_time[1]);
+    cudaEventElapsedTime(&t_ms, h->ev_time[1], h->ev_time[2]);
+    h->last_timing[0] = h->list_ms;
+    h->last_timing[1] = k_ms;
+    h->last_timing[2] = t_ms;
+    h->last_timing[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
     return 0;
 }
 
@@ -916,6 +972,116 @@ extern "C" int ceg_probe_last_stats(ceg_probe_h h, int64_t* n_points, int64_t* p
     if (pairs_tested) *pairs_tested = (int64_t)st[0];
     if (pairs_in_cutoff) *pairs_in_cutoff = (int64_t)st[1];
     return 0;
+}
+
+// Registers per thread of the library's main kernels as loaded on `device` (bench.py matches them against the ncu
+// captures under profiles/ before quoting a DRAM-traffic figure): 0 = grid_build_tiled_kernel<NT,1,true,true>,
+// 1 = interpolate_kernel<BLOCK>, 2 = interpolate_pair_kernel, 3 = reciprocal_rows_kernel<1>.
+extern "C" int ceg_kernel_registers(int32_t device, int32_t which, int32_t* regs) {
+    if (!regs) return fail("ceg_kernel_registers: null argument");
+    if (use_device(device)) return 1;
+    cudaFuncAttributes a;
+    cudaError_t e;
+    switch (which) {
+        case 0: e = cudaFuncGetAttributes(&a, grid_build_tiled_kernel<CEG_BUILD_NT, 1, true, true>); break;
+        case 1: e = cudaFuncGetAttributes(&a, interpolate_kernel<LAYOUT_BLOCK>); break;
+        case 2: e = cudaFuncGetAttributes(&a, interpolate_pair_kernel); break;
+        case 3: e = cudaFuncGetAttributes(&a, reciprocal_rows_kernel<1>); break;
+        default: return fail("ceg_kernel_registers: unknown kernel");
+    }
+    CEG_CK(e);
+    *regs = a.numRegs;
+    return 0;
+}
+
+// Plain device buffers for callers that chain _dev entry points without a CUDA runtime of their own (the host layer's
+// device-resident build -> gather -> upload hand-off); served from the library's allocation cache.
+extern "C" int ceg_device_malloc(int32_t device, int64_t bytes, void** out) {
+    if (!out || bytes <= 0) return fail("ceg_device_malloc: bad argument");
+    if (use_device(device)) return 1;
+    size_t got = 0;
+    void* p = pool_acquire((size_t)bytes, &got);
+    if (!p) {
+        cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); pool_trim(); e = cudaMalloc(&p, (size_t)bytes); }
+        CEG_CK(e);
+        got = (size_t)bytes;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_user_mu);
+        g_user_bufs.push_back({p, got, device});
+    }
+    *out = p;
+    return 0;
+}
+extern "C" int ceg_device_free(void* ptr) {
+    if (!ptr) return 0;
+    PoolEntry ent{nullptr, 0, 0};
+    {
+        std::lock_guard<std::mutex> lk(g_user_mu);
+        for (size_t i = 0; i < g_user_bufs.size(); i++)
+            if (g_user_bufs[i].p == ptr) { ent = g_user_bufs[i]; g_user_bufs.erase(g_user_bufs.begin() + i); break; }
+    }
+    if (!ent.p) return fail("ceg_device_free: not a ceg_device_malloc pointer");
+    if (use_device(ent.device)) return 1;
+    CEG_CK(cudaDeviceSynchronize());
+    pool_release(ent.p, ent.bytes);
+    return 0;
+}
+// device -> host copy of a ceg_device_malloc buffer (e.g. to write the `.grid` file of a grid that stays on the device)
+extern "C" int ceg_device_download(int32_t device, const void* d_src, int64_t bytes, void* host_dst) {
+    if (!d_src || !host_dst || bytes < 0) return fail("ceg_device_download: bad argument");
+    if (use_device(device)) return 1;
+    CEG_CK(cudaMemcpy(host_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int ceg_device_synchronize(int32_t device) {
+    if (use_device(device)) return 1;
+    CEG_CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int ceg_probe_last_timing(ceg_probe_h h, double* out4) {
+    if (!h || !out4) return fail("ceg_probe_last_timing: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (int i = 0; i < 4; i++) out4[i] = h->last_timing[i];
+    return 0;
+}
+
+// Gather x-slabs that live on several devices of this process into one full grid on `dst_device` (peer copies over
+// NVLink; the reference exchanges them through `.grid` files, raspa.jl:430-438).  Part p holds planes [i0[p], i1[p])
+// as [8][i1-i0][ny][nz] floats on devices[p]; d_full is [8][nx][ny][nz] on dst_device.
+extern "C" int ceg_grid_gather(int32_t n_parts, const int32_t* devices, const float* const* d_slabs, const int32_t* i0,
+                               const int32_t* i1, const ceg_gridspec_t* gs, int32_t dst_device, float* d_full) {
+    if (n_parts <= 0 || !devices || !d_slabs || !i0 || !i1 || !gs || !d_full) return fail("ceg_grid_gather: null argument");
+    const int64_t nx = gs->dims[0] + 1, plane = (int64_t)(gs->dims[1] + 1) * (gs->dims[2] + 1), npts = nx * plane;
+    for (int p = 0; p < n_parts; p++)
+        if (!d_slabs[p] || i0[p] < 0 || i1[p] > nx || i0[p] >= i1[p]) return fail("ceg_grid_gather: bad part");
+    if (use_device(dst_device)) return 1;
+    cudaStream_t s;
+    CEG_CK(acquire_stream(&s));
+    int rc = 0;
+    for (int p = 0; p < n_parts && !rc; p++) {
+        const int64_t cslab = (int64_t)(i1[p] - i0[p]) * plane;
+        if (devices[p] != dst_device) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, dst_device, devices[p]);
+            if (can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[p], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { rc = fail_cuda(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__); break; }
+                cudaGetLastError();
+            }
+        }
+        for (int c = 0; c < 8 && !rc; c++) {   // (without peer access the runtime stages the copy through the host)
+            cudaError_t e = cudaMemcpyPeerAsync(d_full + (int64_t)c * npts + (int64_t)i0[p] * plane, dst_device,
+                                                d_slabs[p] + (int64_t)c * cslab, devices[p], sizeof(float) * cslab, s);
+            if (e != cudaSuccess) rc = fail_cuda(e, "cudaMemcpyPeerAsync", __FILE__, __LINE__);
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    release_stream(s);
+    if (!rc && e != cudaSuccess) rc = fail_cuda(e, "ceg_grid_gather", __FILE__, __LINE__);
+    return rc;
 }
 
 // ================================================================================================
@@ -1133,6 +1299,95 @@ extern "C" int ceg_interpolate_multi(int32_t n_grids, const ceg_grid_h* grids, i
     }
     if (n == 0) return 0;
     return interpolate_pipelined(n_grids, grids, n, xyz, outs);
+}
+
+// ---- fused (VdW, Coulomb) pair grids --------------------------------------------------------------------------
+extern "C" int ceg_grid_pair_create(ceg_grid_h vdw, ceg_grid_h coulomb, ceg_gridpair_h* out) {
+    if (!vdw || !coulomb || !out) return fail("ceg_grid_pair_create: null argument");
+    if (vdw->device != coulomb->device) return fail("ceg_grid_pair_create: grids live on different devices");
+    if (!vdw->g.is_vdw || coulomb->g.is_vdw) return fail("ceg_grid_pair_create: expects (VdW grid, Coulomb grid)");
+    for (ceg_grid_s* g : {vdw, coulomb})
+        if (g->g.layout != LAYOUT_NODE && g->g.layout != LAYOUT_BLOCK)
+            return fail("ceg_grid_pair_create: grids must use the node or brick layout");
+    if (memcmp(&vdw->g.gs, &coulomb->g.gs, sizeof(GridSpecDev)) != 0 || memcmp(&vdw->g.uc, &coulomb->g.uc, sizeof(CellDev)) != 0)
+        return fail("ceg_grid_pair_create: the two grids do not share one GridCoordinatesSetup");
+    if (use_device(vdw->device)) return 1;
+    std::unique_ptr<ceg_gridpair_s> h(new ceg_gridpair_s);
+    h->device = vdw->device;
+    h->g.uc = vdw->g.uc;
+    h->g.gs = vdw->g.gs;
+    h->vdw = vdw;
+    h->coul = coulomb;
+    const int nx = vdw->g.gs.n[0], ny = vdw->g.gs.n[1], nz = vdw->g.gs.n[2];
+    const size_t bricks = (size_t)((nx + 1) / 2) * ((ny + 1) / 2) * ((nz + 1) / 2);
+    CEG_CK(acquire_stream(&h->stream));
+    CEG_CK(h->d_nodes.reserve(sizeof(Rec8) * 16 * bricks));
+    pair_records_kernel<<<sm_count_here() * 32, 256, 0, h->stream>>>(reinterpret_cast<const Rec8*>(vdw->g.data), vdw->g.layout,
+                                                                     reinterpret_cast<const Rec8*>(coulomb->g.data),
+                                                                     coulomb->g.layout, h->d_nodes.as<Rec8>(), nx, ny, nz);
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    CEG_CK(cudaStreamSynchronize(h->stream));
+    h->g.data = h->d_nodes.as<float>();
+    {
+        std::lock_guard<std::mutex> lk(vdw->mu);
+        vdw->pair = h.get();       // ceg_energy_points picks the fused records up when it is given this (VdW, Coulomb) couple
+    }
+    *out = h.release();
+    return 0;
+}
+
+extern "C" int ceg_grid_pair_free(ceg_gridpair_h h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->vdw) {
+        std::lock_guard<std::mutex> lk(h->vdw->mu);
+        if (h->vdw->pair == h) h->vdw->pair = nullptr;
+    }
+    delete h;
+    return 0;
+}
+
+extern "C" int ceg_interpolate_pair_dev(ceg_gridpair_h h, int64_t n, const double* d_xyz, double* d_out_vdw, double* d_out_coul,
+                                        void* stream) {
+    if (!h || n < 0 || (n > 0 && (!d_xyz || !d_out_vdw || !d_out_coul))) return fail("ceg_interpolate_pair_dev: bad argument");
+    if (n == 0) return 0;
+    if (use_device(h->device)) return 1;
+    interpolate_pair_kernel<<<interp_blocks(n), 256, 0, (cudaStream_t)stream>>>(h->g, n, d_xyz, d_out_vdw, d_out_coul);
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    return 0;
+}
+
+// host pointers: chunks on two streams, upload / kernel / two downloads overlapped (as interpolate_pipelined)
+extern "C" int ceg_interpolate_pair(ceg_gridpair_h h, int64_t n, const double* xyz, double* out_vdw, double* out_coul) {
+    if (!h || n < 0 || (n > 0 && (!xyz || !out_vdw || !out_coul))) return fail("ceg_interpolate_pair: bad argument");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    if (!h->stream2) CEG_CK(acquire_stream(&h->stream2));
+    const int64_t chunk = std::min<int64_t>(n, 1 << 20);
+    for (int b = 0; b < 2; b++) {
+        CEG_CK(h->d_xyz[b].reserve(sizeof(double) * 3 * chunk));
+        CEG_CK(h->d_out[b].reserve(sizeof(double) * 2 * chunk));
+    }
+    cudaStream_t st[2] = {h->stream, h->stream2};
+    int c = 0;
+    for (int64_t q0 = 0; q0 < n; q0 += chunk, c++) {
+        const int64_t m = std::min(chunk, n - q0);
+        const int b = c & 1;
+        double* d_v = h->d_out[b].as<double>();
+        double* d_c = d_v + chunk;
+        CEG_CK(cudaMemcpyAsync(h->d_xyz[b].p, xyz + 3 * q0, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, st[b]));
+        interpolate_pair_kernel<<<interp_blocks(m), 256, 0, st[b]>>>(h->g, m, h->d_xyz[b].as<double>(), d_v, d_c);
+        count_launch();
+        CEG_CK(cudaGetLastError());
+        CEG_CK(cudaMemcpyAsync(out_vdw + q0, d_v, sizeof(double) * m, cudaMemcpyDeviceToHost, st[b]));
+        CEG_CK(cudaMemcpyAsync(out_coul + q0, d_c, sizeof(double) * m, cudaMemcpyDeviceToHost, st[b]));
+    }
+    CEG_CK(cudaStreamSynchronize(st[0]));
+    CEG_CK(cudaStreamSynchronize(st[1]));
+    return 0;
 }
 
 // ================================================================================================
@@ -1527,24 +1782,38 @@ extern "C" int ceg_block_free(ceg_block_h h) {
     return 0;
 }
 
-// Per-thread pinned staging block and stream for small ceg_energy_points calls (one device per thread at a time).
+// Per-thread pinned staging block (mapped into the device address space), stream and completion counter for small
+// ceg_energy_points calls (one device per thread at a time).
 struct SmallStage {
     static constexpr size_t BYTES = 1u << 20;
     void* host = nullptr;
+    void* host_dev = nullptr;          // device view of `host`
+    unsigned int* counter = nullptr;   // device
+    unsigned long long gen = 0;
     cudaStream_t stream = nullptr;
     int device = -1;
     bool ready(int dev) {
         if (dev < 0) return false;
         if (device != dev) {                       // (re)create for this device
             if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+            if (counter) { cudaFree(counter); counter = nullptr; }
+            if (host) { cudaFreeHost(host); host = nullptr; }
             if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { stream = nullptr; cudaGetLastError(); return false; }
+            if (cudaMalloc(&counter, sizeof(unsigned int)) != cudaSuccess || cudaMemset(counter, 0, sizeof(unsigned int)) != cudaSuccess) {
+                counter = nullptr; cudaGetLastError(); return false;
+            }
             device = dev;
         }
-        if (!host && cudaHostAlloc(&host, BYTES, cudaHostAllocPortable) != cudaSuccess) { host = nullptr; cudaGetLastError(); return false; }
+        if (!host) {
+            if (cudaHostAlloc(&host, BYTES, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { host = nullptr; cudaGetLastError(); return false; }
+            if (cudaHostGetDevicePointer(&host_dev, host, 0) != cudaSuccess) { cudaFreeHost(host); host = nullptr; cudaGetLastError(); return false; }
+            memset(host, 0, 64);                    // completion flag
+        }
         return true;
     }
     ~SmallStage() {                                 // thread exit; the context may already be gone: ignore errors
         if (host) cudaFreeHost(host);
+        if (counter) cudaFree(counter);
         if (stream) cudaStreamDestroy(stream);
         cudaGetLastError();
     }
@@ -1589,6 +1858,13 @@ static int energy_points_setup(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_h 
     }
     P.has_coulomb = coulomb ? 1 : 0;
     if (coulomb) P.coulomb = coulomb->g;
+    for (int g = 0; g < n_vdw; g++) {      // fused {VdW, Coulomb} records registered for this couple of handles?
+        P.pair_data[g] = nullptr;
+        if (P.vdw_present[g] && coulomb) {
+            std::lock_guard<std::mutex> lk(vdw[g]->mu);
+            if (vdw[g]->pair && vdw[g]->pair->coul == coulomb) P.pair_data[g] = vdw[g]->pair->g.data;
+        }
+    }
     P.has_block = block ? 1 : 0;
     if (block) P.block = block->b;
     P.n_atoms = n_atoms;
@@ -1629,6 +1905,72 @@ extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_
     if (st < 0) {   // nothing resident: all grids are zero grids
         for (int64_t i = 0; i < n_pos; i++) { out_vdw[i] = 0.0; out_coulomb[i] = 0.0; }
         return 0;
+    }
+    // Latency path (single Monte-Carlo steps): ONE kernel launch per call.  Inputs and outputs sit in a pinned block mapped
+    // into the device address space (the kernel reads positions and writes energies over PCIe itself) and the host waits on
+    // a flag raised by the last CTA — no copies, no stream synchronisation (csrc/latency.cuh).
+    constexpr int64_t LATENCY_MAX_POS = 256;
+    if (n_pos <= LATENCY_MAX_POS && n_atoms <= SMALL_MAX_ATOMS) {
+        SmallStage& stg = small_stage();
+        const size_t n_idx8 = ((size_t)n_atoms + 1) / 2;
+        const size_t need = sizeof(double) * (8 + n_idx8 + (size_t)n_atoms + (size_t)3 * n_atoms * n_pos + (size_t)2 * n_pos);
+        size_t smem = 0;
+        bool tables_fit = true;
+        if (coulomb && ewald && ewald->n_k > 0) {
+            smem = sizeof(double2) * (size_t)n_atoms * ((size_t)(ewald->kmax[0] + 1) + (2 * ewald->kmax[1] + 1) + (2 * ewald->kmax[2] + 1));
+            tables_fit = smem <= 40 * 1024;
+        }
+        if (need <= SmallStage::BYTES && tables_fit && stg.ready(P_device_of(vdw, n_vdw, coulomb, ewald, block))) {
+            double* hb = static_cast<double*>(stg.host);
+            double* db = static_cast<double*>(stg.host_dev);
+            volatile unsigned long long* hflag = reinterpret_cast<volatile unsigned long long*>(hb);
+            const size_t o_idx = 8, o_q = o_idx + n_idx8, o_xyz = o_q + n_atoms, o_v = o_xyz + (size_t)3 * n_atoms * n_pos, o_c = o_v + n_pos;
+            SmallParams S;
+            S.E = P;
+            S.E.n_pos = n_pos;
+            S.n_idx8 = (int)n_idx8;
+            const size_t n_in = n_idx8 + (size_t)n_atoms + (size_t)3 * n_atoms * n_pos;
+            S.n_inline = n_in <= (size_t)SMALL_INLINE_DOUBLES ? (int)n_in : 0;
+            double* dst = S.n_inline ? S.inl : hb + o_idx;      // by value in the launch, or through the mapped block
+            if (S.n_inline) dst[n_idx8 - 1] = 0.0;              // padding word of an odd atom count
+            memcpy(dst, atomsidx, sizeof(int32_t) * n_atoms);
+            memcpy(dst + n_idx8, charges, sizeof(double) * n_atoms);
+            memcpy(dst + n_idx8 + n_atoms, xyz, sizeof(double) * 3 * n_atoms * n_pos);
+            S.in = db + o_idx;
+            S.has_ewald = (coulomb && ewald && ewald->n_k > 0) ? 1 : 0;
+            if (S.has_ewald) {
+                memcpy(S.invmat, ewald->invmat, sizeof S.invmat);
+                S.kx = ewald->kmax[0]; S.ky = ewald->kmax[1]; S.kz = ewald->kmax[2];
+                S.n_k = ewald->n_k;
+                S.kv = ewald->d_kv.as<KVecDev>();
+            } else {
+                S.n_k = 0; S.kv = nullptr; S.kx = S.ky = S.kz = 0;
+            }
+            S.energy_net_charges = energy_net_charges;
+            S.static_contribution = static_contribution;
+            S.out_vdw = db + o_v;
+            S.out_coul = db + o_c;
+            S.flag = reinterpret_cast<volatile unsigned long long*>(db);
+            S.counter = stg.counter;
+            S.gen = ++stg.gen;
+            energy_points_small_kernel<<<(unsigned)n_pos, SMALL_THREADS, smem, stg.stream>>>(S);
+            count_launch();
+            CEG_CK(cudaGetLastError());
+            unsigned long long spins = 0;
+            while (*hflag != S.gen) {
+                if ((++spins & 0xfffff) == 0) {            // every ~1M polls: has the launch failed?
+                    cudaError_t q = cudaStreamQuery(stg.stream);
+                    if (q != cudaErrorNotReady && q != cudaSuccess) return fail_cuda(q, "energy_points_small_kernel", __FILE__, __LINE__);
+                    if (q == cudaSuccess && *hflag != S.gen) {     // finished without raising the flag: cannot happen, do not hang
+                        return fail("ceg_energy_points: latency kernel finished without completing");
+                    }
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            memcpy(out_vdw, hb + o_v, sizeof(double) * n_pos);
+            memcpy(out_coulomb, hb + o_c, sizeof(double) * n_pos);
+            return 0;
+        }
     }
     // Small batches (single Monte-Carlo steps): latency is what matters.  Inputs are packed into one pinned, thread-local
     // staging block and uploaded with ONE copy, the two outputs come back with ONE copy, and the stream is kept per

@@ -42,7 +42,7 @@ __device__ __forceinline__ double rcp_fast(double d) {
 
 // exp(x) = 2^n p(f), n = rint(x / ln 2), f = x - n ln 2 (|f| <= ln2/2), for -707 < x < 700; no memory access.
 // One-constant reduction: |n| (ln 2 - fl(ln 2)) <= 2.4e-14 over the whole range, 2e-15 for |x| <= 60.
-// Arguments below ~-707 return ~2^-1021 instead of wrapping.  DEG/coef: c_expp (degree 8, 1.1e-12: the one
+// Arguments below ~-707 return ~2^-1021 instead of wrapping.  DEG/coef: c_expp (degree 9, 1.8e-14: the one
 // exponential of a Buckingham pair) or c_expa (degree 10, 5e-16: the per-tile Gaussian factors).
 #ifndef CEG_POLY_SPLIT
 #define CEG_POLY_SPLIT 1   // even/odd Horner: two half-length chains (+1 instruction), the inner loop is latency bound

@@ -630,7 +630,7 @@ grid_build_tiled_kernel(const BuildParams P) {
                     double E = 1.0;
                     if (COUL && !GT) {
                         if (PIPE == 2) d2 = fma(dx, dx, fma(dy, dy, dz * dz));
-                        E = exp_fast<SPLIT>(-(P.alpha2 * d2));
+                        E = exp_poly<EXPA_DEG, SPLIT>(-(P.alpha2 * d2), c_expa);   // partly cancelling Coulomb sums: the accurate degree
                     } else if (COUL) {
                         if (RUNPTR) {
                             E = (lds_f64(pgx) * lds_f64(pgy)) * lds_f64(pgz);

@@ -137,6 +137,16 @@ __device__ __forceinline__ void hermite(double t, double* h) {
     h[3] = t3 - t2;
 }
 
+// contribution of corner (ix, iy, iz) to the tensor-product Hermite sum (same expression as interp_one)
+__device__ __forceinline__ double hermite_corner(const float4& lo, const float4& hi, double x0, double x1, double y0, double y1,
+                                                 double z0, double z1) {
+    const double a = x0 * (double)lo.x + x1 * (double)lo.y;   // f , fx
+    const double b = x0 * (double)lo.z + x1 * (double)hi.x;   // fy, fxy
+    const double c = x0 * (double)lo.w + x1 * (double)hi.y;   // fz, fxz
+    const double d = x0 * (double)hi.z + x1 * (double)hi.w;   // fyz, fxyz
+    return z0 * (y0 * a + y1 * b) + z1 * (y0 * c + y1 * d);
+}
+
 // Interpolate one grid at one prepared stencil.  Returns 1e100 if a VdW corner value exceeds 5e6 K
 // (grids.jl:245-248).
 template <int LAYOUT>
@@ -212,12 +222,7 @@ __device__ __forceinline__ double interp_one(const GridDev& g, const Stencil& st
 #pragma unroll
             for (int iz = 0; iz < 2; iz++) {
                 const int n = (ix * 2 + iy) * 2 + iz;
-                const double x0 = hx[ix], x1 = hx[2 + ix], y0 = hy[iy], y1 = hy[2 + iy], z0 = hz[iz], z1 = hz[2 + iz];
-                const double a = x0 * (double)lo[n].x + x1 * (double)lo[n].y;   // f , fx
-                const double b = x0 * (double)lo[n].z + x1 * (double)hi[n].x;   // fy, fxy
-                const double c = x0 * (double)lo[n].w + x1 * (double)hi[n].y;   // fz, fxz
-                const double d = x0 * (double)hi[n].z + x1 * (double)hi[n].w;   // fyz, fxyz
-                ret += z0 * (y0 * a + y1 * b) + z1 * (y0 * c + y1 * d);
+                ret += hermite_corner(lo[n], hi[n], hx[ix], hx[2 + ix], hy[iy], hy[2 + iy], hz[iz], hz[2 + iz]);
             }
     return ret;
 }
@@ -240,6 +245,99 @@ __global__ void __launch_bounds__(256) interpolate_kernel(const GridDev g, int64
         Stencil st;
         make_stencil(g.uc, g.gs, p, st);
         out[q] = interp_one<LAYOUT>(g, st);
+    }
+}
+
+// ---- fused (VdW, Coulomb) pair --------------------------------------------------------------------------
+// energy_point evaluates, for every atom, its species' VdW grid and the Coulomb grid at the SAME position
+// (grids.jl:316-318).  Two separate record arrays cost two half-used 64-byte DRAM fetches per corner whenever the
+// stencil's z pair straddles two bricks (ncu, round 1: 402 B of traffic per 288 B query).  The pair layout
+// interleaves the two grids node by node — 64-byte node records {VdW 32 B, Coulomb 32 B} in 2x2x2-node bricks of
+// 512 B — so every 64-byte unit a query touches is used entirely: 8 x 64 B + 24 B position + 16 B of results per
+// pair of interpolations, and the position, offsetpoint and stencil arithmetic are shared.
+__device__ __forceinline__ int64_t node_record_index(int layout, int x, int y, int z, int64_t ny, int64_t nz) {
+    if (layout == LAYOUT_BLOCK) {
+        const int64_t nby = (ny + 1) >> 1, nbz = (nz + 1) >> 1;
+        return ((((int64_t)(x >> 1) * nby + (y >> 1)) * nbz + (z >> 1)) << 3) + (((x & 1) * 2 + (y & 1)) * 2 + (z & 1));
+    }
+    return ((int64_t)x * ny + y) * nz + z;     // LAYOUT_NODE
+}
+
+// pair bricks from two resident grids (NODE or BLOCK layout each): dst[(brick*8 + slot)*2 + {0: VdW, 1: Coulomb}]
+__global__ void __launch_bounds__(256) pair_records_kernel(const Rec8* __restrict__ gv, int layout_v, const Rec8* __restrict__ gc,
+                                                           int layout_c, Rec8* __restrict__ dst, int nx, int ny, int nz) {
+    const int nby = (ny + 1) / 2, nbz = (nz + 1) / 2, nbx = (nx + 1) / 2;
+    const int64_t total = (int64_t)nbx * nby * nbz * 8;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t & 7);
+        int64_t b = t >> 3;
+        const int bz = (int)(b % nbz); b /= nbz;
+        const int by = (int)(b % nby);
+        const int bx = (int)(b / nby);
+        const int x = min(2 * bx + ((c >> 2) & 1), nx - 1), y = min(2 * by + ((c >> 1) & 1), ny - 1), z = min(2 * bz + (c & 1), nz - 1);
+        dst[2 * t] = gv[node_record_index(layout_v, x, y, z, ny, nz)];
+        dst[2 * t + 1] = gc[node_record_index(layout_c, x, y, z, ny, nz)];
+    }
+}
+
+// one prepared stencil on a pair grid: -> (VdW energy or 1e100, Coulomb potential); arithmetic and summation order
+// identical to interp_one on each grid.  The corners are taken in two halves (x lower, x upper): 8 records = 64 data
+// registers in flight at a time instead of 128.
+__device__ __forceinline__ void interp_pair(const float* __restrict__ data, const GridSpecDev& gs, const Stencil& st,
+                                            double& e_vdw, double& e_coul) {
+    const int64_t ny = gs.n[1], nz = gs.n[2];
+    const int64_t nby = (ny + 1) >> 1, nbz = (nz + 1) >> 1;
+    double hx[4], hy[4], hz[4];
+    hermite(st.r[0], hx);
+    hermite(st.r[1], hy);
+    hermite(st.r[2], hz);
+    double sv = 0.0, sc = 0.0;
+    bool blocked = false;
+#pragma unroll
+    for (int ix = 0; ix < 2; ix++) {
+        float4 lo[4], hi[4], clo[4], chi[4];
+        const int x = st.p0[0] + (ix ? st.step[0] : 0);
+#pragma unroll
+        for (int iy = 0; iy < 2; iy++)
+#pragma unroll
+            for (int iz = 0; iz < 2; iz++) {
+                const int y = st.p0[1] + (iy ? st.step[1] : 0), z = st.p0[2] + (iz ? st.step[2] : 0);
+                const int64_t rec = ((((int64_t)(x >> 1) * nby + (y >> 1)) * nbz + (z >> 1)) << 3) +
+                                    (((x & 1) * 2 + (y & 1)) * 2 + (z & 1));
+                ld_rec(data + rec * 16, lo[iy * 2 + iz], hi[iy * 2 + iz]);
+                ld_rec(data + rec * 16 + 8, clo[iy * 2 + iz], chi[iy * 2 + iz]);
+            }
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const int iy = m >> 1, iz = m & 1;
+            blocked |= (lo[m].x > 5e6f);
+            sv += hermite_corner(lo[m], hi[m], hx[ix], hx[2 + ix], hy[iy], hy[2 + iy], hz[iz], hz[2 + iz]);
+            sc += hermite_corner(clo[m], chi[m], hx[ix], hx[2 + ix], hy[iy], hy[2 + iy], hz[iz], hz[2 + iz]);
+        }
+    }
+    e_vdw = blocked ? 1e100 : sv;
+    e_coul = sc;
+}
+
+struct PairGridDev {
+    CellDev uc;
+    GridSpecDev gs;
+    const float* data;     // 512-byte bricks of 2x2x2 nodes x {VdW, Coulomb} records
+};
+
+#ifndef CEG_PAIR_MINB
+#define CEG_PAIR_MINB 2
+#endif
+__global__ void __launch_bounds__(256, CEG_PAIR_MINB) interpolate_pair_kernel(const PairGridDev g, int64_t n, const double* __restrict__ xyz,
+                                                               double* __restrict__ out_vdw, double* __restrict__ out_coul) {
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const double p[3] = {xyz[3 * q], xyz[3 * q + 1], xyz[3 * q + 2]};
+        Stencil st;
+        make_stencil(g.uc, g.gs, p, st);
+        double ev, ec;
+        interp_pair(g.data, g.gs, st, ev, ec);
+        out_vdw[q] = ev;
+        out_coul[q] = ec;
     }
 }
 
@@ -403,6 +501,7 @@ struct EnergyPointsParams {
     int vdw_present[EP_MAX_VDW];     // 0 = zero grid
     GridDev coulomb;
     int has_coulomb;
+    const float* pair_data[EP_MAX_VDW];   // fused {vdw[g], coulomb} records (interp_pair), or null
     BlockDev block;
     int has_block;
     int n_atoms;
@@ -415,21 +514,52 @@ struct EnergyPointsParams {
     uint8_t* blocked;                // n_pos flags for the reciprocal kernel
 };
 
+// block test of one atom (coordinates.jl:97-101: round(Int, offsetpoint) into the mask)
+__device__ __forceinline__ bool atom_blocked(const BlockDev& B, const double* p) {
+    double s[3];
+    offsetpoint_x(B.uc, B.gs, p, s);
+    // round(Int, x): half to even
+    int64_t ia = (int64_t)rint(s[0]) - 1, ib = (int64_t)rint(s[1]) - 1, ic = (int64_t)rint(s[2]) - 1;
+    ia = ia < 0 ? 0 : (ia >= B.gs.n[0] ? B.gs.n[0] - 1 : ia);
+    ib = ib < 0 ? 0 : (ib >= B.gs.n[1] ? B.gs.n[1] - 1 : ib);
+    ic = ic < 0 ? 0 : (ic >= B.gs.n[2] ? B.gs.n[2] - 1 : ic);
+    return B.mask[(ia * B.gs.n[1] + ib) * B.gs.n[2] + ic] != 0;
+}
+
+// VdW and (charge-weighted) Coulomb grid terms of one atom (grids.jl:316-318)
+__device__ __forceinline__ void atom_grid_terms(const EnergyPointsParams& P, int gi, double qa, const double* p, double& vdw,
+                                                double& coul) {
+    vdw = 0.0;
+    coul = 0.0;
+    if (P.pair_data[gi]) {   // same GridCoordinatesSetup for both grids: one stencil, 64-byte node records
+        Stencil st;
+        make_stencil(P.coulomb.uc, P.coulomb.gs, p, st);
+        double ev, ec;
+        interp_pair(P.pair_data[gi], P.coulomb.gs, st, ev, ec);
+        vdw = ev;
+        coul = qa * ec;
+        return;
+    }
+    if (P.vdw_present[gi]) {
+        Stencil st;
+        make_stencil(P.vdw[gi].uc, P.vdw[gi].gs, p, st);
+        vdw = interp_any(P.vdw[gi], st);
+    }
+    if (P.has_coulomb) {
+        Stencil st;
+        make_stencil(P.coulomb.uc, P.coulomb.gs, p, st);
+        coul = qa * interp_any(P.coulomb, st);
+    }
+}
+
 __global__ void __launch_bounds__(128) energy_points_kernel(const EnergyPointsParams P) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.n_pos; i += (int64_t)gridDim.x * blockDim.x) {
         const double* mol = P.xyz + (int64_t)3 * P.n_atoms * i;
         bool blocked = false;
         if (P.has_block) {
             for (int a = 0; a < P.n_atoms && !blocked; a++) {
-                double s[3];
                 const double p[3] = {mol[3 * a], mol[3 * a + 1], mol[3 * a + 2]};
-                offsetpoint_x(P.block.uc, P.block.gs, p, s);
-                // round(Int, x): half to even
-                int64_t ia = (int64_t)rint(s[0]) - 1, ib = (int64_t)rint(s[1]) - 1, ic = (int64_t)rint(s[2]) - 1;
-                ia = ia < 0 ? 0 : (ia >= P.block.gs.n[0] ? P.block.gs.n[0] - 1 : ia);
-                ib = ib < 0 ? 0 : (ib >= P.block.gs.n[1] ? P.block.gs.n[1] - 1 : ib);
-                ic = ic < 0 ? 0 : (ic >= P.block.gs.n[2] ? P.block.gs.n[2] - 1 : ic);
-                blocked = P.block.mask[(ia * P.block.gs.n[1] + ib) * P.block.gs.n[2] + ic] != 0;
+                blocked = atom_blocked(P.block, p);
             }
         }
         if (blocked) {
@@ -441,17 +571,10 @@ __global__ void __launch_bounds__(128) energy_points_kernel(const EnergyPointsPa
         double vdw = 0.0, coul = 0.0;
         for (int a = 0; a < P.n_atoms; a++) {
             const double p[3] = {mol[3 * a], mol[3 * a + 1], mol[3 * a + 2]};
-            const int gi = P.atomsidx[a];
-            if (P.vdw_present[gi]) {
-                Stencil st;
-                make_stencil(P.vdw[gi].uc, P.vdw[gi].gs, p, st);
-                vdw += interp_any(P.vdw[gi], st);
-            }
-            if (P.has_coulomb) {
-                Stencil st;
-                make_stencil(P.coulomb.uc, P.coulomb.gs, p, st);
-                coul += P.charges[a] * interp_any(P.coulomb, st);
-            }
+            double v, c;
+            atom_grid_terms(P, P.atomsidx[a], P.charges[a], p, v, c);
+            vdw += v;
+            coul += c;
         }
         P.out_vdw[i] = vdw;
         P.out_coulomb[i] = coul;

@@ -1,0 +1,132 @@
+// Small-batch (latency) path of energy_point (sm_100a).
+//
+// A serial Monte-Carlo chain asks for ONE placement at a time (montecarlo.jl:490-504 + compute_ewald): the batched
+// kernels then cost five API calls and two launches for a few microseconds of work (round 1: 69 us per call).  Here a
+// call is one kernel launch and nothing else: inputs and outputs live in a pinned host block that is MAPPED into the
+// device address space, so the kernel reads the positions and writes the energies over PCIe itself, and the host
+// waits on a flag the last CTA raises instead of synchronising a stream.
+//
+// One CTA (4 warps) per placement: block test and grid terms with one thread per atom (grids.jl:311-318), then the
+// reciprocal-space term (ewald.jl:555-577) with the k-list spread over the CTA — power tables by sincospi in shared
+// memory as in reciprocal_kernel, fixed-order reduction.
+#pragma once
+#include "ewald.cuh"
+#include "interp.cuh"
+
+namespace ceg {
+
+constexpr int SMALL_THREADS = 128;
+constexpr int SMALL_MAX_ATOMS = 64;
+
+constexpr int SMALL_INLINE_DOUBLES = 160;   // inputs up to this size travel inside the kernel parameters
+
+struct SmallParams {
+    EnergyPointsParams E;            // grids, block mask, n_atoms (its atomsidx / charges / xyz pointers are not used)
+    // inputs, as doubles: [atomsidx as int32, padded to 8 bytes][charges n_atoms][xyz n_pos x n_atoms x 3] — either in
+    // the mapped host block (`in`) or, when small, by value in `inl` (no PCIe read on the critical path)
+    const double* in;
+    int n_inline;
+    int n_idx8;
+    double inl[SMALL_INLINE_DOUBLES];
+    int has_ewald;
+    double invmat[9];
+    int kx, ky, kz;
+    int64_t n_k;
+    const KVecDev* kv;
+    double energy_net_charges, static_contribution;
+    double* out_vdw;                 // mapped host
+    double* out_coul;                // mapped host
+    volatile unsigned long long* flag;   // mapped host: receives `gen` when every placement is done
+    unsigned int* counter;           // device: CTAs finished
+    unsigned long long gen;
+};
+
+__global__ void __launch_bounds__(SMALL_THREADS) energy_points_small_kernel(const __grid_constant__ SmallParams S) {
+    extern __shared__ double2 s_tab[];
+    __shared__ double s_v[SMALL_MAX_ATOMS], s_c[SMALL_MAX_ATOMS];
+    __shared__ double s_fa[SMALL_THREADS / 32], s_aa[SMALL_THREADS / 32];
+    __shared__ int s_blocked;
+    const EnergyPointsParams& P = S.E;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t i = blockIdx.x;
+    const double* in = S.n_inline ? S.inl : S.in;             // __grid_constant__: the parameter block is addressable
+    const int* idx = reinterpret_cast<const int*>(in);
+    const double* q_in = in + S.n_idx8;
+    const double* mol = q_in + P.n_atoms + (int64_t)3 * P.n_atoms * i;
+    __shared__ double s_q[SMALL_MAX_ATOMS];
+    if (tid == 0) s_blocked = 0;
+    __syncthreads();
+    double p[3] = {0.0, 0.0, 0.0};
+    if (tid < P.n_atoms) {
+        p[0] = mol[3 * tid]; p[1] = mol[3 * tid + 1]; p[2] = mol[3 * tid + 2];
+        s_q[tid] = q_in[tid];
+        if (P.has_block && atom_blocked(P.block, p)) s_blocked = 1;
+    }
+    __syncthreads();
+    const bool blocked = s_blocked != 0;
+    if (!blocked && tid < P.n_atoms) atom_grid_terms(P, idx[tid], s_q[tid], p, s_v[tid], s_c[tid]);
+    double fa = 0.0, aa = 0.0;
+    const bool recip = S.has_ewald && !blocked && S.n_k > 0;
+    if (recip) {
+        const int nx = S.kx + 1, ny = 2 * S.ky + 1, nz = 2 * S.kz + 1;
+        const int per_atom = nx + ny + nz;
+        for (int t = tid; t < per_atom * P.n_atoms; t += SMALL_THREADS) {
+            const int a = t / per_atom, u = t - a * per_atom;
+            const double x = mol[3 * a], y = mol[3 * a + 1], z = mol[3 * a + 2];
+            int axis, m;
+            if (u < nx) { axis = 0; m = u; }
+            else if (u < nx + ny) { axis = 1; m = u - nx - S.ky; }
+            else { axis = 2; m = u - nx - ny - S.kz; }
+            double f = S.invmat[axis] * x + S.invmat[3 + axis] * y + S.invmat[6 + axis] * z;   // ewald.jl:358
+            f -= floor(f);
+            double sn, cs;
+            sincospi(2.0 * red_prod((double)m, f), &sn, &cs);
+            s_tab[t] = make_double2(cs, sn);
+        }
+        __syncthreads();
+        for (int64_t k = tid; k < S.n_k; k += SMALL_THREADS) {
+            const KVecDev kv = S.kv[k];
+            double sre = 0.0, sim = 0.0;
+            for (int a = 0; a < P.n_atoms; a++) {
+                const double2* ta = s_tab + a * per_atom;
+                const double2 ex = ta[kv.ix], ey = ta[nx + S.ky + kv.jy], ez = ta[nx + ny + S.kz + kv.jz];
+                const double yzr = ey.x * ez.x - ey.y * ez.y, yzi = ey.x * ez.y + ey.y * ez.x;
+                const double qa = s_q[a];
+                sre += qa * (ex.x * yzr - ex.y * yzi);
+                sim += qa * (ex.x * yzi + ex.y * yzr);
+            }
+            fa += kv.kf * (kv.sf_re * sre + kv.sf_im * sim);
+            aa += kv.kf * (sre * sre + sim * sim);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fa += __shfl_xor_sync(0xffffffffu, fa, o);
+            aa += __shfl_xor_sync(0xffffffffu, aa, o);
+        }
+        if (lane == 0) { s_fa[warp] = fa; s_aa[warp] = aa; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double vdw = 0.0, coul = 0.0;
+        if (blocked) {
+            vdw = 1e100;     // grids.jl:313
+        } else {
+            for (int a = 0; a < P.n_atoms; a++) { vdw += s_v[a]; coul += s_c[a]; }
+            if (recip) {
+                double f = 0.0, q = 0.0;
+                for (int w = 0; w < SMALL_THREADS / 32; w++) { f += s_fa[w]; q += s_aa[w]; }
+                coul += 2.0 * (f + S.energy_net_charges) + (q + S.static_contribution);   // ewald.jl:572-576
+            }
+        }
+        S.out_vdw[i] = vdw;
+        S.out_coul[i] = coul;
+        __threadfence_system();
+        if (atomicAdd(S.counter, 1u) == gridDim.x - 1) {
+            *S.counter = 0;
+            __threadfence_system();
+            *S.flag = S.gen;
+        }
+    }
+}
+
+}  // namespace ceg

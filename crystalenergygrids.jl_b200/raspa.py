@@ -23,6 +23,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import forcefields as FF
+from .constants import GRID_TO_KELVIN
 from .cell import find_supercell, mat_from_parameters
 from .constants import CUTOFF_COULOMB
 from .forcefields import ForceField, InteractionRule, InteractionRuleSum, Kind, Mixing, get_atom_name
@@ -176,6 +177,28 @@ def _ffname(pff) -> str:
     return pff[0]
 
 
+def hash_forcefield(ff: ForceField) -> str:
+    """Stable content hash of a ForceField (rules, shifts, cutoff, species order): the role hash_string(forcefield)
+    plays in raspa.jl:196-204 (the reference hashes Julia's serialisation; any stable digest serves the cache name)."""
+    import hashlib
+    h = hashlib.sha1()
+    h.update(repr((sorted(ff.sdict.items(), key=lambda kv: kv[1]), float(ff.cutoff))).encode())
+    for row in ff.interactions:
+        for rule in row:
+            parts = rule.rules if isinstance(rule, InteractionRuleSum) else (rule,)
+            h.update(repr([(int(r.kind), tuple(float(x).hex() for x in r.params), float(r.shift).hex(), bool(r.tailcorrection))
+                           for r in parts]).encode())
+    return h.hexdigest()[:16]
+
+
+def _fffullname(pff, forcefield: ForceField) -> str:
+    """raspa.jl:196-204: the stock name for a force field given by name, '<name>-<hash>' for a customised ForceField
+    or (name, ForceField / PseudoAtomListing) tuple, so that its grids never collide with the stock ones."""
+    if isinstance(pff, str):
+        return pff
+    return f"{_ffname(pff)}-{hash_forcefield(forcefield)}"
+
+
 def _ffpal(pff) -> PseudoAtomListing:
     if isinstance(pff, tuple) and isinstance(pff[1], PseudoAtomListing):
         return pff[1]
@@ -299,9 +322,9 @@ def grid_locations(framework, pff, forcefield: ForceField, atoms, gridstep: floa
     """raspa.jl:403-418 — `.grid` cache paths: grids/<ff>/<framework>/<step %.6f>/[<AxBxC>/]…"""
     if not isinstance(framework, str):
         return "", []
-    rawname = _ffname(pff)
+    rawname = _ffname(pff)          # locates force_field_mixing_rules.def
     raspa = getdir_RASPA()
-    rootdir = os.path.join(root if root is not None else os.path.join(raspa, "grids"), rawname, framework)
+    rootdir = os.path.join(root if root is not None else os.path.join(raspa, "grids"), _fffullname(pff, forcefield), framework)
     grid_dir = os.path.join(rootdir, "%.6f" % gridstep)
     supercell_name = "x".join(str(int(x)) for x in supercell)
     coulomb_grid_path = os.path.join(grid_dir, supercell_name, framework + "_Electrostatics_Ewald.grid")
@@ -484,37 +507,70 @@ def retrieve_or_create_grid(grid_path, syst_framework, forcefield, gridstep, ato
 
 
 def _create_missing_grids_fused(syst_framework, forcefield, gridstep, cutoff, new, devices, coulomb_path, ewald,
-                                vdw_atoms_paths):
+                                vdw_atoms_paths, keep_on_device: bool = True):
     """Create the `.grid` files of one setup that do not exist yet (or all of them if `new`), fusing
-    up to four VdW probes and the Coulomb grid per pass (grids.jl:137-185 writes them one by one)."""
-    from .grids import build_grids, write_grid
+    up to four VdW probes and the Coulomb grid per pass (grids.jl:137-185 writes them one by one).
+
+    keep_on_device: the reference writes each file and parses it straight back (raspa.jl:430-438: disk -> host ->
+    scale -> EnergyGrid).  Here the freshly built grids stay in HBM: the build output is gathered (several GPUs) and
+    turned into interpolation handles on the device (ceg_grid_upload_dev applies parse_grid's conversion,
+    grids.jl:78), and the files are written from one downloaded copy by a background thread.
+    -> {path: EnergyGrid} of the grids created (device-resident), empty with keep_on_device=False."""
+    import threading
+    from .grids import build_grids, build_grids_device, write_grid
     if cutoff != 12.0:
         raise ValueError("Cutoff other than 12 Å or infinity is not supported.")
     todo_vdw = [(a, p) for a, p in vdw_atoms_paths if p and (new or not os.path.isfile(p))]
     todo_coul = bool(coulomb_path) and (new or not os.path.isfile(coulomb_path))
+    made = {}
     if not todo_vdw and not todo_coul:
-        return
+        return made
     num_vdw = find_supercell(syst_framework.mat, forcefield.cutoff)
     num_coul = find_supercell(syst_framework.mat, CUTOFF_COULOMB)
     first = True
     while todo_vdw or (todo_coul and first):
         batch, todo_vdw = todo_vdw[:4], todo_vdw[4:]
         with_coul = todo_coul and first
-        cset, grids, _ = build_grids(syst_framework, forcefield, gridstep, atoms=tuple(a for a, _ in batch),
-                                     coulomb=with_coul, alpha=ewald.alpha if with_coul else 0.0, devices=devices)
-        for (a, p), g in zip(batch, grids):
+        atoms = tuple(a for a, _ in batch)
+        alpha = ewald.alpha if with_coul else 0.0
+        paths = [p for _, p in batch] + ([coulomb_path] if with_coul else [])
+        for p in paths:
             os.makedirs(os.path.dirname(p), exist_ok=True)
-            write_grid(p, cset, num_vdw, g)
-        if with_coul:
-            os.makedirs(os.path.dirname(coulomb_path), exist_ok=True)
-            write_grid(coulomb_path, cset, num_coul, grids[-1], ewald_precision=ewald.precision)
+        if keep_on_device:
+            cset, egs, host = build_grids_device(syst_framework, forcefield, gridstep, atoms=atoms, coulomb=with_coul, alpha=alpha,
+                                                 devices=devices, ewald_precision=ewald.precision if with_coul else 1e-6,
+                                                 download=True)
+
+            def finish(eg, arr, path, nuc, prec):
+                write_grid(path, cset, nuc, arr, ewald_precision=prec)
+                eg._grid = (arr.astype(np.float64) * GRID_TO_KELVIN).astype(np.float32)     # grids.jl:78
+
+            for k, (eg, arr, path) in enumerate(zip(egs, host, paths)):
+                is_coul = with_coul and k == len(egs) - 1
+                t = threading.Thread(target=finish, args=(eg, arr, path, num_coul if is_coul else num_vdw,
+                                                          ewald.precision if is_coul else None))
+                eg._pending = t
+                t.start()
+                made[path] = eg
+        else:
+            cset, grids, _ = build_grids(syst_framework, forcefield, gridstep, atoms=atoms, coulomb=with_coul, alpha=alpha,
+                                         devices=devices)
+            for (a, p), g in zip(batch, grids):
+                write_grid(p, cset, num_vdw, g)
+            if with_coul:
+                write_grid(coulomb_path, cset, num_coul, grids[-1], ewald_precision=ewald.precision)
         first = False
+    return made
 
 
 def setup_RASPA(framework, pff, molecule, ffname_molecule: str | None = None, *, gridstep: float = 0.15,
                 supercell=None, blockfile=None, new: bool = False, cutoff: float = 12.0, grids_root: str | None = None,
-                devices=None):
-    """raspa.jl:472-530 — returns a CrystalEnergySetup (grids.jl:284-294)."""
+                devices=None, keep_on_device: bool = True):
+    """raspa.jl:472-530 — returns a CrystalEnergySetup (grids.jl:284-294).
+
+    Grids that have to be created are handed from the construction kernels to the interpolator on the device
+    (keep_on_device, see _create_missing_grids_fused); their `.grid` files are written in the background, in the
+    reference's byte layout.  Cached files are parsed as in the reference."""
     from .ewald import EwaldFramework, initialize_ewald
     from .grids import CrystalEnergySetup, EnergyGrid
     syst_framework = load_framework_RASPA(framework, pff)
@@ -545,13 +601,18 @@ def setup_RASPA(framework, pff, molecule, ffname_molecule: str | None = None, *,
         # Every missing grid of this setup is built in fused passes over the framework atoms (up to four
         # VdW probes + the Coulomb grid share one distance computation), instead of one pass per grid as
         # the loop below would do through retrieve_or_create_grid; the files written are the same.
-        _create_missing_grids_fused(syst_framework, forcefield, gridstep, cutoff, new, devices,
-                                    coulomb_grid_path if needcoulomb else None, ewald,
-                                    [(a, p) for a, p in zip(rev_atomdict, vdws) if FF.needsvdwgrid(forcefield, a)])
+        made = _create_missing_grids_fused(syst_framework, forcefield, gridstep, cutoff, new, devices,
+                                           coulomb_grid_path if needcoulomb else None, ewald,
+                                           [(a, p) for a, p in zip(rev_atomdict, vdws) if FF.needsvdwgrid(forcefield, a)],
+                                           keep_on_device)
         new = False
+    else:
+        made = {}
     if needcoulomb:
         if not isinstance(framework, str):
             coulomb = EnergyGrid.zero()
+        elif coulomb_grid_path in made:
+            coulomb = made[coulomb_grid_path]
         else:
             coulomb = retrieve_or_create_grid(coulomb_grid_path, syst_framework, forcefield, gridstep, ewald, mat, new,
                                               cutoff, devices)
@@ -561,6 +622,8 @@ def setup_RASPA(framework, pff, molecule, ffname_molecule: str | None = None, *,
     for i, atom in enumerate(rev_atomdict):
         if not isinstance(framework, str):
             grids.append(EnergyGrid.zero())
+        elif vdws[i] in made:
+            grids.append(made[vdws[i]])
         else:
             grids.append(retrieve_or_create_grid(vdws[i], syst_framework, forcefield, gridstep, atom, mat, new, cutoff,
                                                  devices))

@@ -88,6 +88,7 @@ typedef struct ceg_grid_s*  ceg_grid_h;    /* device-resident EnergyGrid grids.j
 typedef struct ceg_ewald_s* ceg_ewald_h;   /* EwaldFramework            ewald.jl:40-50    */
 typedef struct ceg_block_s* ceg_block_h;   /* BlockFile                 coordinates.jl:83 */
 typedef struct ceg_guest_s* ceg_guest_h;   /* guests of a SimulationStep energy.jl:43-60  */
+typedef struct ceg_gridpair_s* ceg_gridpair_h; /* {VdW grid of a species, Coulomb grid} fused on the device */
 
 const char* ceg_last_error(void);
 int ceg_abi_version(void);
@@ -107,6 +108,16 @@ int ceg_measure_fp64_peak(int32_t device, double* tflops);
 /* Same chains with three per-thread register operands per DFMA (what real kernels issue): on B200 the
  * register-file read bandwidth caps this form ~30 % below the uniform-operand figure. */
 int ceg_measure_fp64_peak_regops(int32_t device, double* tflops);
+
+/* Registers per thread of the main kernels as loaded on `device`: which = 0 fused one-probe + Coulomb build kernel,
+ * 1 interpolation (brick layout), 2 fused VdW + Coulomb pair interpolation, 3 reciprocal rows kernel (one atom). */
+int ceg_kernel_registers(int32_t device, int32_t which, int32_t* regs);
+/* Plain device buffers for chaining the _dev entry points from a host language without a CUDA runtime binding
+ * (build_dev -> gather -> upload_dev); ceg_device_download copies one back (e.g. to write its `.grid` file). */
+int ceg_device_malloc(int32_t device, int64_t bytes, void** out);
+int ceg_device_free(void* ptr);
+int ceg_device_download(int32_t device, const void* d_src, int64_t bytes, void* host_dst);
+int ceg_device_synchronize(int32_t device);
 
 /* Self-test hook for the branch-free device math of the construction kernels (fastmath.cuh):
  * out[6*i..] = exp_fast(-x[i]), erfcx_fast(x[i]), rsqrt_fast(x[i]), rcp_fast(x[i]), exp_acc(-x[i]), exp_fast(x[i]), x[i] > 0. */
@@ -160,6 +171,17 @@ int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int3
  * number of (point, atom image) pairs tested, number inside the cutoff. */
 int ceg_probe_last_stats(ceg_probe_h h, int64_t* n_points, int64_t* pairs_tested, int64_t* pairs_in_cutoff);
 
+/* Phases of the last ceg_grid_build on this handle, in ms: out4 = { host time spent building image lists, device span
+ * first-to-last kernel, device tail between the last kernel and the last slab copy, host time of the whole call }. */
+int ceg_probe_last_timing(ceg_probe_h h, double* out4);
+
+/* Gather the x-slabs of one grid that were built on several devices of this process into a full grid on dst_device
+ * (peer copies over NVLink) — the device-resident form of the hand-off the reference makes through `.grid` files
+ * (raspa.jl:430-438).  Part p: planes [i0[p], i1[p]) as [8][i1-i0][ny][nz] floats on devices[p] (ceg_grid_build_dev
+ * output); d_full: [8][nx][ny][nz] floats on dst_device, ready for ceg_grid_upload_dev.  Blocking. */
+int ceg_grid_gather(int32_t n_parts, const int32_t* devices, const float* const* d_slabs, const int32_t* i0,
+                    const int32_t* i1, const ceg_gridspec_t* gs, int32_t dst_device, float* d_full);
+
 /* ------------------------------------------------------------------------------------------
  * Interpolation.  Replaces interpolate_grid (grids.jl:212-273) + offsetpoint
  * (coordinates.jl:58-66).  `grid` is the host array AFTER parse_grid (values already multiplied
@@ -187,6 +209,18 @@ int ceg_interpolate_dev(ceg_grid_h h, int64_t n, const double* d_xyz, double* d_
 /* Several grids (e.g. the VdW grid of an atom and the Coulomb grid, grids.jl:316-318) at the same
  * positions: positions are uploaded once; outs[g] receives n energies of grids[g]. */
 int ceg_interpolate_multi(int32_t n_grids, const ceg_grid_h* grids, int64_t n, const double* xyz, double* const* outs);
+/* Fused pair: energy_point interpolates, per atom, its species' VdW grid and the Coulomb grid at the same position
+ * (grids.jl:316-318).  ceg_grid_pair_create interleaves two resident grids that share one GridCoordinatesSetup into
+ * 64-byte node records {VdW, Coulomb} (2x the memory of one grid, in addition to the two handles, which stay valid and
+ * must outlive the pair); a lookup then fetches only fully used 64-byte units and shares the position, offsetpoint and
+ * stencil between the two interpolations.  Results are bit-identical to ceg_interpolate on each grid.  While the pair
+ * exists, ceg_energy_points / ceg_energy_lattice use it whenever they are given this (VdW, Coulomb) couple of handles. */
+int ceg_grid_pair_create(ceg_grid_h vdw, ceg_grid_h coulomb, ceg_gridpair_h* out);
+int ceg_grid_pair_free(ceg_gridpair_h h);
+int ceg_interpolate_pair(ceg_gridpair_h h, int64_t n, const double* xyz, double* out_vdw, double* out_coul);
+int ceg_interpolate_pair_dev(ceg_gridpair_h h, int64_t n, const double* d_xyz, double* d_out_vdw, double* d_out_coul,
+                             void* stream);
+
 /* Interpolation sweep over positions generated on the device (the 10^9-query sweep of C5): query
  * first + t (t < n) sits at mat * (u0,u1,u2), u_d = splitmix64(seed, 3 (first + t) + d) in [0,1), mat = 9 doubles
  * column-major.  Returns the sum and the minimum of the unblocked energies and the number of blocked (1e100)

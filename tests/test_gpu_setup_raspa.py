@@ -95,6 +95,7 @@ def test_setup_raspa_co2_fused_grids_and_cache(cuda_lib, orc, tmp_path):
     assert setup.coulomb.ewald_precision == 1e-6 and all(g.ewald_precision == np.inf for g in setup.grids)
     fw = setup.framework
     assert ceg.find_supercell(fw.mat, 12.0) == (2, 2, 3) == setup.grids[0].num_unitcell
+    setup.wait()        # the files of freshly created grids are written by a background thread
     gdir = tmp_path / "grids" / "ToyFF" / "Toy" / "0.400000"
     files = sorted(p.name for p in gdir.rglob("*.grid"))
     assert files == ["Toy_C_co2_truncated.grid", "Toy_Electrostatics_Ewald.grid", "Toy_O_co2_truncated.grid"]
@@ -141,6 +142,7 @@ def test_setup_raspa_co2_fused_grids_and_cache(cuda_lib, orc, tmp_path):
     assert np.array_equal(setup2.grids[0].grid, setup.grids[0].grid)
     # a single-atom probe defined in the framework force field (raspa.jl:526-529)
     s3 = ceg.setup_RASPA("Toy", "ToyFF", "Na", gridstep=0.4)
+    s3.wait()
     assert s3.block.empty and s3.charges[0] == 1.0 and (gdir / "Toy_Na_truncated.grid").exists()
     e = ceg.energy_point(s3, np.array([[3.0, 4.0, 5.0]]))
     assert np.isfinite(e[1]) and (np.isfinite(e[0]) or e[0] == 1e100)
