@@ -46,7 +46,7 @@ EXPORTS = [
     "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_guest_env_create", "ceg_guest_env_free", "ceg_guest_env_update", "ceg_guest_env_energy", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
     "ceg_probe_last_timing", "ceg_grid_gather", "ceg_kernel_registers", "ceg_device_malloc", "ceg_device_free",
     "ceg_device_download", "ceg_device_synchronize", "ceg_grid_pair_create", "ceg_grid_pair_free", "ceg_interpolate_pair",
-    "ceg_interpolate_pair_dev",
+    "ceg_interpolate_pair_dev", "ceg_ewald_create_from_sf", "ceg_grid_upload_parts_dev",
 ]
 
 _lib = None
@@ -289,6 +289,21 @@ def grid_upload_dev(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, d_grid: i
     return h
 
 
+def grid_upload_parts_dev(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, d_parts, i0s, i1s, strides, scale: float,
+                          is_vdw: bool):
+    """x-slabs on this device (after an all-gather) -> grid handle, without assembling the full grid."""
+    n = len(d_parts)
+    ptrs = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in d_parts])
+    a = np.ascontiguousarray(i0s, dtype=np.int32)
+    b = np.ascontiguousarray(i1s, dtype=np.int32)
+    st = np.ascontiguousarray(strides, dtype=np.int64) if strides is not None else None
+    h = C.c_void_p()
+    _check(load().ceg_grid_upload_parts_dev(C.c_int32(device), C.byref(cell), C.byref(gs), C.c_int32(n), ptrs, _p(a, C.c_int32),
+                                            _p(b, C.c_int32), _p(st, C.c_int64) if st is not None else None, C.c_double(scale),
+                                            C.c_int32(int(is_vdw)), C.byref(h)))
+    return h
+
+
 def set_interp_layout(layout: int):
     """-1 auto, 0 node records, 1 quads, 2 cells (include/ceg_cuda.h)."""
     _check(load().ceg_set_interp_layout(C.c_int32(layout)))
@@ -383,6 +398,20 @@ def ewald_create(device: int, invmat9, kmax, kvec, kfactor, frac, charge):
                                    _p(kvec, C.c_int32), _p(kfactor, C.c_double), C.c_int64(frac.shape[0]),
                                    _p(frac, C.c_double), _p(charge, C.c_double), C.byref(h), _p(S, C.c_double)))
     return h, S[:, 0] + 1j * S[:, 1]
+
+
+def ewald_create_from_sf(device: int, invmat9, kmax, kvec, kfactor, S) -> object:
+    """Ewald handle from an existing structure factor S (complex, n_k)."""
+    invmat9 = _f64(invmat9, (9,))
+    kmax = np.ascontiguousarray(kmax, dtype=np.int32)
+    kvec = np.ascontiguousarray(kvec, dtype=np.int32).reshape(-1, 3)
+    kfactor = _f64(kfactor, (-1,))
+    Sr = np.ascontiguousarray(np.stack([np.real(S), np.imag(S)], axis=1), dtype=np.float64)
+    assert kfactor.shape[0] == kvec.shape[0] == Sr.shape[0]
+    h = C.c_void_p()
+    _check(load().ceg_ewald_create_from_sf(C.c_int32(device), _p(invmat9, C.c_double), _p(kmax, C.c_int32), C.c_int64(kvec.shape[0]),
+                                           _p(kvec, C.c_int32), _p(kfactor, C.c_double), _p(Sr, C.c_double), C.byref(h)))
+    return h
 
 
 def ewald_free(h):

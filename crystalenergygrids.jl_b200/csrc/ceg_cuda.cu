@@ -170,12 +170,19 @@ struct ceg_probe_s {
     double min_perp_width = 0;
     DevBuf d_xyz, d_type, d_q, d_table, d_stats;
     // cached expanded image list
-    DevBuf d_ext, d_ext_meta, d_ext_range;
-    int n_ext = 0;
-    int ext_plane0 = 0, ext_planes = 0;
-    double ext_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int ext_key_planes[2] = {-1, -1};
-    bool ext_valid = false;
+    // cached expanded image lists, one per (slab, grid spec) recently built — callers alternate between a few slabs (the
+    // halves of a pipelined build, C1 and C4 of one framework): least recently used of EXT_CACHE entries is replaced
+    struct ExtList {
+        DevBuf d_ext, d_ext_meta, d_ext_range;
+        int n_ext = 0, plane0 = 0, planes = 0;
+        double key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int key_planes[2] = {-1, -1};
+        bool valid = false;
+        unsigned long long used = 0;
+    };
+    static constexpr int EXT_CACHE = 4;
+    ExtList ext_cache[EXT_CACHE];
+    unsigned long long ext_clock = 0;
     int sm_count = 148;
     // events of the write-back ring of ceg_grid_build, created once per handle
     cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr}, ev_free[3] = {nullptr, nullptr, nullptr};
@@ -208,8 +215,8 @@ struct ceg_grid_s {
     DevBuf d_nodes, d_xyz[2], d_out[2];
     ceg_gridpair_s* pair = nullptr;                     // fused {this VdW grid, a Coulomb grid} records (ceg_grid_pair_create)
     ~ceg_grid_s() {
-        if (stream) cudaStreamDestroy(stream);
-        if (stream2) cudaStreamDestroy(stream2);
+        if (stream) release_stream(stream);
+        if (stream2) release_stream(stream2);
     }
 };
 
@@ -755,8 +762,14 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     hi[0] = (i1 - 1) * gs->size[0] / gs->dims[0] + gs->shift[0];
     for (int d = 1; d < 3; d++) { lo[d] = gs->shift[d]; hi[d] = gs->shift[d] + gs->size[d]; }
     double key[8] = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], cutoff, reach};
-    if (!h->ext_valid || memcmp(key, h->ext_key, sizeof key) != 0 || h->ext_key_planes[0] != i0 || h->ext_key_planes[1] != i1) {
+    ceg_probe_s::ExtList* L = nullptr;
+    for (auto& c : h->ext_cache)
+        if (c.valid && memcmp(key, c.key, sizeof key) == 0 && c.key_planes[0] == i0 && c.key_planes[1] == i1) L = &c;
+    if (!L) {
         const auto t_list0 = std::chrono::steady_clock::now();
+        L = &h->ext_cache[0];
+        for (auto& c : h->ext_cache)
+            if (!c.valid || (L->valid && c.used < L->used)) L = &c;
         std::vector<ExtAtom> ext;
         std::vector<ExtMeta> meta;
         build_ext_list(h, lo, hi, reach + 1e-6, ext, meta);
@@ -771,28 +784,30 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
             range[i] = (int)(std::lower_bound(ext.begin(), ext.end(), x - xcut, xless) - ext.begin());
             range[planes + i] = (int)(std::upper_bound(ext.begin(), ext.end(), x + xcut, xgreater) - ext.begin());
         }
-        CEG_CK(cudaDeviceSynchronize());   // an earlier asynchronous build may still be reading the old list
-        h->n_ext = (int)ext.size();
-        CEG_CK(h->d_ext.reserve(sizeof(ExtAtom) * std::max<size_t>(1, ext.size())));
-        CEG_CK(h->d_ext_meta.reserve(sizeof(ExtMeta) * std::max<size_t>(1, meta.size())));
-        CEG_CK(h->d_ext_range.reserve(sizeof(int) * range.size()));
+        if (L->valid) CEG_CK(cudaDeviceSynchronize());   // an earlier asynchronous build may still be reading the list being replaced
+        L->valid = false;
+        L->n_ext = (int)ext.size();
+        CEG_CK(L->d_ext.reserve(sizeof(ExtAtom) * std::max<size_t>(1, ext.size())));
+        CEG_CK(L->d_ext_meta.reserve(sizeof(ExtMeta) * std::max<size_t>(1, meta.size())));
+        CEG_CK(L->d_ext_range.reserve(sizeof(int) * range.size()));
         if (!ext.empty()) {
-            CEG_CK(cudaMemcpy(h->d_ext.p, ext.data(), sizeof(ExtAtom) * ext.size(), cudaMemcpyHostToDevice));
-            CEG_CK(cudaMemcpy(h->d_ext_meta.p, meta.data(), sizeof(ExtMeta) * meta.size(), cudaMemcpyHostToDevice));
+            CEG_CK(cudaMemcpy(L->d_ext.p, ext.data(), sizeof(ExtAtom) * ext.size(), cudaMemcpyHostToDevice));
+            CEG_CK(cudaMemcpy(L->d_ext_meta.p, meta.data(), sizeof(ExtMeta) * meta.size(), cudaMemcpyHostToDevice));
         }
-        CEG_CK(cudaMemcpy(h->d_ext_range.p, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
-        memcpy(h->ext_key, key, sizeof key);
-        h->ext_key_planes[0] = i0; h->ext_key_planes[1] = i1;
-        h->ext_plane0 = i0; h->ext_planes = planes;
-        h->ext_valid = true;
+        CEG_CK(cudaMemcpy(L->d_ext_range.p, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
+        memcpy(L->key, key, sizeof key);
+        L->key_planes[0] = i0; L->key_planes[1] = i1;
+        L->plane0 = i0; L->planes = planes;
+        L->valid = true;
         h->list_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_list0).count();
     }
-    P.ext = h->d_ext.as<ExtAtom>();
-    P.ext_meta = h->d_ext_meta.as<ExtMeta>();
-    P.n_ext = h->n_ext;
-    P.ext_lo = h->d_ext_range.as<int>();
-    P.ext_hi = h->d_ext_range.as<int>() + h->ext_planes;
-    P.ext_plane0 = h->ext_plane0;
+    L->used = ++h->ext_clock;
+    P.ext = L->d_ext.as<ExtAtom>();
+    P.ext_meta = L->d_ext_meta.as<ExtMeta>();
+    P.n_ext = L->n_ext;
+    P.ext_lo = L->d_ext_range.as<int>();
+    P.ext_hi = L->d_ext_range.as<int>() + L->planes;
+    P.ext_plane0 = L->plane0;
     return 0;
 }
 
@@ -1101,10 +1116,11 @@ extern "C" int ceg_grid_layout(ceg_grid_h h, int32_t* layout) {
     return 0;
 }
 
-// grid: host pointer (from_device = false) or device pointer on `device` (true), [8][nx][ny][nz]
+// grid: host pointer (from_device = false) or device pointer on `device` (true), [8][nx][ny][nz]; or `parts` (device,
+// x-slabs of a sharded build, see GridSource)
 static int grid_upload_impl(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* grid,
-                            bool from_device, double scale, int32_t is_vdw, ceg_grid_h* out) {
-    if (!unitcell || !gs || !grid || !out) return fail("ceg_grid_upload: null argument");
+                            bool from_device, double scale, int32_t is_vdw, ceg_grid_h* out, const GridSource* parts = nullptr) {
+    if (!unitcell || !gs || (!grid && !parts) || !out) return fail("ceg_grid_upload: null argument");
     for (int d = 0; d < 3; d++)
         if (gs->dims[d] < 1) return fail("ceg_grid_upload: bad dims");
     if (use_device(device)) return 1;
@@ -1116,7 +1132,7 @@ static int grid_upload_impl(int32_t device, const ceg_cell_t* unitcell, const ce
     const int nx = gs->dims[0] + 1, ny = gs->dims[1] + 1, nz = gs->dims[2] + 1;
     const int64_t npts = (int64_t)nx * ny * nz;
     const size_t node_bytes = sizeof(float) * 8 * (size_t)npts;
-    CEG_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CEG_CK(acquire_stream(&h->stream));
     // layout unless the caller asked otherwise: 2x2x2-node bricks once the grid no longer fits the L2, plain node
     // records below.  Measured on B200 (10^7 random queries): 34 MB grid NODE 0.384 / BLOCK 0.396 ms; 270 MB grid
     // NODE 0.700 / BLOCK 0.627 / PAIR 1.12 / QUAD 1.42 / CELL 1.57 ms; 907 MB grid NODE 1.359 / BLOCK 1.356 ms; 4 GB
@@ -1127,27 +1143,31 @@ static int grid_upload_impl(int32_t device, const ceg_cell_t* unitcell, const ce
     if (layout < 0) layout = (node_bytes > ((size_t)96 << 20) && node_bytes < ((size_t)1536 << 20)) ? LAYOUT_BLOCK : LAYOUT_NODE;
     {
         DevBuf tmp, nodes;
-        DevBuf& node_dst = (layout == LAYOUT_NODE) ? h->d_nodes : nodes;
-        CEG_CK(node_dst.reserve(node_bytes));
-        const float* src = grid;
-        if (!from_device) {
+        const bool direct = (layout == LAYOUT_NODE || layout == LAYOUT_BLOCK);    // one pass straight into the final layout
+        DevBuf& node_dst = direct ? h->d_nodes : nodes;
+        const size_t bricks = (size_t)((nx + 1) / 2) * ((ny + 1) / 2) * ((nz + 1) / 2);
+        CEG_CK(node_dst.reserve(layout == LAYOUT_BLOCK ? sizeof(Rec8) * 8 * bricks : node_bytes));
+        GridSource S;
+        memset(&S, 0, sizeof S);
+        if (parts) {
+            S = *parts;
+            CEG_CK(cudaDeviceSynchronize());     // the caller's producers (any stream) have finished writing the parts
+        } else if (!from_device) {
             CEG_CK(tmp.reserve(node_bytes));
             CEG_CK(cudaMemcpyAsync(tmp.p, grid, node_bytes, cudaMemcpyHostToDevice, h->stream));
-            src = tmp.as<float>();
+            S.whole = tmp.as<float>();
         } else {
+            S.whole = grid;
             CEG_CK(cudaDeviceSynchronize());     // the caller's producer (any stream) has finished writing the grid
         }
         const int blocks = (int)std::min<int64_t>((npts + 255) / 256, sm_count_here() * 32);
-        relayout_nodes_kernel<<<blocks, 256, 0, h->stream>>>(src, node_dst.as<Rec8>(), npts, scale);
+        if (layout == LAYOUT_BLOCK)
+            relayout_nodes_kernel<true><<<blocks, 256, 0, h->stream>>>(S, node_dst.as<Rec8>(), nx, ny, nz, scale);
+        else
+            relayout_nodes_kernel<false><<<blocks, 256, 0, h->stream>>>(S, node_dst.as<Rec8>(), nx, ny, nz, scale);
         count_launch();
         CEG_CK(cudaGetLastError());
-        if (layout == LAYOUT_BLOCK) {
-            const size_t bricks = (size_t)((nx + 1) / 2) * ((ny + 1) / 2) * ((nz + 1) / 2);
-            CEG_CK(h->d_nodes.reserve(sizeof(Rec8) * 8 * bricks));
-            block_records_kernel<<<sm_count_here() * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz);
-            count_launch();
-            CEG_CK(cudaGetLastError());
-        } else if (layout != LAYOUT_NODE) {
+        if (!direct) {
             const int corners = (layout == LAYOUT_PAIR) ? 2 : (layout == LAYOUT_QUAD) ? 4 : 8;
             CEG_CK(h->d_nodes.reserve(node_bytes * corners));
             expand_records_kernel<<<sm_count_here() * 32, 256, 0, h->stream>>>(nodes.as<Rec8>(), h->d_nodes.as<Rec8>(), nx, ny, nz, corners);
@@ -1160,6 +1180,29 @@ static int grid_upload_impl(int32_t device, const ceg_cell_t* unitcell, const ce
     h->g.layout = layout;
     *out = h.release();
     return 0;
+}
+
+// x-slabs of a sharded build, as they sit on this device after an all-gather, straight into an interpolation handle:
+// part r holds planes [i0[r], i1[r]) in a [8][stride[r]][ny][nz] buffer (stride >= i1 - i0: padded gathers).
+extern "C" int ceg_grid_upload_parts_dev(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, int32_t n_parts,
+                                         const float* const* d_parts, const int32_t* i0, const int32_t* i1, const int64_t* stride,
+                                         double scale, int32_t is_vdw, ceg_grid_h* out) {
+    if (n_parts <= 0 || n_parts > MAX_GRID_PARTS || !d_parts || !i0 || !i1 || !gs)
+        return fail("ceg_grid_upload_parts_dev: between 1 and 16 parts expected");
+    if (!(scale > 0.0)) return fail("ceg_grid_upload_parts_dev: scale must be positive");
+    GridSource S;
+    memset(&S, 0, sizeof S);
+    S.n_parts = n_parts;
+    int next = 0;
+    for (int r = 0; r < n_parts; r++) {
+        if (!d_parts[r] || i0[r] != next || i1[r] <= i0[r]) return fail("ceg_grid_upload_parts_dev: parts must tile the x range in order");
+        S.part[r] = d_parts[r]; S.i0[r] = i0[r]; S.i1[r] = i1[r];
+        S.stride[r] = stride ? stride[r] : (int64_t)(i1[r] - i0[r]);
+        if (S.stride[r] < i1[r] - i0[r]) return fail("ceg_grid_upload_parts_dev: stride shorter than the part");
+        next = i1[r];
+    }
+    if (next != gs->dims[0] + 1) return fail("ceg_grid_upload_parts_dev: parts do not cover the grid");
+    return grid_upload_impl(device, unitcell, gs, nullptr, true, scale, is_vdw, out, &S);
 }
 
 extern "C" int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* grid,
@@ -1259,7 +1302,7 @@ static int interpolate_pipelined(int n_grids, ceg_grid_s* const* grids, int64_t 
     ceg_grid_s* h0 = grids[0];
     std::lock_guard<std::mutex> lk(h0->mu);
     if (use_device(h0->device)) return 1;
-    if (!h0->stream2) CEG_CK(cudaStreamCreateWithFlags(&h0->stream2, cudaStreamNonBlocking));
+    if (!h0->stream2) CEG_CK(acquire_stream(&h0->stream2));
     const int64_t chunk = std::min<int64_t>(n, 1 << 20);
     for (int b = 0; b < 2; b++) {
         CEG_CK(h0->d_xyz[b].reserve(sizeof(double) * 3 * chunk));
@@ -1309,8 +1352,14 @@ extern "C" int ceg_grid_pair_create(ceg_grid_h vdw, ceg_grid_h coulomb, ceg_grid
     for (ceg_grid_s* g : {vdw, coulomb})
         if (g->g.layout != LAYOUT_NODE && g->g.layout != LAYOUT_BLOCK)
             return fail("ceg_grid_pair_create: grids must use the node or brick layout");
-    if (memcmp(&vdw->g.gs, &coulomb->g.gs, sizeof(GridSpecDev)) != 0 || memcmp(&vdw->g.uc, &coulomb->g.uc, sizeof(CellDev)) != 0)
-        return fail("ceg_grid_pair_create: the two grids do not share one GridCoordinatesSetup");
+    {   // field by field (the structs carry padding)
+        const GridSpecDev &a = vdw->g.gs, &b = coulomb->g.gs;
+        const CellDev &ca = vdw->g.uc, &cb = coulomb->g.uc;
+        bool same = memcmp(a.dims, b.dims, sizeof a.dims) == 0 && memcmp(a.size, b.size, sizeof a.size) == 0 &&
+                    memcmp(a.shift, b.shift, sizeof a.shift) == 0 && memcmp(a.delta, b.delta, sizeof a.delta) == 0 &&
+                    memcmp(ca.mat, cb.mat, sizeof ca.mat) == 0 && memcmp(ca.invmat, cb.invmat, sizeof ca.invmat) == 0;
+        if (!same) return fail("ceg_grid_pair_create: the two grids do not share one GridCoordinatesSetup");
+    }
     if (use_device(vdw->device)) return 1;
     std::unique_ptr<ceg_gridpair_s> h(new ceg_gridpair_s);
     h->device = vdw->device;
@@ -1458,6 +1507,58 @@ extern "C" int ceg_ewald_create(int32_t device, const double* invmat, const int3
                 n_k, d_kf.as<double>(), d_S.as<double2>(), h->d_ksf.as<double2>());
             count_launch();
             CEG_CK(cudaGetLastError());
+        }
+        CEG_CK(cudaStreamSynchronize(h->stream));
+    }
+    *out = h.release();
+    return 0;
+}
+
+// The same handle from a structure factor that already exists on the host (EwaldFramework.StoreRigidChargeFramework of
+// an unchanged initialize_ewald, ewald.jl:264-271): nothing is summed on the device.
+extern "C" int ceg_ewald_create_from_sf(int32_t device, const double* invmat, const int32_t kmax[3], int64_t n_k,
+                                        const int32_t* kvec, const double* kfactor, const double* S_f_reim, ceg_ewald_h* out) {
+    if (!invmat || !kmax || !out || n_k < 0) return fail("ceg_ewald_create_from_sf: bad argument");
+    if (n_k > 0 && (!kvec || !kfactor || !S_f_reim)) return fail("ceg_ewald_create_from_sf: null k-list");
+    for (int64_t k = 0; k < n_k; k++)
+        if (kvec[3 * k] < 0 || kvec[3 * k] > kmax[0] || std::abs(kvec[3 * k + 1]) > kmax[1] || std::abs(kvec[3 * k + 2]) > kmax[2])
+            return fail("ceg_ewald_create_from_sf: k-vector outside kmax");
+    if (use_device(device)) return 1;
+    std::unique_ptr<ceg_ewald_s> h(new ceg_ewald_s);
+    h->device = device;
+    memcpy(h->invmat, invmat, sizeof h->invmat);
+    for (int d = 0; d < 3; d++) h->kmax[d] = kmax[d];
+    h->n_k = n_k;
+    CEG_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CEG_CK(h->d_kv.reserve(sizeof(KVecDev) * std::max<int64_t>(1, n_k)));
+    if (n_k > 0) {
+        std::vector<KVecDev> kv((size_t)n_k);
+        std::vector<double2> ksf((size_t)n_k);
+        const int nz = 2 * kmax[2] + 1, ny = 2 * kmax[1] + 1;
+        std::vector<RowDev> rows((size_t)ny * nz, RowDev{0, 0, 0});
+        bool ok = true;
+        h->sum_kf = 0.0;
+        for (int64_t k = 0; k < n_k; k++) {
+            kv[k].kf = kfactor[k]; kv[k].sf_re = S_f_reim[2 * k]; kv[k].sf_im = S_f_reim[2 * k + 1];
+            kv[k].ix = kvec[3 * k]; kv[k].jy = kvec[3 * k + 1]; kv[k].jz = kvec[3 * k + 2]; kv[k]._pad = 0;
+            ksf[k] = make_double2(kfactor[k] * S_f_reim[2 * k], kfactor[k] * S_f_reim[2 * k + 1]);
+            h->sum_kf += kfactor[k];
+            if (ok) {
+                RowDev& r = rows[(size_t)(kvec[3 * k + 1] + kmax[1]) * nz + (kvec[3 * k + 2] + kmax[2])];
+                if (r.count == 0) { r.ix0 = kvec[3 * k]; r.count = 1; r.offset = k; }
+                else if (k == r.offset + r.count && kvec[3 * k] == r.ix0 + r.count) r.count++;
+                else ok = false;
+            }
+        }
+        h->rows_ok = ok;
+        CEG_CK(h->d_kf.reserve(sizeof(double) * n_k));
+        CEG_CK(cudaMemcpyAsync(h->d_kv.p, kv.data(), sizeof(KVecDev) * n_k, cudaMemcpyHostToDevice, h->stream));
+        CEG_CK(cudaMemcpyAsync(h->d_kf.p, kfactor, sizeof(double) * n_k, cudaMemcpyHostToDevice, h->stream));
+        if (ok) {
+            CEG_CK(h->d_rows.reserve(sizeof(RowDev) * rows.size()));
+            CEG_CK(h->d_ksf.reserve(sizeof(double2) * n_k));
+            CEG_CK(cudaMemcpyAsync(h->d_rows.p, rows.data(), sizeof(RowDev) * rows.size(), cudaMemcpyHostToDevice, h->stream));
+            CEG_CK(cudaMemcpyAsync(h->d_ksf.p, ksf.data(), sizeof(double2) * n_k, cudaMemcpyHostToDevice, h->stream));
         }
         CEG_CK(cudaStreamSynchronize(h->stream));
     }

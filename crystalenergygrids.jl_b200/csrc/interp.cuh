@@ -49,21 +49,52 @@ struct alignas(32) Rec8 {
     float4 lo, hi;         // f, fx, fy, fz | fxy, fxz, fyz, fxyz
 };
 
-// [8][npts] -> [npts][8].  `scale` != 1 applies parse_grid's unit conversion (grids.jl:78: Float32(value * GRID_TO_KELVIN),
-// the product formed in double) to a grid that is still in `.grid` units, as left on the device by ceg_grid_build_dev.
-__global__ void __launch_bounds__(256) relayout_nodes_kernel(const float* __restrict__ src, Rec8* __restrict__ dst,
-                                                             int64_t npts, double scale) {
+// Source of a re-layout: one [8][nx][ny][nz] array, or the x-slabs of a sharded build as they sit after an all-gather
+// (part r: planes [i0[r], i1[r]) in a [8][stride[r]][ny][nz] buffer) — the full grid is then never assembled.
+constexpr int MAX_GRID_PARTS = 16;
+struct GridSource {
+    int n_parts;                         // 0: `whole`
+    const float* whole;
+    const float* part[MAX_GRID_PARTS];
+    int i0[MAX_GRID_PARTS], i1[MAX_GRID_PARTS];
+    int64_t stride[MAX_GRID_PARTS];      // planes allocated per channel in the part's buffer
+};
+
+// [8][npts] -> 32-byte node records, written straight to their place in the device layout: node-major (BLOCK = false)
+// or 2x2x2-node bricks (BLOCK = true; slots beyond an odd-sized grid stay unwritten and are never read).  `scale` != 1
+// applies parse_grid's unit conversion (grids.jl:78: Float32(value * GRID_TO_KELVIN), the product formed in double) to a
+// grid that is still in `.grid` units, as left on the device by ceg_grid_build_dev.
+template <bool BLOCK>
+__global__ void __launch_bounds__(256) relayout_nodes_kernel(const GridSource S, Rec8* __restrict__ dst, int nx, int ny, int nz,
+                                                             double scale) {
+    const int64_t plane = (int64_t)ny * nz, npts = (int64_t)nx * plane;
     for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < npts; n += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(n / plane);
+        const int64_t rem = n - (int64_t)x * plane;
+        const float* src = S.whole + n;
+        int64_t cstride = npts;
+        if (S.n_parts > 0) {
+            int r = 0;
+            while (r + 1 < S.n_parts && x >= S.i1[r]) r++;
+            src = S.part[r] + (int64_t)(x - S.i0[r]) * plane + rem;
+            cstride = S.stride[r] * plane;
+        }
         float v[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const float x = src[c * npts + n];
-            v[c] = scale == 1.0 ? x : (float)xmul((double)x, scale);
+            const float f = src[c * cstride];
+            v[c] = scale == 1.0 ? f : (float)xmul((double)f, scale);
         }
-        Rec8 r;
-        r.lo = make_float4(v[0], v[1], v[2], v[3]);
-        r.hi = make_float4(v[4], v[5], v[6], v[7]);
-        dst[n] = r;
+        Rec8 r8;
+        r8.lo = make_float4(v[0], v[1], v[2], v[3]);
+        r8.hi = make_float4(v[4], v[5], v[6], v[7]);
+        int64_t d = n;
+        if (BLOCK) {
+            const int y = (int)(rem / nz), z = (int)(rem - (int64_t)y * nz);
+            const int64_t nby = (ny + 1) >> 1, nbz = (nz + 1) >> 1;
+            d = ((((int64_t)(x >> 1) * nby + (y >> 1)) * nbz + (z >> 1)) << 3) + (((x & 1) * 2 + (y & 1)) * 2 + (z & 1));
+        }
+        dst[d] = r8;
     }
 }
 
@@ -81,23 +112,6 @@ __global__ void __launch_bounds__(256) expand_records_kernel(const Rec8* __restr
         const int iz = c & 1, iy = (c >> 1) & 1, ix = (c >> 2) & 1;   // PAIR: iz only; QUAD: iy, iz
         const int xx = min(x + ix, nx - 1), yy = min(y + iy, ny - 1), zz = min(z + iz, nz - 1);
         dst[t] = nodes[((int64_t)xx * ny + yy) * nz + zz];
-    }
-}
-
-// NODE -> BLOCK: brick (bx,by,bz) holds nodes (2bx+ix, 2by+iy, 2bz+iz) at slot (ix*2+iy)*2+iz; bricks on the upper
-// faces of an odd-sized grid are padded with copies of the last node (never read).
-__global__ void __launch_bounds__(256) block_records_kernel(const Rec8* __restrict__ nodes, Rec8* __restrict__ dst,
-                                                            int nx, int ny, int nz) {
-    const int nby = (ny + 1) / 2, nbz = (nz + 1) / 2, nbx = (nx + 1) / 2;
-    const int64_t total = (int64_t)nbx * nby * nbz * 8;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(t & 7);
-        int64_t b = t >> 3;
-        const int bz = (int)(b % nbz); b /= nbz;
-        const int by = (int)(b % nby);
-        const int bx = (int)(b / nby);
-        const int x = min(2 * bx + ((c >> 2) & 1), nx - 1), y = min(2 * by + ((c >> 1) & 1), ny - 1), z = min(2 * bz + (c & 1), nz - 1);
-        dst[t] = nodes[((int64_t)x * ny + y) * nz + z];
     }
 }
 

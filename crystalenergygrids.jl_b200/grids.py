@@ -139,6 +139,17 @@ class EnergyGrid:
         if h is not None:
             _lib.grid_pair_free(h)
 
+    @staticmethod
+    def from_device_parts(csetup, num_unitcell, ewald_precision: float, d_parts, slabs, strides=None, device: int = 0,
+                          in_kelvin: bool = False):
+        """As from_device, from the x-slabs of a sharded build gathered onto this device (part r = planes
+        slabs[r] = (i0, i1) in a [8][strides[r]][ny][nz] buffer): the full `.grid`-order array is never assembled."""
+        g = EnergyGrid(csetup, tuple(num_unitcell), float(ewald_precision), True, np.zeros((0, 0, 0, 0), dtype=np.float32), device)
+        g._handle = _lib.grid_upload_parts_dev(device, unitcell_struct(csetup.cell), _lib.make_gridspec(csetup), d_parts,
+                                               [a for a, _ in slabs], [b for _, b in slabs], strides,
+                                               1.0 if in_kelvin else GRID_TO_KELVIN, g.is_vdw)
+        return g
+
     def close(self):
         self.wait()
         self.unpair()

@@ -197,6 +197,12 @@ int ceg_grid_upload(int32_t device, const ceg_cell_t* unitcell, const ceg_gridsp
  * grid already in K untouched.  The source may be freed once the call returns. */
 int ceg_grid_upload_dev(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* d_grid,
                         double scale, int32_t is_vdw, ceg_grid_h* out);
+/* The same from the x-slabs of a sharded build as they sit on `device` after an all-gather (NCCL, MPI, peer copies):
+ * part r holds planes [i0[r], i1[r]) in a [8][stride[r]][ny][nz] f32 buffer (stride = NULL: stride[r] = i1[r] - i0[r]);
+ * the parts tile 0..nx in order.  The full grid is never assembled: one pass reads the parts and writes the records. */
+int ceg_grid_upload_parts_dev(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, int32_t n_parts,
+                              const float* const* d_parts, const int32_t* i0, const int32_t* i1, const int64_t* stride,
+                              double scale, int32_t is_vdw, ceg_grid_h* out);
 int ceg_grid_free(ceg_grid_h h);
 /* Device record layout used by subsequent ceg_grid_upload calls: 0 = node records (1x memory),
  * 1 = (y,z) quads (4x), 2 = whole 8-corner cells (8x, one aligned 256 B block per query),
@@ -244,6 +250,10 @@ int ceg_ewald_create(int32_t device, const double* invmat /* supercell inverse, 
                      const int32_t kmax[3], int64_t n_k, const int32_t* kvec, const double* kfactor,
                      int64_t n_sites, const double* frac /* n_sites x 3 */, const double* charge,
                      ceg_ewald_h* out, double* S_f_reim);
+/* The same handle from a structure factor computed elsewhere (the StoreRigidChargeFramework of an unchanged
+ * initialize_ewald): S_f_reim (n_k x 2) is taken as given. */
+int ceg_ewald_create_from_sf(int32_t device, const double* invmat, const int32_t kmax[3], int64_t n_k, const int32_t* kvec,
+                             const double* kfactor, const double* S_f_reim, ceg_ewald_h* out);
 int ceg_ewald_free(ceg_ewald_h h);
 int ceg_ewald_reciprocal(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms,
                          const double* xyz /* n_pos x n_atoms x 3 Cartesian Å */, const double* q /* n_atoms */,

@@ -7,9 +7,13 @@
 #   create_grid_vdw        grids.jl:137-157      -> ceg_probe_create + ceg_grid_build
 #   create_grid_coulomb    grids.jl:159-185      -> ceg_probe_create + ceg_grid_build
 #   interpolate_grid       grids.jl:212-273      -> ceg_grid_upload (once per grid) + ceg_interpolate
-#   energy_point/energy_grid  grids.jl:311-424   -> ceg_energy_points
-#   initialize_ewald (S_f) ewald.jl:264-271      -> ceg_ewald_create
-#   compute_ewald(ctx)     ewald.jl:555-577      -> ceg_ewald_reciprocal
+#   energy_point(setup, positions, ctx)   grids.jl:311-327   -> ceg_energy_points   (METHOD OVERRIDE, same signature)
+#   energy_grid(setup, step, num_rotate)  grids.jl:346-424   -> ceg_energy_lattice  (METHOD OVERRIDE for CrystalEnergySetup)
+#   compute_ewald(ctx, skip)              ewald.jl:555-577   -> ceg_ewald_reciprocal (METHOD OVERRIDE)
+#   initialize_ewald                      ewald.jl:195-281   -> unchanged host code; its EwaldFramework gets a device handle on
+#                                                               first use (ceg_ewald_create_from_sf), or — with the three-line patch
+#                                                               of INTEGRATION.md §2 — S_f itself comes from ceg_ewald_create
+#   setup_RASPA's grid hand-off           raspa.jl:420-439   -> create_grids_resident (ceg_grid_build_dev -> ceg_grid_upload_dev)
 #   single_contribution_ewald  ewald.jl:704-738  -> ceg_ewald_single_contribution   (batched over trial placements)
 #   single_contribution_vdw    energy.jl:397-427 -> ceg_guest_energy                (batched over trial placements)
 #   parse_blockfile / BlockFile(g)  coordinates.jl:112-167, grids.jl:188-204 -> ceg_block_from_spheres / _values
@@ -29,7 +33,10 @@ using ..CrystalEnergyGrids
 using ..CrystalEnergyGrids: ForceField, InteractionRule, InteractionRuleSum, FF, ProbeSystem, EnergyGrid,
     GridCoordinatesSetup, EwaldFramework, EwaldContext, CellMatrix, BlockFile, CrystalEnergySetup,
     prepare_periodic_distance_computations, find_supercell, initialize_ewald, _setup_grid_common,
-    _create_grid_common, GRID_TO_KELVIN, COULOMBIC_CONVERSION_FACTOR, TÅ
+    _create_grid_common, GRID_TO_KELVIN, COULOMBIC_CONVERSION_FACTOR, TÅ, TK, isdefined_ewald, get_rotation_matrices,
+    ChangePositionSystem, bounding_box, hash_string, lebedev_num, scratchspace
+using LinearAlgebra: norm
+using Serialization: serialize, deserialize
 using StaticArrays, Unitful, UnitfulAtomic
 
 const libceg = get(ENV, "LIBCEG_CUDA", "libceg_cuda.so")
@@ -348,6 +355,207 @@ function interpolate_sweep(g::EnergyGrid, n::Integer, seed::Integer; first=0, n_
         (Ptr{Cvoid}, Int64, Int64, UInt64, Ptr{Cdouble}, Ref{Cdouble}, Ref{Cdouble}, Ref{Int64}, Int64, Ptr{Cdouble}, Ref{Cfloat}),
         handle(g), first, n, seed, mat, s, mn, nb, length(keep), keep, ms))
     (sum=s[], min=mn[], n_blocked=nb[], keep=keep, kernel_ms=ms[])
+end
+
+# =====================================================================================================================
+# Method overrides with the reference's own signatures: after `include("CEGCuda.jl")` the calls below run on the GPU.
+# =====================================================================================================================
+
+# ---- device handles of the Julia objects (created on first use, keyed by object identity) ---------------------------------
+const EWALD_HANDLES = IdDict{Vector{ComplexF64},Ptr{Cvoid}}()       # EwaldFramework.StoreRigidChargeFramework -> ceg_ewald_h
+const BLOCK_HANDLES = IdDict{Any,Ptr{Cvoid}}()                      # BlockFile.block -> ceg_block_h
+const HANDLE_LOCK = ReentrantLock()
+
+function _kvec(kspace)
+    kvec = Int32[]
+    for (jy, jz, jxrange, _) in kspace.kindices, ix in jxrange
+        append!(kvec, (ix, jy, jz))
+    end
+    kvec
+end
+
+# EwaldFramework of an unchanged initialize_ewald (ewald.jl:195-281) -> device handle; nothing is re-summed
+function handle(ef::EwaldFramework; device=0)
+    iszero(ef.α) && return C_NULL
+    lock(HANDLE_LOCK) do
+        get!(EWALD_HANDLES, ef.StoreRigidChargeFramework) do
+            out = Ref{Ptr{Cvoid}}(C_NULL)
+            invmat = collect(Float64.(ustrip.(u"Å^-1", ef.invmat)))
+            check(ccall((:ceg_ewald_create_from_sf, libceg), Cint,
+                (Int32, Ptr{Cdouble}, Ptr{Int32}, Int64, Ptr{Int32}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Ptr{Cvoid}}),
+                device, invmat, Int32[ef.kspace.ks...], ef.kspace.num_kvecs, _kvec(ef.kspace), ef.kfactors,
+                reinterpret(Float64, ef.StoreRigidChargeFramework), out))
+            out[]
+        end
+    end
+end
+
+# BlockFile (coordinates.jl:83-101) -> device mask; C_NULL for an empty one
+function handle(b::BlockFile; device=0)
+    b.empty && return C_NULL
+    lock(HANDLE_LOCK) do
+        get!(BLOCK_HANDLES, b.block) do
+            cs = b.csetup
+            cell = CegCell(SMatrix{3,3,Float64,9}(ustrip.(u"Å", cs.cell.mat)), SMatrix{3,3,Float64,9}(ustrip.(u"Å^-1", cs.cell.invmat)))
+            mask = UInt8.(permutedims(b.block, (3, 2, 1)))             # (a,b,c) BitArray -> [a][b][c] bytes
+            out = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:ceg_block_upload, libceg), Cint, (Int32, Ref{CegCell}, Ref{CegGridSpec}, Ptr{UInt8}, Ref{Ptr{Cvoid}}),
+                        device, cell, CegGridSpec(cs), mask, out))
+            out[]
+        end
+    end
+end
+
+_gridhandle(g::EnergyGrid) = (g.ewald_precision == -Inf || isempty(g.grid)) ? C_NULL : handle(g)
+
+# static part of compute_ewald for ONE molecule of the setup (ewald.jl:484-531): energy_net_charges, static_contribution
+function _ewald_constants(setup::CrystalEnergySetup)
+    ctx = EwaldContext(setup.ewald, ((setup.molecule,),))
+    isdefined_ewald(ctx) || return 0.0, 0.0
+    ustrip(u"K", ctx.energy_net_charges), ustrip(u"K", ctx.static_contribution[])
+end
+
+function _handles(setup::CrystalEnergySetup)
+    for g in setup.grids
+        isnan(g.ewald_precision) && error("Invalid grid cannot be interpolated!")
+    end
+    vdw = Ptr{Cvoid}[_gridhandle(g) for g in setup.grids]
+    hascoulomb = setup.coulomb.ewald_precision != -Inf
+    coul = hascoulomb ? _gridhandle(setup.coulomb) : C_NULL
+    ew = hascoulomb ? handle(setup.ewald) : C_NULL
+    vdw, coul, ew, handle(setup.block)
+end
+
+"""
+    energy_point(setup::CrystalEnergySetup, positions, ctx=nothing)          # grids.jl:311-327, same contract
+
+One placement through the library's latency path (a single kernel launch).  `ctx` is accepted for signature
+compatibility; the reciprocal term is evaluated from `positions` on the device (equal to
+`move_one_system!(ctx, 1, positions); compute_ewald(ctx)`), so `ctx` is left untouched.
+"""
+function CrystalEnergyGrids.energy_point(setup::CrystalEnergySetup, positions, ctx=nothing)
+    n = length(setup.atomsidx)
+    pos = Array{Float64,3}(undef, 3, n, 1)
+    for i in 1:n, c in 1:3
+        pos[c, i, 1] = ustrip(u"Å", positions[i][c])
+    end
+    vdw, coul, ew, blk = _handles(setup)
+    enc, stat = _ewald_constants(setup)
+    v, c = energy_points(vdw, coul, ew, blk, setup.atomsidx, setup.charges, pos, enc * u"K", stat * u"K")
+    v[1] == 1e100 && return (1e100u"K", 0.0u"K")
+    (v[1] * u"K", c[1] * u"K")
+end
+
+"""
+    energy_grid(setup::CrystalEnergySetup, step, num_rotate=40)             # grids.jl:346-424, same contract
+
+Same lattice ((iA-1)stepA + (iB-1)stepB + (iC-1)stepC, left-to-right sum), same Lebedev orientations
+(`get_rotation_matrices`, unchanged lebedev.jl), same scratch-space cache; the numA x numB x numC x n_rot
+`energy_point` evaluations run as one batched call with the lattice generated on the device.
+(`num_rotate < 0`, random offsets, and MonteCarloSetup inputs keep the original Julia method.)
+"""
+function CrystalEnergyGrids.energy_grid(setup::CrystalEnergySetup, step, num_rotate=40)
+    num_rotate < 0 && return invoke(CrystalEnergyGrids.energy_grid, Tuple{Any,Any,Any}, setup, step, num_rotate)
+    molecule = setup.molecule
+    store = string(hash_string(setup), '-', ustrip(u"Å", step), '-', lebedev_num(molecule, num_rotate))
+    path = joinpath(scratchspace, store)
+    isfile(path) && return deserialize(path)::Array{Float64,4}
+    __pos = position(molecule) / u"Å"
+    axes = bounding_box(setup.framework)
+    nums = ntuple(d -> floor(Int, norm(axes[d]) / step) + 1, 3)
+    steps = Matrix{Float64}(undef, 3, 3)                       # column d = axis_d / num_d (Å)
+    for d in 1:3
+        steps[:, d] .= ustrip.(u"Å", axes[d] ./ nums[d])
+    end
+    rots = (num_rotate == 0 || length(molecule) == 1) ? [one(SMatrix{3,3,Float64,9})] : first(get_rotation_matrices(molecule, num_rotate))
+    rotpos = Array{Float64,3}(undef, 3, length(__pos), length(rots))
+    for (k, r) in enumerate(rots), (i, p) in enumerate(__pos)
+        rotpos[:, i, k] .= r * SVector{3,Float64}(p)
+    end
+    vdw, coul, ew, blk = _handles(setup)
+    enc, stat = _ewald_constants(setup)
+    raw = energy_lattice(vdw, coul, ew, blk, nums, steps, rotpos, setup.atomsidx, setup.charges, enc * u"K", stat * u"K")
+    allvals = permutedims(raw, (4, 3, 2, 1))                   # (numC,numB,numA,n_rot) -> (n_rot,numA,numB,numC)
+    serialize(path, allvals)
+    allvals
+end
+
+"""
+    compute_ewald(ctx::EwaldContext, skipcontribution=0)                     # ewald.jl:555-577, same contract
+
+The positions of the context's charges are read back from its phase tables (`Eikx[2,l] = e^{2πi f_x}`,
+`Eiky[ky+2,l]`, `Eikz[kz+2,l]`, ewald.jl:69-86,350-364): S_a(k) only depends on the fractional coordinates modulo 1.
+"""
+function CrystalEnergyGrids.compute_ewald(ctx::EwaldContext, skipcontribution=0)
+    isdefined_ewald(ctx) || return 0.0u"K"
+    Eikx, Eiky, Eikz = ctx.Eiks
+    _, ky, kz = ctx.eframework.kspace.ks
+    keep = [l for (l, (ij, _)) in enumerate(ctx.atoms) if ctx.speciesof[ij] != skipcontribution]
+    isempty(keep) && return 2 * ctx.energy_net_charges + ctx.static_contribution[]
+    mat = SMatrix{3,3,Float64,9}(ustrip.(u"Å", ctx.eframework.mat))
+    pos = Array{Float64,3}(undef, 3, length(keep), 1)
+    q = Vector{Float64}(undef, length(keep))
+    for (m, l) in enumerate(keep)
+        f = SVector{3,Float64}(angle(Eikx[2, l]), angle(Eiky[ky+2, l]), angle(Eikz[kz+2, l])) ./ (2π)
+        pos[:, m, 1] .= mat * f
+        ij, k = ctx.atoms[l]
+        q[m] = ustrip(u"e_au", ctx.allcharges[ctx.speciesof[ij]][k])
+    end
+    reciprocal(handle(ctx.eframework), pos, q, ctx.energy_net_charges, ctx.static_contribution[])[1] * u"K"
+end
+
+# ---- setup_RASPA's hand-off without the file round trip (raspa.jl:420-439) ---------------------------------------------
+# Build the missing grids of a setup in one fused pass, keep them on the device, return EnergyGrid objects whose handles
+# are already resident (ceg_grid_build_dev -> ceg_grid_upload_dev applies parse_grid's conversion, grids.jl:78) and
+# write the `.grid` files from one downloaded copy on a background task.  `retrieve_or_create_grid` then only needs
+#     haskey(RESIDENT, grid_path) && return RESIDENT[grid_path]
+# as its first line.
+const RESIDENT = Dict{String,EnergyGrid}()
+
+function create_grids_resident(framework, forcefield::ForceField, spacing::TÅ, atoms::Vector{Symbol}, paths::Vector{String},
+                               ewald::Union{Nothing,EwaldFramework}, coulomb_path::String=""; device=0)
+    cset, num_unitcell = _setup_grid_common(framework, spacing, forcefield.cutoff)
+    probe = ProbeSystem(framework, forcefield)
+    idx = [forcefield.sdict[Symbol(CrystalEnergyGrids.get_atom_name(a))] for a in atoms]
+    withcoul = !(ewald isa Nothing)
+    n = length(idx) + withcoul
+    nz, ny, nx = cset.dims[3] + 1, cset.dims[2] + 1, cset.dims[1] + 1
+    bytes = 8 * nx * ny * nz * sizeof(Cfloat)
+    h = ProbeHandle(probe, idx, withcoul, withcoul ? ustrip(u"Å^-1", ewald.α) : 0.0; device)
+    d = [Ref{Ptr{Cvoid}}(C_NULL) for _ in 1:n]
+    foreach(r -> check(ccall((:ceg_device_malloc, libceg), Cint, (Int32, Int64, Ref{Ptr{Cvoid}}), device, bytes, r)), d)
+    ptrs = Ptr{Cfloat}[Ptr{Cfloat}(r[]) for r in d]
+    λv = inv(GRID_TO_KELVIN); Tv = GRID_TO_KELVIN * 1e7
+    λc = ustrip(u"K*Å/e_au^2", COULOMBIC_CONVERSION_FACTOR) / GRID_TO_KELVIN; Tc = inv(λc) * 1e7
+    check(ccall((:ceg_grid_build_dev, libceg), Cint,
+        (Ptr{Cvoid}, Ref{CegGridSpec}, Int32, Int32, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Ptr{Cfloat}}, Ptr{Cvoid}),
+        h.ptr, CegGridSpec(cset), 0, nx, λv, Tv, λc, Tc, ptrs, C_NULL))
+    check(ccall((:ceg_device_synchronize, libceg), Cint, (Int32,), device))
+    out = EnergyGrid[]
+    for g in 1:n
+        iscoul = withcoul && g == n
+        prec = iscoul ? ewald.precision : Inf
+        host = Array{Cfloat,4}(undef, nz, ny, nx, 8)                                  # `.grid` units, for the file
+        check(ccall((:ceg_device_download, libceg), Cint, (Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}), device, d[g][], bytes, host))
+        eg = EnergyGrid(cset, num_unitcell, prec, true, Float32.(host .* GRID_TO_KELVIN))   # parse_grid's view (grids.jl:78)
+        lock(GRID_LOCK) do
+            GRID_HANDLES[eg.grid] = handle_from_device(cset, ptrs[g], !iscoul; device)      # resident before any file exists
+        end
+        check(ccall((:ceg_device_free, libceg), Cint, (Ptr{Cvoid},), d[g][]))
+        path = iscoul ? coulomb_path : paths[g]
+        Threads.@spawn begin                                                            # the file, in the reference's byte layout
+            mkpath(dirname(path))
+            open(path, "w") do f
+                _create_grid_common(f, cset, num_unitcell)
+                iscoul && write(f, ewald.precision)
+                write(f, host)
+                write(f, NoUnits.(cset.cell.mat ./ u"Å"))
+            end
+        end
+        RESIDENT[path] = eg
+        push!(out, eg)
+    end
+    out
 end
 
 end # module

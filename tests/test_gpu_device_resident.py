@@ -102,6 +102,25 @@ def test_gather_and_device_build_equal_host_build(cuda_lib):
         ref = ceg.EnergyGrid(cs, (1, 1, 1), prec, True, gK[g])
         assert np.array_equal(ceg.interpolate_grid(on_dev, pos), ceg.interpolate_grid(ref, pos))
         on_dev.close(); ref.close()
+    # the same straight from the parts (ceg_grid_upload_parts_dev), exact and padded strides: no assembled copy
+    import torch
+    for g, prec in enumerate((np.inf, 1e-6)):
+        ref = ceg.EnergyGrid(cs, (1, 1, 1), prec, True, gK[g])
+        want = ceg.interpolate_grid(ref, pos)
+        eg = ceg.EnergyGrid.from_device_parts(cs, (1, 1, 1), prec, [p[2][g] for p in parts], [(p[0], p[1]) for p in parts])
+        assert np.array_equal(ceg.interpolate_grid(eg, pos), want)
+        eg.close()
+        pad = []
+        for a, b, _ in parts:
+            t = torch.full((8, b - a + 3, ny, nz), float("nan"), dtype=torch.float32, device="cuda")
+            t[:, :b - a] = torch.from_numpy(outs[g][:, a:b]).cuda()
+            pad.append(t)
+        eg = ceg.EnergyGrid.from_device_parts(cs, (1, 1, 1), prec, [t.data_ptr() for t in pad], [(p[0], p[1]) for p in parts],
+                                              [t.shape[1] for t in pad])
+        assert np.array_equal(ceg.interpolate_grid(eg, pos), want)
+        eg.close(); ref.close()
+    with pytest.raises(ceg.CegError):       # parts must tile the x range
+        ceg.EnergyGrid.from_device_parts(cs, (1, 1, 1), np.inf, [parts[1][2][0]], [(parts[1][0], parts[1][1])])
     for p in parts:
         for d in p[2]:
             ceg._lib.device_free(d)
