@@ -407,6 +407,9 @@ enum { CLS_NONE = 0, CLS_LJ = 1, CLS_BUCK = 2, CLS_GENERAL = 3 };
 // distance and rsqrt seed of entry e+1 are issued inside the arithmetic block of entry e, 2 = also its 1/r, r and erfcx
 // argument map.  Measured on B200 (C4, round 2): 61.2 / see DESIGN.md / 68.0 ms — with the short dependency chains of
 // this version the carried state costs more (registers, spills) than the hidden latency is worth.
+// Measured and rejected in round 2 (C4, B200): walking the list two entries at a time with both entries' arithmetic in one
+// straight-line block (warp-uniform votes, masked contributions) — two independent chains for the in-order scheduler —
+// 65.3 ms against 61.3 ms: the selects and the wasted lanes cost more than the second chain hides.
 #ifndef CEG_PIPE_DEPTH
 #define CEG_PIPE_DEPTH 0
 #endif
