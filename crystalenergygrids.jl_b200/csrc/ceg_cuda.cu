@@ -1573,9 +1573,11 @@ extern "C" int ceg_ewald_free(ceg_ewald_h h) {
     return 0;
 }
 
+// q_host (optional): the charges on the host; molecules of up to RECIP_QV atoms then carry them by value in the kernel
+// parameters instead of reading d_q
 static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const double* d_xyz, const double* d_q,
                              double enc, double stat, double* d_out, const uint8_t* d_skip, int accumulate,
-                             cudaStream_t s, const double2* d_rest = nullptr) {
+                             cudaStream_t s, const double2* d_rest = nullptr, const double* q_host = nullptr) {
     // Small batches (single Monte-Carlo steps) do not fill the GPU with one thread per placement, and that thread walks
     // the whole k-list alone; the warp-per-placement kernel spreads the k-list over 32 lanes and returns sooner.
     constexpr int64_t ROWS_MIN_PLACEMENTS = 16384;
@@ -1596,6 +1598,7 @@ static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const d
             R.ksf = h->d_ksf_rest.as<double2>();
         }
         R.n_pos = n_pos; R.xyz = d_xyz; R.q = d_q;
+        if (q_host) { R.q = nullptr; for (int a = 0; a < n_atoms; a++) R.qv[a] = q_host[a]; }
         R.energy_net_charges = enc; R.static_contribution = stat;
         R.out = d_out; R.skip = d_skip; R.accumulate = accumulate;
         const unsigned blocks = (unsigned)((n_pos + ROWS_THREADS - 1) / ROWS_THREADS);
@@ -1617,6 +1620,7 @@ static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const d
     P.kv = h->d_kv.as<KVecDev>();
     P.n_pos = n_pos; P.n_atoms = n_atoms;
     P.xyz = d_xyz; P.q = d_q;
+    if (q_host && n_atoms <= RECIP_QV) { P.q = nullptr; for (int a = 0; a < n_atoms; a++) P.qv[a] = q_host[a]; }
     P.energy_net_charges = enc; P.static_contribution = stat;
     P.out = d_out; P.skip = d_skip; P.accumulate = accumulate;
     const size_t per_atom = (size_t)(P.kx + 1) + (2 * P.ky + 1) + (2 * P.kz + 1);
@@ -1640,10 +1644,13 @@ extern "C" int ceg_ewald_reciprocal_dev(ceg_ewald_h h, int64_t n_pos, int32_t n_
     std::lock_guard<std::mutex> lk(h->mu);
     if (use_device(h->device)) return 1;
     cudaStream_t s = (cudaStream_t)stream;
-    CEG_CK(h->d_q.reserve(sizeof(double) * n_atoms));
-    CEG_CK(cudaMemcpyAsync(h->d_q.p, q_host, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, s));
+    if (n_atoms > RECIP_QV) {
+        // large molecules: handle-owned charge buffer — calls with different charges must then share one stream
+        CEG_CK(h->d_q.reserve(sizeof(double) * n_atoms));
+        CEG_CK(cudaMemcpyAsync(h->d_q.p, q_host, sizeof(double) * n_atoms, cudaMemcpyHostToDevice, s));
+    }
     return launch_reciprocal(h, n_pos, n_atoms, d_xyz, h->d_q.as<double>(), energy_net_charges, static_contribution,
-                             d_out, nullptr, 0, s);
+                             d_out, nullptr, 0, s, nullptr, q_host);
 }
 
 extern "C" int ceg_ewald_reciprocal(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, const double* xyz, const double* q,
@@ -1791,6 +1798,7 @@ extern "C" int ceg_guest_env_energy(ceg_guest_h h, int64_t n_trials, int32_t n_a
     CEG_CK(cudaMemcpyAsync(h->d_txyz.p, trial_xyz, sizeof(double) * 3 * n_atoms * n_trials, cudaMemcpyHostToDevice, s));
     GuestParams P;
     P.cell = h->cell; P.cutoff2 = h->cutoff2; P.n_species = h->n_species; P.table = h->d_tab.as<PairEnergyDev>();
+    P.fast_ok = (2.0 * std::sqrt(h->cutoff2) <= perp_width_min(h->cell.mat) * (1.0 - 1e-9)) ? 1 : 0;
     P.n_env = (int)h->n_env; P.env_xyz = h->d_exyz.as<double>(); P.env_species = h->d_esp.as<int>(); P.env_mol = h->d_emol.as<int>();
     P.n_trials = n_trials; P.n_atoms = n_atoms; P.mol_species = h->d_msp.as<int>(); P.skip_mol = skip_mol;
     P.trial_xyz = h->d_txyz.as<double>(); P.out = h->d_out.as<double>();

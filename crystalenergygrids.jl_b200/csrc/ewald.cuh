@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(128) structure_factor_reduce_kernel(int64_t n_
     S_out[2 * k + 1] = im;
 }
 
+constexpr int RECIP_QV = 32;
 struct RecipParams {
     double invmat[9];      // supercell inverse, column-major
     int kx, ky, kz;
@@ -99,7 +100,8 @@ struct RecipParams {
     int64_t n_pos;
     int n_atoms;
     const double* xyz;     // n_pos x n_atoms x 3
-    const double* q;       // n_atoms (device)
+    const double* q;       // n_atoms (device); null: the charges travel by value in qv
+    double qv[RECIP_QV];   // (no handle-owned buffer that a second call on another stream could overwrite)
     double energy_net_charges, static_contribution;
     double* out;
     const double2* rest;   // optional: replaces S_f (single_contribution_ewald's `rest`, ewald.jl:722-729)
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(RECIP_WARPS * 32) reciprocal_kernel(const Reci
                 const double2* ta = tab + a * per_atom;
                 const double2 ex = ta[kv.ix], ey = ta[nx + P.ky + kv.jy], ez = ta[nx + ny + P.kz + kv.jz];
                 const double yzr = ey.x * ez.x - ey.y * ez.y, yzi = ey.x * ez.y + ey.y * ez.x;
-                const double qa = P.q[a];
+                const double qa = P.q ? P.q[a] : P.qv[a];
                 sre += qa * (ex.x * yzr - ex.y * yzi);
                 sim += qa * (ex.x * yzi + ex.y * yzr);
             }
@@ -192,7 +194,8 @@ struct RowsParams {
     double sum_kf;         // sum of the kfactors in list order (single-atom molecules: |S_a|^2 = q^2 for every k)
     int64_t n_pos;
     const double* xyz;
-    const double* q;
+    const double* q;       // device; null: qv
+    double qv[4];
     double energy_net_charges, static_contribution;
     double* out;
     const uint8_t* skip;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) reciprocal_rows_kernel(const Row
         e1z[a] = cis2pi(f[2]);
         ey[a] = cis2pi(red_prod(-(double)P.ky, f[1]));
         const double2 ez = cis2pi(red_prod(-(double)P.kz, f[2]));
-        const double qa = P.q[a];
+        const double qa = P.q ? P.q[a] : P.qv[a];
         ez0[a] = make_double2(qa * ez.x, qa * ez.y);
     }
     double fa = 0.0, aa = 0.0;
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(ROWS_THREADS) reciprocal_rows_kernel(const Row
     }
     // one atom: S_a(k) = q e^{i phase}, so sum_k kf |S_a|^2 = q^2 sum_k kf (equal to the reference's abs2 sum to
     // rounding, 1e-16 relative)
-    if (NA == 1) aa = (P.q[0] * P.q[0]) * P.sum_kf;
+    if (NA == 1) { const double q0 = P.q ? P.q[0] : P.qv[0]; aa = (q0 * q0) * P.sum_kf; }
     // ewald.jl:572-576
     const double E = 2.0 * (fa + P.energy_net_charges) + (aa + P.static_contribution);
     if (P.accumulate) P.out[i] += E; else P.out[i] = E;

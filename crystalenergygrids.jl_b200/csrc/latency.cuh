@@ -6,8 +6,8 @@
 // device address space, so the kernel reads the positions and writes the energies over PCIe itself, and the host
 // waits on a flag the last CTA raises instead of synchronising a stream.
 //
-// One CTA (4 warps) per placement: block test and grid terms with one thread per atom (grids.jl:311-318), then the
-// reciprocal-space term (ewald.jl:555-577) with the k-list spread over the CTA — power tables by sincospi in shared
+// One CTA (16 warps) per placement: grid terms (warp 0, one lane per atom, grids.jl:311-318), block test (warp 1) and the
+// reciprocal-space term (ewald.jl:555-577, the k-list spread over the CTA) run side by side — power tables by sincospi in shared
 // memory as in reciprocal_kernel, fixed-order reduction.
 #pragma once
 #include "ewald.cuh"
@@ -15,8 +15,8 @@
 
 namespace ceg {
 
-constexpr int SMALL_THREADS = 128;
-constexpr int SMALL_MAX_ATOMS = 64;
+constexpr int SMALL_THREADS = 512;
+constexpr int SMALL_MAX_ATOMS = 32;       // one lane per atom for the grid terms and the block test
 
 constexpr int SMALL_INLINE_DOUBLES = 160;   // inputs up to this size travel inside the kernel parameters
 
@@ -43,7 +43,7 @@ struct SmallParams {
 
 __global__ void __launch_bounds__(SMALL_THREADS) energy_points_small_kernel(const __grid_constant__ SmallParams S) {
     extern __shared__ double2 s_tab[];
-    __shared__ double s_v[SMALL_MAX_ATOMS], s_c[SMALL_MAX_ATOMS];
+    __shared__ double s_v[SMALL_MAX_ATOMS], s_c[SMALL_MAX_ATOMS], s_q[SMALL_MAX_ATOMS];
     __shared__ double s_fa[SMALL_THREADS / 32], s_aa[SMALL_THREADS / 32];
     __shared__ int s_blocked;
     const EnergyPointsParams& P = S.E;
@@ -53,20 +53,21 @@ __global__ void __launch_bounds__(SMALL_THREADS) energy_points_small_kernel(cons
     const int* idx = reinterpret_cast<const int*>(in);
     const double* q_in = in + S.n_idx8;
     const double* mol = q_in + P.n_atoms + (int64_t)3 * P.n_atoms * i;
-    __shared__ double s_q[SMALL_MAX_ATOMS];
+    const bool recip = S.has_ewald && S.n_k > 0;
     if (tid == 0) s_blocked = 0;
+    if (tid < P.n_atoms) s_q[tid] = q_in[tid];
     __syncthreads();
-    double p[3] = {0.0, 0.0, 0.0};
-    if (tid < P.n_atoms) {
-        p[0] = mol[3 * tid]; p[1] = mol[3 * tid + 1]; p[2] = mol[3 * tid + 2];
-        s_q[tid] = q_in[tid];
-        if (P.has_block && atom_blocked(P.block, p)) s_blocked = 1;
+    // The three parts of energy_point are independent until the final sum and run side by side: warp 0 interpolates
+    // (one lane per atom), warp 1 tests the blocking mask, every warp then fills the Ewald phase tables.
+    if (warp == 0 && lane < P.n_atoms) {
+        const double p[3] = {mol[3 * lane], mol[3 * lane + 1], mol[3 * lane + 2]};
+        atom_grid_terms(P, idx[lane], s_q[lane], p, s_v[lane], s_c[lane]);
     }
-    __syncthreads();
-    const bool blocked = s_blocked != 0;
-    if (!blocked && tid < P.n_atoms) atom_grid_terms(P, idx[tid], s_q[tid], p, s_v[tid], s_c[tid]);
+    if (warp == 1 && lane < P.n_atoms && P.has_block) {
+        const double p[3] = {mol[3 * lane], mol[3 * lane + 1], mol[3 * lane + 2]};
+        if (atom_blocked(P.block, p)) s_blocked = 1;
+    }
     double fa = 0.0, aa = 0.0;
-    const bool recip = S.has_ewald && !blocked && S.n_k > 0;
     if (recip) {
         const int nx = S.kx + 1, ny = 2 * S.ky + 1, nz = 2 * S.kz + 1;
         const int per_atom = nx + ny + nz;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) energy_points_small_kernel(cons
     __syncthreads();
     if (tid == 0) {
         double vdw = 0.0, coul = 0.0;
-        if (blocked) {
+        if (s_blocked) {
             vdw = 1e100;     // grids.jl:313
         } else {
             for (int a = 0; a < P.n_atoms; a++) { vdw += s_v[a]; coul += s_c[a]; }

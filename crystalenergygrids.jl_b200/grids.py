@@ -238,6 +238,46 @@ def _slabs(n_planes: int, n_parts: int):
     return out
 
 
+def set_gridpoint(raw: np.ndarray, delta, lam: float, thr: float) -> np.ndarray:
+    """grids.jl:118-135 _set_gridpoint! on an array of raw derivatives (..., 8) -> float32 (..., 8)."""
+    r = np.array(raw, dtype=np.float64, copy=True)
+    over = r[..., 0] > thr                      # also catches Inf; NaN falls through
+    r[over, 0] = 2.0 * thr
+    r[over, 1:4] = np.clip(r[over, 1:4], -thr, thr)
+    r[over, 4:] = 0.0
+    d = np.asarray(delta, dtype=np.float64)
+    scale = np.array([1.0, d[0], d[1], d[2], d[0] * d[1], d[0] * d[2], d[1] * d[2], (d[0] * d[1]) * d[2]])
+    return ((r * scale) * lam).astype(np.float32)
+
+
+def _build_grids_literal(inputs, cset, outs, i0, i1, device, raw):
+    """Slab [i0, i1) through the reference's per-pair algorithm on the device (ceg_compute_derivatives: minimum-image
+    search for every supercell atom) — for force fields whose cutoff exceeds half the width of the 12 Å probe supercell
+    (probes.jl:24), which the tiled kernel's unique-image argument does not cover."""
+    nx, ny, nz = cset.nodes
+    lam_v, thr_v = vdw_scaling()
+    lam_c, thr_c = coulomb_scaling()
+    n_grids = len(outs)
+    ps = ProbeSystem(None, None, inputs=inputs, device=device)
+    try:
+        jj, kk = np.meshgrid(np.arange(ny), np.arange(nz), indexing="ij")
+        for i in range(i0, i1):
+            # abc_to_xyz (coordinates.jl:72-76): multiply, divide, add
+            pos = np.stack([np.full(jj.shape, i * cset.size[0] / cset.dims[0] + cset.shift[0]),
+                            jj * cset.size[1] / cset.dims[1] + cset.shift[1],
+                            kk * cset.size[2] / cset.dims[2] + cset.shift[2]], axis=-1).reshape(-1, 3)
+            der = ps.compute_derivatives(pos)                                  # (n_grids, ny*nz, 8)
+            for g in range(n_grids):
+                coul = inputs.want_coulomb and g == n_grids - 1
+                f32 = set_gridpoint(der[g], cset.delta, lam_c if coul else lam_v, thr_c if coul else thr_v)
+                if outs[g] is not None:
+                    outs[g][:, i] = f32.reshape(ny, nz, 8).transpose(2, 0, 1)
+                if raw is not None:
+                    raw[g, :, i - i0] = der[g].reshape(ny, nz, 8).transpose(2, 0, 1)
+    finally:
+        ps.close()
+
+
 def build_grids(framework, forcefield: ForceField, spacing: float, atoms=(), coulomb: bool = False, alpha: float = 0.0,
                 devices=None, xrange=None, want_raw: bool = False, outs=None):
     """Fused construction of the VdW grids of `atoms` and (optionally) the Coulomb real-space
@@ -267,9 +307,20 @@ def build_grids(framework, forcefield: ForceField, spacing: float, atoms=(), cou
     slabs = [(i0 + a, i0 + b) for a, b in _slabs(i1 - i0, len(devices))]
     errors = []
 
+    # the tiled kernel needs 2 * cutoff <= the perpendicular widths of the probe supercell, which is sized for 12 Å
+    # (probes.jl:24) whatever the force field's cutoff: larger cutoffs go through the literal kernel (slow, exact)
+    from .cell import perpendicular_lengths
+    literal = 2.0 * math.sqrt(inputs.cutoff2) > min(perpendicular_lengths(np.asarray(inputs.mat))) * (1.0 + 1e-12)
+
     def work(dev, a, b):
         try:
             if b <= a:
+                return
+            if literal:
+                r = np.empty((n_grids, 8, b - a, ny, nz), dtype=np.float64) if raw is not None else None
+                _build_grids_literal(inputs, cset, outs, a, b, dev, r)
+                if raw is not None:
+                    raw[:, :, a - i0:b - i0] = r
                 return
             ps = ProbeSystem(None, None, inputs=inputs, device=dev)
             try:

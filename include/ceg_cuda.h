@@ -264,6 +264,8 @@ int ceg_ewald_reciprocal(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms,
  *   out = 2 sum_k kf Re(rest conj S_single) + sum_k kf |S_single|^2 */
 int ceg_ewald_single_contribution(ceg_ewald_h h, const double* rest_reim, int64_t n_pos, int32_t n_atoms,
                                   const double* xyz, const double* q, double* out);
+/* (asynchronous on `stream`; the charges of molecules of up to 32 atoms travel by value with the launch, so calls on
+ * different streams never share state; larger molecules use a handle-owned buffer and must then share one stream) */
 int ceg_ewald_reciprocal_dev(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, const double* d_xyz, const double* q_host,
                              double energy_net_charges, double static_contribution, double* d_out, void* stream);
 

@@ -242,3 +242,18 @@ def test_thick_slab_of_a_large_cell_uses_x_windows(cuda_lib):
         for g in range(2):
             assert np.array_equal(thin[g][:, a:b], full[g][:, a:b]), (g, a, b)
     ps.close()
+
+
+def test_cutoff_beyond_the_probe_supercell_uses_the_literal_kernel(cuda_lib, orc):
+    """A force-field cutoff above half the width of the 12 Å probe supercell (probes.jl:24): the reference still builds the
+    grid through its minimum-image search; build_grids routes such slabs through ceg_compute_derivatives + _set_gridpoint!."""
+    from util import assert_close_f64
+    fw, _, species = wl.mfi_shaped()
+    ff14 = wl._lj_forcefield(species, cutoff=14.0)
+    inp = ceg.probe_inputs(fw, ff14, ("C_ch4",))
+    assert 2 * 14.0 > min(ceg.perpendicular_lengths(inp.mat))
+    cset, grids, raw = ceg.build_grids(fw, ff14, 1.2, atoms=("C_ch4",), xrange=(3, 5), want_raw=True)
+    o_outs, o_raw = orc.grid_build(inp, cset, 3, 5, 1, want_f32=True, want_raw=True)
+    assert_close_f64(raw[0], o_raw[0], False, "cutoff 14 raw")
+    lam, thr = ceg.vdw_scaling()
+    assert_f32_grids_match(grids[0][:, 3:5], o_outs[0][:, 3:5], o_raw[0], lam, thr, "cutoff 14 f32")

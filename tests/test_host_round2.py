@@ -1,0 +1,72 @@
+"""Round-2 host logic that needs no GPU: grid-cache naming of customised force fields (raspa.jl:196-204), the
+energy_grid orientation contract (grids.jl:385-390), _set_gridpoint! on arrays (grids.jl:118-135) against the oracle,
+the EnergyGrid host-copy hand-shake, the setup_montecarlo argument checks."""
+import dataclasses
+import threading
+import time
+
+import numpy as np
+import pytest
+
+import ceg_b200 as ceg
+from ceg_b200 import forcefields as FF
+from test_host_raspa import raspa_dir  # noqa: F401  (fixture)
+
+
+def test_customised_forcefield_gets_its_own_grid_cache(raspa_dir):  # noqa: F811
+    ff = ceg.parse_forcefield_RASPA("ToyFF")
+    by_name, _ = ceg.grid_locations("Toy", "ToyFF", ff, ["O_co2"], 0.15, (2, 2, 3))
+    as_object, vd = ceg.grid_locations("Toy", ff, ff, ["O_co2"], 0.15, (2, 2, 3))
+    assert "/ToyFF/Toy/" in by_name
+    assert f"/ToyFF-{ceg.hash_forcefield(ff)}/Toy/" in as_object and as_object != by_name
+    assert vd[0].endswith("Toy_O_co2_truncated.grid")
+    # a modified rule changes the hash (and so the cache directory); an identical copy does not
+    inter = [list(row) for row in ff.interactions]
+    i, j = ff.sdict["O_co2"], ff.sdict["Oz"]
+    inter[i][j] = inter[j][i] = FF.LennardJones(99.0, 3.0)
+    ff2 = ceg.ForceField(inter, ff.sdict, ff.symbols, ff.cutoff, ff.name)
+    ff3 = ceg.ForceField([list(row) for row in ff.interactions], dict(ff.sdict), list(ff.symbols), ff.cutoff, ff.name)
+    assert ceg.hash_forcefield(ff2) != ceg.hash_forcefield(ff) == ceg.hash_forcefield(ff3)
+    tup, _ = ceg.grid_locations("Toy", ("ToyFF", ff2), ff2, ["O_co2"], 0.15, (2, 2, 3))
+    assert f"/ToyFF-{ceg.hash_forcefield(ff2)}/" in tup
+
+
+def test_energy_grid_refuses_to_drop_the_orientations():
+    mol = ceg.RASPASystem(np.diag([np.inf] * 3), np.array([[0, 0, 1.1], [0, 0, 0], [0, 0, -1.1]]), ["O", "C", "O"],
+                          np.ones(3), np.array([-0.3, 0.6, -0.3]), True)
+    fw = ceg.RASPASystem(np.diag([10.0, 10.0, 10.0]), np.zeros((1, 3)), ["X"], np.ones(1), np.zeros(1), False)
+    setup = ceg.CrystalEnergySetup(fw, mol, ceg.EnergyGrid.zero(), np.array([-0.3, 0.6, -0.3]), [ceg.EnergyGrid.zero()] * 2,
+                                   [0, 1, 0], None, None, ceg.BlockFile(ceg.GridCoordinatesSetup.from_cell(fw.mat, 1.0)))
+    with pytest.raises(ValueError, match="rotations"):
+        ceg.energy_grid(setup, 1.0)            # num_rotate = 40, polyatomic, no rotation set: grids.jl:385-390 would use >= 40
+
+
+def test_set_gridpoint_matches_the_oracle(orc):
+    from ceg_b200.grids import set_gridpoint
+    rng = np.random.default_rng(3)
+    raw = rng.standard_normal((500, 8)) * 10.0 ** rng.integers(-3, 9, size=(500, 1))
+    raw[::7, 0] = np.inf
+    raw[3::11, 0] = np.nan
+    delta = np.array([0.149, 0.151, 0.148])
+    for lam, thr in (ceg.vdw_scaling(), ceg.coulomb_scaling()):
+        got = set_gridpoint(raw, delta, lam, thr)
+        want = np.stack([orc.set_gridpoint(delta, lam, thr, r) for r in raw])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_energy_grid_host_copy_waits_for_its_writer():
+    g = ceg.EnergyGrid(None, (1, 1, 1), np.inf, True, np.zeros((0, 0, 0, 0), dtype=np.float32))
+    done = []
+
+    def fill():
+        time.sleep(0.05)
+        g._grid = np.ones((8, 2, 2, 2), dtype=np.float32)
+        done.append(1)
+    g._pending = threading.Thread(target=fill)
+    g._pending.start()
+    assert g.grid.shape == (8, 2, 2, 2) and done == [1] and g._pending is None
+
+
+def test_setup_montecarlo_argument_checks(raspa_dir):  # noqa: F811
+    with pytest.raises(ValueError, match="one blockfiles element per system"):
+        ceg.setup_montecarlo("Toy", "ToyFF", ["Na"], blockfiles=[None, None])

@@ -5,7 +5,10 @@ profiles/: a transposed table of the metrics the design notes quote, and the exe
 tools/fp64_operands_ubench.cu).
 
 usage: ncu_extract.py raw  <raw.csv> <out.csv>
-       ncu_extract.py mix  <src.csv> <out.json> <units of work> <label>"""
+       ncu_extract.py mix  <src.csv> <out.json> <units of work> <label>
+       ncu_extract.py traffic <raw.csv> <key> <units per launch> <source label> [launch index]
+           -> profiles/traffic.json[key] = DRAM bytes per unit of that launch, with the kernel's register count and the
+              digest of the csrc/ sources it was built from (bench.py quotes the figure only while both still match)"""
 import collections
 import csv
 import json
@@ -66,8 +69,41 @@ def mix(path, out, units, label):
                if "build" in label else "unit as stated in the label"}, open(out, "w"), indent=1)
 
 
+# the sources a kernel is compiled from (bench.py keeps the same table)
+KERNEL_SOURCES = {"build": ["common.cuh", "fastmath.cuh", "grid_build.cuh", "math_coeffs.cuh"], "interp": ["common.cuh", "interp.cuh"]}
+
+
+def traffic(path, key, units, source, launch=0):
+    import hashlib
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rows = list(csv.reader(open(path)))
+    hdr, unit_row, r = rows[0], rows[1], rows[2 + int(launch)]
+
+    def val(name):
+        j = hdr.index(name)
+        v = float(r[j])
+        u = unit_row[j].lower()
+        return v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(u, 1.0)
+    h = hashlib.sha1()
+    d = os.path.join(root, "crystalenergygrids.jl_b200", "csrc")
+    for f in KERNEL_SOURCES["interp" if key.startswith("interp") else key]:
+        h.update(open(os.path.join(d, f), "rb").read())
+    out = os.path.join(root, "profiles", "traffic.json")
+    data = json.load(open(out)) if os.path.isfile(out) else {}
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    data[key] = {"kernel": r[hdr.index("Kernel Name")], "registers": int(float(r[hdr.index("launch__registers_per_thread")])),
+                 "csrc_digest": h.hexdigest()[:12], "dram_bytes_read": rd, "dram_bytes_write": wr, "units_per_launch": float(units),
+                 "dram_bytes_per_unit": (rd + wr) / float(units), "gpu_time_ms": val("gpu__time_duration.sum") if "gpu__time_duration.sum" in hdr else None,
+                 "source": source}
+    json.dump(data, open(out, "w"), indent=1)
+    print(key, data[key])
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "raw":
         raw(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:])
     else:
         mix(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5])
