@@ -275,7 +275,7 @@ def run_product(args):
             tx = 4
             self.chunks = []        # per rank: list of (i0, i1)
             for (s0, s1) in sl:
-                cuts = [s0 + (s1 - s0) * k // pieces // tx * tx for k in range(pieces)] + [s1]
+                cuts = [min(s1, s0 + -(-((s1 - s0) * k) // (pieces * tx)) * tx) for k in range(pieces)] + [s1]   # whole tiles; the last is the smallest
                 self.chunks.append([(cuts[k], cuts[k + 1]) for k in range(pieces) if cuts[k + 1] > cuts[k]])
             self.pieces = min(len(c) for c in self.chunks)
             assert all(len(c) == self.pieces for c in self.chunks)
@@ -393,31 +393,66 @@ def run_product(args):
     del host, host_np
 
     # ================= C4 end to end, (2): grid pair resident and interpolable on EVERY GPU =============
-    # build_dev (x-slab) -> all-gather over NVLink -> ceg_grid_upload_dev (parse_grid's conversion on the device):
-    # the hand-off the reference makes through `.grid` files (raspa.jl:430-438), without host memory in the path.
-    handoff4 = Handoff(ps, inp, cset4, (np.inf, 1e-6), pieces=2 if world > 1 else 1)
-    device_resident_step = handoff4.step
+    # The hand-off the reference makes through `.grid` files (raspa.jl:430-438), without host memory in the path.
+    # Product path (ceg.ShardedGridBuild): the build kernel of every rank writes each node as a finished interpolation
+    # record into the grids of ALL ranks (NVLink peer stores through CUDA IPC mappings; ceg_grid_build_records) — the
+    # all-gather and the re-layout pass are fused into the kernel's epilogue.  The destination grids are allocated and
+    # mapped once, like the pinned host arrays of the host-landing arm above.
+    def exchange(o):
+        got = [None] * world
+        dist.all_gather_object(got, o)
+        return got
 
-    for eg in device_resident_step():
-        eg.close()
-    barrier()
-    n_dr = max(2, K // 3)
+    sb4 = ceg.ShardedGridBuild(inp, cset4, inp.supercell, (np.inf, 1e-6), rank, world, exchange, device=dev)
+
+    def device_resident_step():
+        sb4.build(stream)
+        torch.cuda.synchronize()
+        barrier()                    # every rank's slab has landed in every replica
+
+    for _ in range(2):
+        device_resident_step()
+    n_dr = max(3, K // 2)
     t0 = time.perf_counter()
     for i in range(n_dr):
-        egs = device_resident_step()
-        torch.cuda.synchronize()
-        if i < n_dr - 1:
-            for eg in egs:
-                eg.close()
-    barrier()
+        device_resident_step()
     dr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_dr
     # proof of use: the same 1000 queries on every rank's replica
     chk_pos = wl.random_positions(cset4.cell.mat, 1000, 5)
-    chk = float(np.where(ceg.interpolate_grid(egs[0], chk_pos) == 1e100, 0.0, ceg.interpolate_grid(egs[0], chk_pos)).sum())
+
+    def checksum(eg):
+        v = ceg.interpolate_grid(eg, chk_pos)
+        return float(np.where(v == 1e100, 0.0, v).sum())
+
+    chk = checksum(sb4.grids[0]) + checksum(sb4.grids[1])
     chk_same = (min_over_ranks(chk) == max_over_ranks(chk))
+
+    # The library-collective baseline of the same hand-off (round-2 first version, kept as the comparison): sub-slab
+    # ceg_grid_build_dev -> NCCL all-gather overlapped with the next sub-slab's build -> ceg_grid_upload_parts_dev.
+    n_pieces = int(os.environ.get("CEG_BENCH_PIECES", 0)) or (1 if world == 1 else 2 if world < 4 else 4)
+    handoff4 = Handoff(ps, inp, cset4, (np.inf, 1e-6), pieces=n_pieces)
+    for eg in handoff4.step():
+        eg.close()
+    barrier()
+    n_nc = 3
+    t0 = time.perf_counter()
+    for i in range(n_nc):
+        egs = handoff4.step()
+        torch.cuda.synchronize()
+        if i < n_nc - 1:
+            for eg in egs:
+                eg.close()
+    barrier()
+    nccl_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_nc
+    chk_nccl = checksum(egs[0]) + checksum(egs[1])
+    chk_same = chk_same and (chk_nccl == chk)          # both hand-offs produce the same grids
     for eg in egs:
         eg.close()
     del d_out, handoff4
+    sb4.close(barrier=barrier)
+    for eg in sb4.grids:
+        eg.close()
+    del sb4
 
     # ================= C1 (0.15 Å) on this GPU: the "< 1 s" headline, and the grids for C2 ============
     nx1, ny1, nz1 = cset1.nodes
@@ -618,17 +653,19 @@ def run_product(args):
         fl5, nin5 = flops_per_point(inp5, st5)
         c5_tflops = fl5 * st5["n_points"] / (c5_mine * 1e-3) / 1e12
         del d5
-        ho5 = Handoff(ps5, inp5, cs5, (np.inf, 1e-6), pieces=2 if world > 1 else 1)
-        for eg in ho5.step():      # warm-up: NCCL channels, image lists of the sub-slabs
-            eg.close()
+        ps5.close()
+        sb5 = ceg.ShardedGridBuild(inp5, cs5, inp5.supercell, (np.inf, 1e-6), rank, world, exchange, device=dev)
+        sb5.build(stream)          # warm-up: image list, peer mappings touched
+        torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
-        grids5 = ho5.step()
+        sb5.build(stream)
+        torch.cuda.synchronize()
         barrier()
         c5_total_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         c5_handoff_ms = max(0.0, c5_total_ms - c5_ms)
-        ps5.close()
-        del ho5
+        grids5 = sb5.grids
+        sb5.close(barrier=barrier)
         q0, q1 = slabs(N_SWEEP, world)[rank]
         for eg in grids5:
             ceg.interpolate_sweep(eg, 10 ** 6, 4)
@@ -655,8 +692,8 @@ def run_product(args):
                                      "kernel": "grid_build_tiled_kernel<256,1,true,true>"},
                         "gpu_launches": int(c5_launches)},
               "build_and_handoff_ms": c5_total_ms, "handoff_ms_beyond_build": c5_handoff_ms,
-              "handoff_note": "sub-slab builds overlapped with the all-gather of the 8.1 GB grid pair over NVLink, then "
-                              "ceg_grid_upload_parts_dev on every GPU (parse_grid on the device, no assembled copy)",
+              "handoff_note": "ceg_grid_build_records: every rank's build kernel writes its x-slab as interpolation records into the grids of all ranks (NVLink peer stores); "
+                              "no all-gather, no re-layout pass",
               "sweep": {"value": 2 * N_SWEEP / (c5_sweep_ms * 1e-3), "unit": "interpolations/s", "ms": c5_sweep_ms,
                         "kernel_ms_max_over_ranks": c5_kernel_ms, "queries": N_SWEEP, "grids": 2,
                         "roofline": {"bound": "hbm", "achieved": 2 * (q1 - q0) * 264.0 / (c5_kernel_ms * 1e-3) / 1e9 if c5_kernel_ms else None,
@@ -702,10 +739,16 @@ def run_product(args):
             "e2e_device": {"value": total_points / (dr_ms * 1e-3), "unit": "grid points/s", "ms_per_step": dr_ms,
                            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                            "replicas_identical": bool(chk_same),
-                           "note": "per step: ceg_grid_build_dev of this rank's x-slab in two sub-slabs, all-gather of both grids over "
-                                   "NVLink (NCCL) overlapped with the second build, ceg_grid_upload_parts_dev on every GPU -> the "
-                                   "VdW + Coulomb grid pair is resident and interpolable on every GPU (the reference: .grid files, "
-                                   "raspa.jl:430-438)"},
+                           "note": "per step: ceg_grid_build_records of this rank's x-slab — the build kernel writes every node as a "
+                                   "finished interpolation record into the grids of all ranks (NVLink peer stores; all-gather and "
+                                   "re-layout fused into the kernel) — device synchronize, barrier -> the VdW + Coulomb grid pair is "
+                                   "resident and interpolable on every GPU (the reference: .grid files, raspa.jl:430-438); destination "
+                                   "grids allocated and IPC-mapped once",
+                           "nccl_baseline": {"ms_per_step": nccl_ms, "value": total_points / (nccl_ms * 1e-3),
+                                             "sub_slabs_per_rank": n_pieces,
+                                             "note": "same hand-off with library collectives: ceg_grid_build_dev in sub-slabs, NCCL "
+                                                     "all-gather overlapped with the next sub-slab's build, "
+                                                     "ceg_grid_upload_parts_dev"}},
             "roofline": {"bound": "fp64", "achieved": my_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": my_tflops / fp64_peak if fp64_peak else None,
                          "traffic": tr_b * stats["n_points"] if tr_b else None, "traffic_source": tr_b_src,

@@ -19,7 +19,7 @@ from .ewald import (EwaldContext, EwaldFramework, EwaldKspace, adsorbate_sums, b
                     ewald_context, ewald_parameters, framework_sites, initialize_ewald)
 from .forcefields import (ForceField, InteractionRule, InteractionRuleSum, Kind, Mixing, UndefinedInteractionError,
                           get_atom_name, needsvdwgrid, pair_dtype, pair_table)
-from .grids import (CrystalEnergySetup, EnergyGrid, build_grids, build_grids_device, coulomb_scaling, create_grid_coulomb,
+from .grids import (CrystalEnergySetup, EnergyGrid, ShardedGridBuild, build_grids, build_grids_device, coulomb_scaling, create_grid_coulomb,
                     create_grid_vdw, energy_grid, energy_point, energy_points, interpolate_grid, interpolate_pair,
                     interpolate_sweep, parse_grid, vdw_scaling, write_grid)
 from .montecarlo import MonteCarloGrids, framework_interactions, setup_montecarlo

@@ -47,6 +47,7 @@ EXPORTS = [
     "ceg_probe_last_timing", "ceg_grid_gather", "ceg_kernel_registers", "ceg_device_malloc", "ceg_device_free",
     "ceg_device_download", "ceg_device_synchronize", "ceg_grid_pair_create", "ceg_grid_pair_free", "ceg_interpolate_pair",
     "ceg_interpolate_pair_dev", "ceg_ewald_create_from_sf", "ceg_grid_upload_parts_dev",
+    "ceg_grid_create_empty", "ceg_grid_records", "ceg_grid_build_records", "ceg_ipc_export", "ceg_ipc_open", "ceg_ipc_close",
 ]
 
 _lib = None
@@ -302,6 +303,53 @@ def grid_upload_parts_dev(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, d_p
                                             _p(b, C.c_int32), _p(st, C.c_int64) if st is not None else None, C.c_double(scale),
                                             C.c_int32(int(is_vdw)), C.byref(h)))
     return h
+
+
+def grid_create_empty(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, is_vdw: bool):
+    """Grid handle whose records a build will write (ceg_grid_build_records)."""
+    h = C.c_void_p()
+    _check(load().ceg_grid_create_empty(C.c_int32(device), C.byref(cell), C.byref(gs), C.c_int32(int(is_vdw)), C.byref(h)))
+    return h
+
+
+def grid_records(h):
+    """(device pointer, bytes, layout) of a grid's record storage."""
+    p, n, lay = C.c_void_p(), C.c_int64(0), C.c_int32(0)
+    _check(load().ceg_grid_records(h, C.byref(p), C.byref(n), C.byref(lay)))
+    return int(p.value), n.value, lay.value
+
+
+def grid_build_records(h, gs: ceg_gridspec_t, i0: int, i1: int, lam_v: float, thr_v: float, lam_c: float, thr_c: float,
+                       dest_records, layout: int, scales, d_out=None, stream: int = 0):
+    """Build planes [i0, i1) straight into interpolation records: dest_records[t][g] = record pointer of grid g at
+    destination t (local handle, peer device or IPC mapping); d_out: optional `.grid`-order device buffers."""
+    n_dest = len(dest_records)
+    flat = [int(p) for dest in dest_records for p in dest]
+    ptrs = (C.c_void_p * len(flat))(*[C.c_void_p(p) for p in flat])
+    sc = np.ascontiguousarray(scales, dtype=np.float64)
+    outs = (C.c_void_p * len(d_out))(*[C.c_void_p(int(p)) for p in d_out]) if d_out is not None else None
+    _check(load().ceg_grid_build_records(h, C.byref(gs), C.c_int32(i0), C.c_int32(i1), C.c_double(lam_v), C.c_double(thr_v),
+                                         C.c_double(lam_c), C.c_double(thr_c), C.c_int32(n_dest), ptrs, C.c_int32(layout),
+                                         _p(sc, C.c_double), outs, C.c_void_p(stream)))
+
+
+def ipc_export(device: int, d_ptr: int):
+    """(64-byte handle, offset) of a device buffer for another process (CUDA IPC)."""
+    hd = (C.c_uint8 * 64)()
+    off = C.c_int64(0)
+    _check(load().ceg_ipc_export(C.c_int32(device), C.c_void_p(int(d_ptr)), hd, C.byref(off)))
+    return bytes(hd), off.value
+
+
+def ipc_open(device: int, handle: bytes, offset: int) -> int:
+    hd = (C.c_uint8 * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    _check(load().ceg_ipc_open(C.c_int32(device), hd, C.c_int64(offset), C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(device: int, d_ptr: int):
+    _check(load().ceg_ipc_close(C.c_int32(device), C.c_void_p(int(d_ptr))))
 
 
 def set_interp_layout(layout: int):

@@ -755,6 +755,11 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     P.raw = nullptr;
     P.raw_slab = 0;
     P.raw_plane0 = 0;
+    P.n_dest = 0;
+    P.rec_block = 0;
+    for (int t = 0; t < MAX_BUILD_DEST; t++)
+        for (int g = 0; g < MAX_GRIDS; g++) P.rec[t][g] = nullptr;
+    for (int g = 0; g < MAX_GRIDS; g++) P.rec_scale[g] = 1.0;
     P.stats = h->d_stats.as<unsigned long long>();
     // image list for the slab's bounding box
     double lo[3], hi[3];
@@ -854,14 +859,50 @@ static int check_build_args(const char* who, ceg_probe_h h, const ceg_gridspec_t
     return 0;
 }
 
-extern "C" int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
-                                  double thr_vdw, double lambda_coul, double thr_coul, float* const* d_out, void* stream) {
-    if (check_build_args("ceg_grid_build_dev", h, gs, i0, i1)) return 1;
-    if (!d_out) return fail("ceg_grid_build_dev: null argument");
-    for (int g = 0; g < h->n_probes + h->want_coulomb; g++)
-        if (!d_out[g]) return fail("ceg_grid_build_dev: null output buffer");
-    std::lock_guard<std::mutex> lk(h->mu);
-    if (use_device(h->device)) return 1;
+// Record destinations of a build (BuildParams::rec): validated, peer access enabled where a destination lives on
+// another device of this process (IPC mappings of other processes' memory arrive with access enabled, ceg_ipc_open).
+struct RecordTargets {
+    int n_dest = 0, block = 0;
+    Rec8* rec[MAX_BUILD_DEST][MAX_GRIDS];
+    double scale[MAX_GRIDS];
+};
+static int fill_record_targets(const char* who, ceg_probe_h h, int32_t n_dest, void* const* d_records, int32_t layout,
+                               const double* scale, RecordTargets& T) {
+    const int ng = h->n_probes + h->want_coulomb;
+    if (n_dest < 1 || n_dest > MAX_BUILD_DEST) return fail(std::string(who) + ": between 1 and 8 destinations expected");
+    if (!d_records || !scale) return fail(std::string(who) + ": null argument");
+    if (layout != LAYOUT_NODE && layout != LAYOUT_BLOCK) return fail(std::string(who) + ": records are written in the NODE or BLOCK layout");
+    T.n_dest = n_dest;
+    T.block = layout == LAYOUT_BLOCK;
+    for (int g = 0; g < ng; g++) {
+        if (!(scale[g] > 0.0)) return fail(std::string(who) + ": scale must be positive");
+        T.scale[g] = scale[g];
+    }
+    for (int t = 0; t < n_dest; t++)
+        for (int g = 0; g < ng; g++) {
+            void* p = d_records[(size_t)t * ng + g];
+            if (!p || ((uintptr_t)p & 31)) return fail(std::string(who) + ": null or misaligned record buffer");
+            T.rec[t][g] = reinterpret_cast<Rec8*>(p);
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, p) != cudaSuccess || a.type != cudaMemoryTypeDevice) {
+                cudaGetLastError();
+                return fail(std::string(who) + ": record buffer is not device memory");
+            }
+            if (a.device != h->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, h->device, a.device);
+                if (!can) return fail(std::string(who) + ": no peer access from the probe's device to a destination device");
+                cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail_cuda(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+                cudaGetLastError();
+            }
+        }
+    return 0;
+}
+
+static int grid_build_dev_impl(const char* who, ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
+                               double thr_vdw, double lambda_coul, double thr_coul, float* const* d_out,
+                               const RecordTargets* T, void* stream) {
     std::vector<std::pair<int, int>> win;
     if (list_windows(h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, win)) return 1;
     const int ng = h->n_probes + h->want_coulomb;
@@ -871,10 +912,102 @@ extern "C" int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32
         BuildParams P;
         if (prepare_build(h, gs, w.first, w.second, lambda_vdw, thr_vdw, lambda_coul, thr_coul, P)) return 1;
         P.i0 = i0; P.i1 = i1;                       // the output buffers hold the caller's whole slab
-        for (int g = 0; g < ng; g++) P.out[g] = d_out[g];
-        CEG_CK(launch_planes(h, P, gs, std::sqrt(h->cutoff2), w.first, w.second, s));
+        for (int g = 0; g < ng; g++) P.out[g] = d_out ? d_out[g] : nullptr;
+        if (T) {
+            P.n_dest = T->n_dest;
+            P.rec_block = T->block;
+            for (int t = 0; t < T->n_dest; t++)
+                for (int g = 0; g < ng; g++) P.rec[t][g] = T->rec[t][g];
+            for (int g = 0; g < ng; g++) P.rec_scale[g] = T->scale[g];
+        }
+        cudaError_t e = launch_planes(h, P, gs, std::sqrt(h->cutoff2), w.first, w.second, s);
+        if (e != cudaSuccess) return fail_cuda(e, who, __FILE__, __LINE__);
     }
     h->last_points = (int64_t)(i1 - i0) * (gs->dims[1] + 1) * (gs->dims[2] + 1);
+    return 0;
+}
+
+extern "C" int ceg_grid_build_dev(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
+                                  double thr_vdw, double lambda_coul, double thr_coul, float* const* d_out, void* stream) {
+    if (check_build_args("ceg_grid_build_dev", h, gs, i0, i1)) return 1;
+    if (!d_out) return fail("ceg_grid_build_dev: null argument");
+    for (int g = 0; g < h->n_probes + h->want_coulomb; g++)
+        if (!d_out[g]) return fail("ceg_grid_build_dev: null output buffer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    return grid_build_dev_impl("ceg_grid_build_dev", h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, d_out, nullptr, stream);
+}
+
+// The build with its hand-off fused in: every node is written as a finished interpolation record (parse_grid's
+// conversion applied, NODE or BLOCK layout) into the record storage of n_dest grids — ceg_grid_create_empty handles on
+// this device and on its NVLink peers — so a sharded build leaves a complete replica on every GPU when its kernels
+// have finished; no all-gather, no re-layout pass.  d_out (optional) receives the `.grid`-order slab as well.
+extern "C" int ceg_grid_build_records(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
+                                      double thr_vdw, double lambda_coul, double thr_coul, int32_t n_dest,
+                                      void* const* d_records, int32_t layout, const double* scale, float* const* d_out,
+                                      void* stream) {
+    if (check_build_args("ceg_grid_build_records", h, gs, i0, i1)) return 1;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (use_device(h->device)) return 1;
+    RecordTargets T;
+    if (fill_record_targets("ceg_grid_build_records", h, n_dest, d_records, layout, scale, T)) return 1;
+    if (d_out)
+        for (int g = 0; g < h->n_probes + h->want_coulomb; g++)
+            if (!d_out[g]) return fail("ceg_grid_build_records: null output buffer");
+    return grid_build_dev_impl("ceg_grid_build_records", h, gs, i0, i1, lambda_vdw, thr_vdw, lambda_coul, thr_coul, d_out, &T, stream);
+}
+
+// Device buffers across processes (CUDA IPC): the owner exports, a peer process opens the mapping (peer access
+// enabled) and passes it as a record destination.  Library buffers are whole cudaMalloc allocations or sit at a fixed
+// offset inside one; the offset travels with the handle.
+extern "C" int ceg_ipc_export(int32_t device, const void* d_ptr, uint8_t* handle64, int64_t* offset) {
+    if (!d_ptr || !handle64 || !offset) return fail("ceg_ipc_export: null argument");
+    if (use_device(device)) return 1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ceg_ipc_export: 64-byte handles");
+    cudaIpcMemHandle_t hd;
+    CEG_CK(cudaIpcGetMemHandle(&hd, const_cast<void*>(d_ptr)));
+    // base of the allocation d_ptr lies in (driver entry point fetched through the runtime: the library does not link libcuda)
+    typedef int (*range_fn_t)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CEG_CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail("ceg_ipc_export: cuMemGetAddressRange is not available");
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<range_fn_t>(fn)(&base, &size, (unsigned long long)(uintptr_t)d_ptr) != 0)
+        return fail("ceg_ipc_export: cuMemGetAddressRange failed");
+    memcpy(handle64, &hd, 64);
+    *offset = (int64_t)((unsigned long long)(uintptr_t)d_ptr - base);
+    return 0;
+}
+namespace {
+std::mutex g_ipc_mu;
+std::vector<std::pair<void*, void*>> g_ipc_open;     // (pointer handed out, mapping base)
+}  // namespace
+extern "C" int ceg_ipc_open(int32_t device, const uint8_t* handle64, int64_t offset, void** d_ptr) {
+    if (!handle64 || !d_ptr || offset < 0) return fail("ceg_ipc_open: bad argument");
+    if (use_device(device)) return 1;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    void* base = nullptr;
+    CEG_CK(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = (char*)base + offset;
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    g_ipc_open.push_back({*d_ptr, base});
+    return 0;
+}
+extern "C" int ceg_ipc_close(int32_t device, void* d_ptr) {
+    if (!d_ptr) return 0;
+    void* base = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ipc_mu);
+        for (size_t i = 0; i < g_ipc_open.size(); i++)
+            if (g_ipc_open[i].first == d_ptr) { base = g_ipc_open[i].second; g_ipc_open.erase(g_ipc_open.begin() + i); break; }
+    }
+    if (!base) return fail("ceg_ipc_close: not a ceg_ipc_open pointer");
+    if (use_device(device)) return 1;
+    CEG_CK(cudaDeviceSynchronize());
+    CEG_CK(cudaIpcCloseMemHandle(base));
     return 0;
 }
 
@@ -1116,6 +1249,45 @@ extern "C" int ceg_grid_layout(ceg_grid_h h, int32_t* layout) {
     return 0;
 }
 
+static int default_layout(size_t node_bytes) {
+    return (node_bytes > ((size_t)96 << 20) && node_bytes < ((size_t)1536 << 20)) ? LAYOUT_BLOCK : LAYOUT_NODE;
+}
+static size_t record_bytes(int layout, int nx, int ny, int nz) {
+    const size_t bricks = (size_t)((nx + 1) / 2) * ((ny + 1) / 2) * ((nz + 1) / 2);
+    return layout == LAYOUT_BLOCK ? sizeof(Rec8) * 8 * bricks : sizeof(Rec8) * (size_t)nx * ny * nz;
+}
+
+// An interpolation grid whose records are still to be written — by ceg_grid_build_records on this device and/or on the
+// other GPUs that hold the rest of the x range.  Layout: the one ceg_grid_upload would choose (NODE or BLOCK).
+extern "C" int ceg_grid_create_empty(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, int32_t is_vdw,
+                                     ceg_grid_h* out) {
+    if (!unitcell || !gs || !out) return fail("ceg_grid_create_empty: null argument");
+    for (int d = 0; d < 3; d++)
+        if (gs->dims[d] < 1) return fail("ceg_grid_create_empty: bad dims");
+    if (use_device(device)) return 1;
+    std::unique_ptr<ceg_grid_s> h(new ceg_grid_s);
+    h->device = device;
+    h->g.uc = to_dev(*unitcell);
+    h->g.gs = to_dev(*gs);
+    h->g.is_vdw = is_vdw ? 1 : 0;
+    const int nx = gs->dims[0] + 1, ny = gs->dims[1] + 1, nz = gs->dims[2] + 1;
+    int layout = g_interp_layout.load();
+    if (layout != LAYOUT_NODE && layout != LAYOUT_BLOCK) layout = default_layout(sizeof(Rec8) * (size_t)nx * ny * nz);
+    CEG_CK(acquire_stream(&h->stream));
+    CEG_CK(h->d_nodes.reserve(record_bytes(layout, nx, ny, nz)));
+    h->g.data = h->d_nodes.as<float>();
+    h->g.layout = layout;
+    *out = h.release();
+    return 0;
+}
+extern "C" int ceg_grid_records(ceg_grid_h h, void** d_records, int64_t* bytes, int32_t* layout) {
+    if (!h) return fail("ceg_grid_records: null handle");
+    if (d_records) *d_records = h->d_nodes.p;
+    if (bytes) *bytes = (int64_t)record_bytes(h->g.layout, h->g.gs.n[0], h->g.gs.n[1], h->g.gs.n[2]);
+    if (layout) *layout = h->g.layout;
+    return 0;
+}
+
 // grid: host pointer (from_device = false) or device pointer on `device` (true), [8][nx][ny][nz]; or `parts` (device,
 // x-slabs of a sharded build, see GridSource)
 static int grid_upload_impl(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, const float* grid,
@@ -1140,13 +1312,12 @@ static int grid_upload_impl(int32_t device, const ceg_cell_t* unitcell, const ce
     // duplicating layouts lose to their own footprint; the bricks remove half of the 64-byte-granularity over-fetch
     // of a z pair without growing the grid.
     int layout = g_interp_layout.load();
-    if (layout < 0) layout = (node_bytes > ((size_t)96 << 20) && node_bytes < ((size_t)1536 << 20)) ? LAYOUT_BLOCK : LAYOUT_NODE;
+    if (layout < 0) layout = default_layout(node_bytes);
     {
         DevBuf tmp, nodes;
         const bool direct = (layout == LAYOUT_NODE || layout == LAYOUT_BLOCK);    // one pass straight into the final layout
         DevBuf& node_dst = direct ? h->d_nodes : nodes;
-        const size_t bricks = (size_t)((nx + 1) / 2) * ((ny + 1) / 2) * ((nz + 1) / 2);
-        CEG_CK(node_dst.reserve(layout == LAYOUT_BLOCK ? sizeof(Rec8) * 8 * bricks : node_bytes));
+        CEG_CK(node_dst.reserve(layout == LAYOUT_BLOCK ? record_bytes(layout, nx, ny, nz) : node_bytes));
         GridSource S;
         memset(&S, 0, sizeof S);
         if (parts) {
@@ -1188,7 +1359,7 @@ extern "C" int ceg_grid_upload_parts_dev(int32_t device, const ceg_cell_t* unitc
                                          const float* const* d_parts, const int32_t* i0, const int32_t* i1, const int64_t* stride,
                                          double scale, int32_t is_vdw, ceg_grid_h* out) {
     if (n_parts <= 0 || n_parts > MAX_GRID_PARTS || !d_parts || !i0 || !i1 || !gs)
-        return fail("ceg_grid_upload_parts_dev: between 1 and 16 parts expected");
+        return fail("ceg_grid_upload_parts_dev: between 1 and 64 parts expected");
     if (!(scale > 0.0)) return fail("ceg_grid_upload_parts_dev: scale must be positive");
     GridSource S;
     memset(&S, 0, sizeof S);

@@ -117,6 +117,22 @@ __device__ __forceinline__ double norm2_x(const double* v) {
     return xadd(xadd(xmul(v[0], v[0]), xmul(v[1], v[1])), xmul(v[2], v[2]));
 }
 
+// One grid node as the interpolation kernels read it: the eight channels of `.grid` in 32 bytes (one DRAM sector).
+struct alignas(32) Rec8 {
+    float4 lo, hi;         // f, fx, fy, fz | fxy, fxz, fyz, fxyz
+};
+// Place of node (x, y, z) among the records: node-major, or 2x2x2-node bricks of 256 bytes (interp.cuh).
+__device__ __forceinline__ int64_t record_index(bool block, int x, int y, int z, int ny, int nz) {
+    if (!block) return ((int64_t)x * ny + y) * nz + z;
+    const int64_t nby = (ny + 1) >> 1, nbz = (nz + 1) >> 1;
+    return ((((int64_t)(x >> 1) * nby + (y >> 1)) * nbz + (z >> 1)) << 3) + (((x & 1) * 2 + (y & 1)) * 2 + (z & 1));
+}
+// parse_grid's unit conversion of one `.grid` value (grids.jl:78: Float32(value * GRID_TO_KELVIN), the product formed in
+// double); scale == 1 leaves the value as it is.
+__device__ __forceinline__ float record_value(float f, double scale) {
+    return scale == 1.0 ? f : (float)xmul((double)f, scale);
+}
+
 // utils.jl:210-246 periodic_distance2_fromcartesian!, literally: `b` = Cartesian difference on
 // entry, the vector the reference leaves in its buffer on exit (stale last-tried image included).
 __device__ __noinline__ double periodic_distance2_ref(double* b, const CellDev& c) {

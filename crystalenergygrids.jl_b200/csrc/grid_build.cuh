@@ -103,6 +103,7 @@ __device__ __forceinline__ HotBuck load_buck_general(uint32_t pr) {
 #define CEG_COMPACT_WARPS 1
 #endif
 constexpr int MAX_GRIDS = 5;       // up to 4 fused VdW probes + Coulomb per pass
+constexpr int MAX_BUILD_DEST = 8;  // replicas one build launch can write its interpolation records to (one per GPU of a node)
 constexpr int LIST_CAP_MAX = 1024;   // shared-memory image list capacity per round (the host picks the actual one)
 constexpr size_t TABLE_SMEM_MAX = 64 << 10;   // bytes of shared memory the (probe x species) pair table may take
 
@@ -377,6 +378,14 @@ struct BuildParams {
     const PairDev* table;
     int n_types;
     float* out[MAX_GRIDS];     // each [8][i1-i0][ny][nz]
+    // Interpolation records written by the kernel itself: node (i, j, k) of grid g goes, converted like parse_grid would
+    // (rec_scale), to its place in the record layout of n_dest destinations — this device's grid handle and, over NVLink
+    // peer mappings, the replicas on the other GPUs of a sharded build (the all-gather of the slabs and the re-layout
+    // pass fused into the epilogue; the reference hands the grids over through `.grid` files, raspa.jl:430-438).
+    int n_dest;                // 0: no record output
+    int rec_block;             // destination layout: 2x2x2 bricks (1) or node-major (0)
+    Rec8* rec[MAX_BUILD_DEST][MAX_GRIDS];
+    double rec_scale[MAX_GRIDS];
     double* raw;               // optional [g][8][raw_slab/plane][ny][nz]; this launch's slab starts at raw_plane0
     int64_t raw_slab;
     int raw_plane0;
@@ -838,11 +847,22 @@ grid_build_tiled_kernel(const BuildParams P) {
             for (int c = 0; c < 8; c++)
                 P.raw[((int64_t)g * 8 + c) * P.raw_slab + (int64_t)P.raw_plane0 * plane + node] = acc[g][c];
         }
-        if (P.out[g]) {
+        if (P.out[g] || P.n_dest) {
             float o[8];
             set_gridpoint(acc[g], P.gs.delta, coul ? P.lam_c : P.lam_v, coul ? P.thr_c : P.thr_v, o);
+            if (P.out[g]) {
 #pragma unroll
-            for (int c = 0; c < 8; c++) P.out[g][(int64_t)c * slab + node] = o[c];
+                for (int c = 0; c < 8; c++) P.out[g][(int64_t)c * slab + node] = o[c];
+            }
+            if (P.n_dest) {
+                const double sc = P.rec_scale[g];
+                Rec8 r8;
+                r8.lo = make_float4(record_value(o[0], sc), record_value(o[1], sc), record_value(o[2], sc), record_value(o[3], sc));
+                r8.hi = make_float4(record_value(o[4], sc), record_value(o[5], sc), record_value(o[6], sc), record_value(o[7], sc));
+                const int64_t d = record_index(P.rec_block != 0, i, j, k, (int)ny, (int)nz);
+#pragma unroll 1
+                for (int t = 0; t < P.n_dest; t++) P.rec[t][g][d] = r8;      // local, or a peer GPU's memory
+            }
         }
     }
 }

@@ -45,13 +45,9 @@ struct BlockDev {
     const uint8_t* mask;   // [x][y][z]
 };
 
-struct alignas(32) Rec8 {
-    float4 lo, hi;         // f, fx, fy, fz | fxy, fxz, fyz, fxyz
-};
-
 // Source of a re-layout: one [8][nx][ny][nz] array, or the x-slabs of a sharded build as they sit after an all-gather
 // (part r: planes [i0[r], i1[r]) in a [8][stride[r]][ny][nz] buffer) — the full grid is then never assembled.
-constexpr int MAX_GRID_PARTS = 16;
+constexpr int MAX_GRID_PARTS = 64;
 struct GridSource {
     int n_parts;                         // 0: `whole`
     const float* whole;
@@ -81,18 +77,14 @@ __global__ void __launch_bounds__(256) relayout_nodes_kernel(const GridSource S,
         }
         float v[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const float f = src[c * cstride];
-            v[c] = scale == 1.0 ? f : (float)xmul((double)f, scale);
-        }
+        for (int c = 0; c < 8; c++) v[c] = record_value(src[c * cstride], scale);
         Rec8 r8;
         r8.lo = make_float4(v[0], v[1], v[2], v[3]);
         r8.hi = make_float4(v[4], v[5], v[6], v[7]);
         int64_t d = n;
         if (BLOCK) {
             const int y = (int)(rem / nz), z = (int)(rem - (int64_t)y * nz);
-            const int64_t nby = (ny + 1) >> 1, nbz = (nz + 1) >> 1;
-            d = ((((int64_t)(x >> 1) * nby + (y >> 1)) * nbz + (z >> 1)) << 3) + (((x & 1) * 2 + (y & 1)) * 2 + (z & 1));
+            d = record_index(true, x, y, z, ny, nz);
         }
         dst[d] = r8;
     }

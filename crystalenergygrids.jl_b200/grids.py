@@ -348,11 +348,11 @@ def build_grids(framework, forcefield: ForceField, spacing: float, atoms=(), cou
 
 def build_grids_device(framework, forcefield: ForceField, spacing: float, atoms=(), coulomb: bool = False, alpha: float = 0.0,
                        devices=None, ewald_precision: float = 1e-6, download: bool = False, replicate: bool = True):
-    """The same fused construction with the result LEFT ON THE DEVICES: every GPU of `devices` builds its x-slab
-    (ceg_grid_build_dev), the slabs are gathered over NVLink into a full grid on each GPU (ceg_grid_gather) and turned
-    into interpolation handles there (ceg_grid_upload_dev, which applies parse_grid's unit conversion, grids.jl:78) —
-    the hand-off the reference makes by writing `.grid` files and parsing them back (raspa.jl:430-438), without the
-    trip through the file system and host memory.
+    """The same fused construction with the result LEFT ON THE DEVICES as interpolable grids: every GPU of `devices`
+    builds its x-slab and the build kernel itself writes each node as a finished interpolation record (parse_grid's
+    unit conversion applied, grids.jl:78) into the grid handle of EVERY target GPU over NVLink peer stores
+    (ceg_grid_build_records) — the hand-off the reference makes by writing `.grid` files and parsing them back
+    (raspa.jl:430-438), without the file system, host memory, an all-gather or a re-layout pass.
 
     -> (csetup, [EnergyGrid ...] (VdW grids of `atoms`, then the Coulomb grid), host) where every EnergyGrid is
     resident on devices[0] with replicas on the other devices (replicate=True), and host = list of float32 arrays in
@@ -371,64 +371,58 @@ def build_grids_device(framework, forcefield: ForceField, spacing: float, atoms=
     inputs = probe_inputs(framework, forcefield, atoms, coulomb, alpha)
     slabs = [(a, b) for a, b in _slabs(nx, len(devices)) if b > a]
     devs = devices[:len(slabs)]
-    plane_bytes = 8 * ny * nz * 4
-    d_slab = [[0] * n_grids for _ in devs]
+    targets = devices if replicate else devices[:1]
+    uc = unitcell_struct(cset.cell)
+    handles = [[None] * n_grids for _ in targets]
+    host = [np.empty((8, nx, ny, nz), dtype=np.float32) for _ in range(n_grids)] if download else None
     errors = []
 
     def build(k):
+        d_slab = []
         try:
             dev, (a, b) = devs[k], slabs[k]
             ps = ProbeSystem(None, None, inputs=inputs, device=dev)
             try:
-                for g in range(n_grids):
-                    d_slab[k][g] = _lib.device_malloc(dev, (b - a) * plane_bytes)
-                _lib.grid_build_dev(ps.handle, gs, a, b, lam_v, thr_v, lam_c, thr_c, d_slab[k], 0)
+                slab_bytes = (b - a) * ny * nz * 4
+                if download:
+                    d_slab = [_lib.device_malloc(dev, 8 * slab_bytes) for _ in range(n_grids)]
+                _lib.grid_build_records(ps.handle, gs, a, b, lam_v, thr_v, lam_c, thr_c, dest, layout,
+                                        [GRID_TO_KELVIN] * n_grids, d_slab if download else None, 0)
                 _lib.device_synchronize(dev)
+                for g in range(n_grids if download else 0):
+                    for c in range(8):              # the slab of channel c is one contiguous run of the `.grid` array
+                        _lib.device_download(dev, d_slab[g] + c * slab_bytes, host[g][c, a:b])
             finally:
                 ps.close()
         except Exception as e:  # noqa: BLE001
             errors.append(e)
+        finally:
+            for p in d_slab:
+                _lib.device_free(p)
 
-    def run(fn, n):
-        if n == 1:
-            fn(0)
+    try:
+        for t, dev in enumerate(targets):
+            for g in range(n_grids):
+                handles[t][g] = _lib.grid_create_empty(dev, uc, gs, g < len(atoms))
+        recs = [[_lib.grid_records(h) for h in hs] for hs in handles]
+        layout = recs[0][0][2]
+        if any(r[2] != layout for rs in recs for r in rs):
+            raise _lib.CegError("build_grids_device: the replicas disagree on the record layout")
+        dest = [[r[0] for r in rs] for rs in recs]
+        if len(devs) == 1:
+            build(0)
         else:
-            ths = [threading.Thread(target=fn, args=(k,)) for k in range(n)]
+            ths = [threading.Thread(target=build, args=(k,)) for k in range(len(devs))]
             [t.start() for t in ths]
             [t.join() for t in ths]
         if errors:
             raise errors[0]
-
-    targets = devices if replicate else devices[:1]
-    handles = [[None] * n_grids for _ in targets]
-    host = [np.empty((8, nx, ny, nz), dtype=np.float32) for _ in range(n_grids)] if download else None
-    uc = unitcell_struct(cset.cell)
-
-    def gather(t):
-        try:
-            dev = targets[t]
-            for g in range(n_grids):
-                is_vdw = g < len(atoms)
-                d_full = _lib.device_malloc(dev, nx * plane_bytes)
-                try:
-                    _lib.grid_gather(devs, [d_slab[k][g] for k in range(len(devs))], [a for a, _ in slabs],
-                                     [b for _, b in slabs], gs, dev, d_full)
-                    handles[t][g] = _lib.grid_upload_dev(dev, uc, gs, d_full, GRID_TO_KELVIN, is_vdw)
-                    if download and t == 0:
-                        _lib.device_download(dev, d_full, host[g])
-                finally:
-                    _lib.device_free(d_full)
-        except Exception as e:  # noqa: BLE001
-            errors.append(e)
-
-    try:
-        run(build, len(devs))
-        run(gather, len(targets))
-    finally:
-        for k in range(len(devs)):
-            for p in d_slab[k]:
-                if p:
-                    _lib.device_free(p)
+    except BaseException:
+        for hs in handles:
+            for h in hs:
+                if h is not None:
+                    _lib.grid_free(h)
+        raise
     grids = []
     num_vdw = find_supercell(framework.mat, forcefield.cutoff)
     num_coul = find_supercell(framework.mat, CUTOFF_COULOMB)
@@ -440,6 +434,70 @@ def build_grids_device(framework, forcefield: ForceField, spacing: float, atoms=
         eg._replicas = {targets[t]: handles[t][g] for t in range(1, len(targets))}
         grids.append(eg)
     return cset, grids, host
+
+
+class ShardedGridBuild:
+    """One process per GPU (torchrun, MPI): the grids of one probe pass built x-slab by x-slab across `world` ranks so
+    that EVERY rank ends up with the complete, interpolable grids in its own HBM.  Each rank allocates empty grids
+    (ceg_grid_create_empty), the record buffers are exchanged once as CUDA IPC handles, and `build()` launches this
+    rank's slab of the build kernel, which writes every node record into all `world` replicas over NVLink
+    (ceg_grid_build_records) — construction and hand-off in one kernel; the reference exchanges `.grid` files
+    (raspa.jl:430-438).  After build(): synchronise the device, then the ranks (barrier), then interpolate.
+
+    exchange(obj) -> list: all-gather of a picklable object over the ranks, indexed by rank (for torch.distributed:
+    `lambda o: (lambda L: (dist.all_gather_object(L, o), L)[1])([None] * world)`).
+    precisions: EnergyGrid.ewald_precision per grid (inf for VdW grids, probes in order, Coulomb last); supercell:
+    EnergyGrid.num_unitcell, one triple for all grids or one per grid."""
+
+    def __init__(self, inputs, cset, supercell, precisions, rank: int, world: int, exchange, device: int = 0):
+        self.cset, self.rank, self.world, self.device = cset, rank, world, device
+        self.gs = _lib.make_gridspec(cset)
+        self.slabs = _slabs(cset.nodes[0], world)
+        self.ps = ProbeSystem(None, None, inputs=inputs, device=device)
+        uc = unitcell_struct(cset.cell)
+        self.grids = []
+        per_grid = len(supercell) == len(precisions) and all(np.ndim(sc) == 1 for sc in supercell)
+        for g, prec in enumerate(precisions):
+            eg = EnergyGrid(cset, tuple(supercell[g] if per_grid else supercell), float(prec), True,
+                            np.zeros((0, 0, 0, 0), dtype=np.float32), device)
+            eg._handle = _lib.grid_create_empty(device, uc, self.gs, eg.is_vdw)
+            self.grids.append(eg)
+        recs = [_lib.grid_records(eg._handle) for eg in self.grids]
+        self.layout = recs[0][2]
+        mine = [_lib.ipc_export(device, r[0]) + (r[2],) for r in recs] if world > 1 else None
+        self._peer_ptrs = []
+        self.dest = []
+        for r, theirs in enumerate(exchange(mine) if world > 1 else [None]):
+            if r == rank:
+                self.dest.append([rec[0] for rec in recs])
+                continue
+            if any(lay != self.layout for _, _, lay in theirs):
+                raise _lib.CegError("ShardedGridBuild: the ranks disagree on the record layout")
+            ptrs = [_lib.ipc_open(device, hd, off) for hd, off, _ in theirs]
+            self._peer_ptrs += ptrs
+            self.dest.append(ptrs)
+        self.lam = vdw_scaling() + coulomb_scaling()
+
+    def build(self, stream: int = 0, i0: int | None = None, i1: int | None = None):
+        """Launch (asynchronously, on `stream`) the build of this rank's x-slab — or of planes [i0, i1) — into every replica."""
+        a, b = self.slabs[self.rank]
+        a, b = (a if i0 is None else i0), (b if i1 is None else i1)
+        if b > a:
+            _lib.grid_build_records(self.ps.handle, self.gs, a, b, *self.lam, self.dest, self.layout,
+                                    [GRID_TO_KELVIN] * len(self.grids), None, stream)
+
+    def close(self, barrier=None):
+        """Unmap the peers' buffers, (barrier: every rank has unmapped), release this rank's probe system.  The grids
+        stay valid and are owned by the caller (EnergyGrid.close)."""
+        _lib.device_synchronize(self.device)
+        ptrs, self._peer_ptrs = self._peer_ptrs, []
+        for p in ptrs:
+            _lib.ipc_close(self.device, p)
+        if barrier is not None:
+            barrier()
+        ps, self.ps = self.ps, None
+        if ps is not None:
+            ps.close()
 
 
 def create_grid_vdw(file, framework, forcefield: ForceField, spacing: float, atom: str, devices=None) -> np.ndarray:

@@ -199,10 +199,36 @@ int ceg_grid_upload_dev(int32_t device, const ceg_cell_t* unitcell, const ceg_gr
                         double scale, int32_t is_vdw, ceg_grid_h* out);
 /* The same from the x-slabs of a sharded build as they sit on `device` after an all-gather (NCCL, MPI, peer copies):
  * part r holds planes [i0[r], i1[r]) in a [8][stride[r]][ny][nz] f32 buffer (stride = NULL: stride[r] = i1[r] - i0[r]);
- * the parts tile 0..nx in order.  The full grid is never assembled: one pass reads the parts and writes the records. */
+ * the parts (at most 64) tile 0..nx in order.  The full grid is never assembled: one pass reads the parts and writes the records. */
 int ceg_grid_upload_parts_dev(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, int32_t n_parts,
                               const float* const* d_parts, const int32_t* i0, const int32_t* i1, const int64_t* stride,
                               double scale, int32_t is_vdw, ceg_grid_h* out);
+/* ---- build with the hand-off fused in (replaces the `.grid` file exchange of raspa.jl:430-438 between the
+ * construction and the interpolation stage; single- and multi-GPU) ----
+ * ceg_grid_create_empty: an interpolation grid on `device` whose node records are still to be written (layout: the
+ * one ceg_grid_upload would choose, NODE or BLOCK); ceg_grid_records: its record storage (device pointer, bytes,
+ * layout).  ceg_grid_build_records runs the build kernel of planes [i0, i1) and writes every node straight to its
+ * place in the record storage of n_dest grids, converted as Float32(value * scale[g]) (parse_grid, grids.jl:78; one
+ * scale per grid of the pass: probes in order, Coulomb last): d_records[t * n_grids + g] = records of grid g at
+ * destination t — a handle on the probe's device, on another device of this process, or a ceg_ipc_open mapping of
+ * another process's handle (peer stores over NVLink).  A build sharded over the GPUs of a node thus leaves a complete
+ * replica on every GPU when the kernels of all ranks have finished (synchronise the ranks before interpolating):
+ * no all-gather, no re-layout pass, no `.grid`-order intermediate.  d_out (may be NULL) additionally receives the
+ * `.grid`-order slab [8][i1-i0][ny][nz] per grid, for callers that also write the file.  Asynchronous on `stream`
+ * like ceg_grid_build_dev.  Results are bit-identical to build -> `.grid` -> parse_grid -> ceg_grid_upload. */
+int ceg_grid_create_empty(int32_t device, const ceg_cell_t* unitcell, const ceg_gridspec_t* gs, int32_t is_vdw,
+                          ceg_grid_h* out);
+int ceg_grid_records(ceg_grid_h grid, void** d_records, int64_t* bytes, int32_t* layout);
+int ceg_grid_build_records(ceg_probe_h probe, const ceg_gridspec_t* gs, int32_t i0, int32_t i1, double lambda_vdw,
+                           double thr_vdw, double lambda_coul, double thr_coul, int32_t n_dest,
+                           void* const* d_records, int32_t layout, const double* scale, float* const* d_out,
+                           void* stream);
+/* Device buffers across processes (CUDA IPC, one process per GPU): the owner exports a 64-byte handle + the offset
+ * of d_ptr inside its allocation; a peer process opens it on its own device (peer access enabled) and closes it
+ * before the owner frees the buffer. */
+int ceg_ipc_export(int32_t device, const void* d_ptr, uint8_t* handle64, int64_t* offset);
+int ceg_ipc_open(int32_t device, const uint8_t* handle64, int64_t offset, void** d_ptr);
+int ceg_ipc_close(int32_t device, void* d_ptr);
 int ceg_grid_free(ceg_grid_h h);
 /* Device record layout used by subsequent ceg_grid_upload calls: 0 = node records (1x memory),
  * 1 = (y,z) quads (4x), 2 = whole 8-corner cells (8x, one aligned 256 B block per query),

@@ -118,7 +118,16 @@ def test_gather_and_device_build_equal_host_build(cuda_lib):
         eg = ceg.EnergyGrid.from_device_parts(cs, (1, 1, 1), prec, [t.data_ptr() for t in pad], [(p[0], p[1]) for p in parts],
                                               [t.shape[1] for t in pad])
         assert np.array_equal(ceg.interpolate_grid(eg, pos), want)
+        eg.close()
+        # many narrow parts (8 ranks x 4 sub-slabs in bench.py): up to 64, the 65th is refused
+        edges = np.unique(np.linspace(0, nx, min(nx, 64) + 1).astype(int))
+        many = [torch.from_numpy(np.ascontiguousarray(outs[g][:, a:b])).cuda() for a, b in zip(edges[:-1], edges[1:])]
+        eg = ceg.EnergyGrid.from_device_parts(cs, (1, 1, 1), prec, [t.data_ptr() for t in many],
+                                              list(zip(edges[:-1].tolist(), edges[1:].tolist())))
+        assert np.array_equal(ceg.interpolate_grid(eg, pos), want)
         eg.close(); ref.close()
+    with pytest.raises(ceg.CegError):
+        ceg.EnergyGrid.from_device_parts(cs, (1, 1, 1), np.inf, [parts[0][2][0]] * 65, [(i, i + 1) for i in range(65)])
     with pytest.raises(ceg.CegError):       # parts must tile the x range
         ceg.EnergyGrid.from_device_parts(cs, (1, 1, 1), np.inf, [parts[1][2][0]], [(parts[1][0], parts[1][1])])
     for p in parts:
@@ -256,3 +265,106 @@ def test_two_gpus_in_one_process(cuda_lib):
         assert np.array_equal(ceg._lib.interpolate(eg.handle_on(0), pos), want)
         assert np.array_equal(ceg._lib.interpolate(eg.handle_on(1), pos), want)
         ref.close(); eg.close()
+
+
+@pytest.mark.parametrize("layout", [0, 4], ids=["node", "block"])
+def test_build_records_equals_build_file_parse_upload(cuda_lib, layout):
+    """ceg_grid_build_records: the build kernel writes finished interpolation records (parse_grid's conversion and the
+    device layout applied in its epilogue) into several destination grids at once — bit-identical to build -> `.grid`
+    values -> parse_grid scaling -> ceg_grid_upload, for slabs of any parity, with the `.grid`-order slab on the side."""
+    inp, cs, ex, outs, gK = _two_grids(0.5)
+    nx, ny, nz = cs.nodes
+    gs = ceg._lib.make_gridspec(cs)
+    uc = ceg.grids.unitcell_struct(cs.cell)
+    lam = ceg.vdw_scaling() + ceg.coulomb_scaling()
+    pos = wl.random_positions(cs.cell.mat, 30000, 11)
+    ceg._lib.set_interp_layout(layout)
+    try:
+        dests = [[ceg._lib.grid_create_empty(0, uc, gs, g == 0) for g in range(2)] for _ in range(3)]
+        recs = [[ceg._lib.grid_records(h) for h in hs] for hs in dests]
+        assert all(r[2] == layout and r[1] >= 32 * nx * ny * nz for rs in recs for r in rs)
+        ps = ceg.ProbeSystem(None, None, inputs=inp)
+        cut = nx // 3 | 1                                   # an odd first plane for the second slab: bricks straddle it
+        for a, b in ((0, cut), (cut, nx)):
+            d_out = [ceg._lib.device_malloc(0, 8 * (b - a) * ny * nz * 4) for _ in range(2)]
+            ceg._lib.grid_build_records(ps.handle, gs, a, b, *lam, [[r[0] for r in rs] for rs in recs], layout,
+                                        [ceg.GRID_TO_KELVIN] * 2, d_out, 0)
+            ceg._lib.device_synchronize(0)
+            for g in range(2):
+                back = np.empty((8, b - a, ny, nz), dtype=np.float32)
+                ceg._lib.device_download(0, d_out[g], back)
+                assert np.array_equal(back.view(np.uint32), outs[g][:, a:b].view(np.uint32))
+                ceg._lib.device_free(d_out[g])
+        for g, prec in enumerate((np.inf, 1e-6)):
+            ref = ceg.EnergyGrid(cs, (1, 1, 1), prec, True, gK[g])
+            want = ceg.interpolate_grid(ref, pos)
+            for hs in dests:
+                assert np.array_equal(ceg._lib.interpolate(hs[g], pos), want)
+            ref.close()
+        # argument checks
+        good = [[r[0] for r in recs[0]]]
+        with pytest.raises(ceg.CegError):
+            ceg._lib.grid_build_records(ps.handle, gs, 0, nx, *lam, good * 9, layout, [1.0, 1.0], None, 0)
+        with pytest.raises(ceg.CegError):
+            ceg._lib.grid_build_records(ps.handle, gs, 0, nx, *lam, good, 1, [1.0, 1.0], None, 0)       # QUAD layout
+        with pytest.raises(ceg.CegError):
+            ceg._lib.grid_build_records(ps.handle, gs, 0, nx, *lam, [[good[0][0] + 4, good[0][1]]], layout, [1.0, 1.0], None, 0)
+        with pytest.raises(ceg.CegError):
+            ceg._lib.grid_build_records(ps.handle, gs, 0, nx, *lam, good, layout, [1.0, 0.0], None, 0)
+        ps.close()
+        for hs in dests:
+            for h in hs:
+                ceg._lib.grid_free(h)
+    finally:
+        ceg._lib.set_interp_layout(-1)
+
+
+def _sharded_worker(rank, world, port, outdir):
+    import sys
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch
+    dev = rank % torch.cuda.device_count()               # one GPU: both ranks share it (IPC works within a device too)
+
+    def exchange(o):
+        got = [None] * world
+        dist.all_gather_object(got, o)
+        return got
+
+    inp, cset, _ = wl.load_fixture("cha_na")
+    cs = wl.respace(cset, 0.5)
+    nx = cs.nodes[0]
+    sb = ceg.ShardedGridBuild(inp, cs, (1, 1, 1), (np.inf, 1e-6), rank, world, exchange, device=dev)
+    sb.build()
+    ceg._lib.device_synchronize(dev)
+    dist.barrier()                                        # every rank's slab has landed in every replica
+    # reference: the whole grid built by this process alone, through host arrays
+    ps = ceg.ProbeSystem(None, None, inputs=inp, device=dev)
+    outs = [np.zeros((8,) + tuple(cs.nodes), dtype=np.float32) for _ in range(2)]
+    ceg._lib.grid_build(ps.handle, sb.gs, 0, nx, *sb.lam, outs, None)
+    ps.close()
+    pos = wl.random_positions(cs.cell.mat, 20000, 5 + rank)
+    for g, eg in enumerate(sb.grids):
+        ref = ceg.EnergyGrid(cs, (1, 1, 1), eg.ewald_precision, True,
+                             (outs[g].astype(np.float64) * ceg.GRID_TO_KELVIN).astype(np.float32), device=dev)
+        assert np.array_equal(ceg.interpolate_grid(eg, pos), ceg.interpolate_grid(ref, pos))
+        ref.close()
+    sb.close(barrier=dist.barrier)
+    for eg in sb.grids:
+        eg.close()
+    open(os.path.join(outdir, f"ok{rank}"), "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_build_across_processes_writes_every_replica(cuda_lib, tmp_path):
+    """ShardedGridBuild with one process per rank: each rank builds its x-slab and its kernel writes the records into
+    the grids of BOTH processes (CUDA IPC mappings; NVLink peer stores when the ranks sit on different GPUs)."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
