@@ -596,6 +596,10 @@ def run_product(args):
             "c_abi_framework_interactions_1_placement": med_us(callf, 2000),
             "c_abi_note": "ceg_energy_points re-issued on prepared argument buffers (no Python marshalling): what a compiled "
                           "host — the Julia shim's ccall — pays per call; one kernel launch, mapped pinned I/O, flag wait",
+            "empty_launch_roundtrip": ceg._lib.measure_launch_roundtrip(dev, 1000),
+            "empty_launch_note": "ceg_measure_launch_roundtrip: one EMPTY kernel through the same stream, mapped flag and polling "
+                                 "loop, timed inside the library — the floor of any single-launch evaluation on this box; "
+                                 "c_abi_* minus this = argument marshalling + the kernel's work",
             "energy_point_1_placement": med_us(lambda: ceg.energy_points(setup, one)),
             "energy_points_64_placements": med_us(lambda: ceg.energy_points(setup, p64)),
             "framework_interactions_1_placement": med_us(lambda: ceg.energy_points(setup, one, reciprocal=False)),
@@ -787,6 +791,10 @@ def run_product(args):
                                      "frac": sep_gbs / hbm_peak, "peak_source": hbm_src,
                                      "traffic": tr_i * nq if tr_i else None, "traffic_source": tr_i_src,
                                      "traffic_unit": "DRAM bytes per launch of 10^7/N queries on one grid (this rank)",
+                                     "dram_throughput_frac": (tr_i * nq / (sep_ms / 2 * 1e-3) / 1e9 / hbm_peak) if tr_i else None,
+                                     "dram_note": "profiled DRAM bytes (64-byte access granularity against 32-byte records) / "
+                                                  "this run's launch time / peak: how close the kernel is to the bandwidth "
+                                                  "limit with the bytes its access pattern actually moves",
                                      "algorithmic_bytes_per_query": 288, "kernel": "interpolate_kernel<BLOCK>", "registers": sep_regs}),
                        "separate_kernels": {"value": 2 * N_QUERIES / (sep_ms * 1e-3), "ms_per_step": sep_ms,
                                             "achieved_gbs": sep_gbs, "frac": sep_gbs / hbm_peak,

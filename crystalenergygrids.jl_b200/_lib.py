@@ -47,7 +47,7 @@ EXPORTS = [
     "ceg_probe_last_timing", "ceg_grid_gather", "ceg_kernel_registers", "ceg_device_malloc", "ceg_device_free",
     "ceg_device_download", "ceg_device_synchronize", "ceg_grid_pair_create", "ceg_grid_pair_free", "ceg_interpolate_pair",
     "ceg_interpolate_pair_dev", "ceg_ewald_create_from_sf", "ceg_grid_upload_parts_dev",
-    "ceg_grid_create_empty", "ceg_grid_records", "ceg_grid_build_records", "ceg_ipc_export", "ceg_ipc_open", "ceg_ipc_close",
+    "ceg_measure_launch_roundtrip", "ceg_grid_create_empty", "ceg_grid_records", "ceg_grid_build_records", "ceg_ipc_export", "ceg_ipc_open", "ceg_ipc_close",
 ]
 
 _lib = None
@@ -303,6 +303,13 @@ def grid_upload_parts_dev(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, d_p
                                             _p(b, C.c_int32), _p(st, C.c_int64) if st is not None else None, C.c_double(scale),
                                             C.c_int32(int(is_vdw)), C.byref(h)))
     return h
+
+
+def measure_launch_roundtrip(device: int = 0, reps: int = 300) -> float:
+    """Median µs of one empty launch through the latency path (launch -> mapped completion flag seen by the CPU)."""
+    t = C.c_double(0.0)
+    _check(load().ceg_measure_launch_roundtrip(C.c_int32(device), C.c_int32(reps), C.byref(t)))
+    return t.value
 
 
 def grid_create_empty(device: int, cell: ceg_cell_t, gs: ceg_gridspec_t, is_vdw: bool):

@@ -2102,6 +2102,32 @@ static SmallStage& small_stage() {
     static thread_local SmallStage st;
     return st;
 }
+// Median round trip of ONE empty launch on the latency path's machinery (same stream, same mapped flag, same polling
+// loop): what any single-launch evaluation pays on this box before its kernel does any work.
+extern "C" int ceg_measure_launch_roundtrip(int32_t device, int32_t reps, double* median_us) {
+    if (!median_us || reps < 1) return fail("ceg_measure_launch_roundtrip: bad argument");
+    if (use_device(device)) return 1;
+    SmallStage& stg = small_stage();
+    if (!stg.ready(device)) return fail("ceg_measure_launch_roundtrip: staging block unavailable");
+    volatile unsigned long long* hflag = reinterpret_cast<volatile unsigned long long*>(stg.host);
+    std::vector<double> t((size_t)reps);
+    for (int r = -10; r < reps; r++) {
+        const unsigned long long gen = ++stg.gen;
+        const auto t0 = std::chrono::steady_clock::now();
+        flag_only_kernel<<<1, 32, 0, stg.stream>>>(reinterpret_cast<volatile unsigned long long*>(stg.host_dev), gen);
+        CEG_CK(cudaGetLastError());
+        unsigned long long spins = 0;
+        while (*hflag != gen)
+            if ((++spins & 0xfffff) == 0 && cudaStreamQuery(stg.stream) != cudaErrorNotReady && *hflag != gen)
+                return fail("ceg_measure_launch_roundtrip: kernel finished without raising the flag");
+        if (r >= 0) t[r] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    }
+    CEG_CK(cudaStreamSynchronize(stg.stream));
+    std::sort(t.begin(), t.end());
+    *median_us = t[t.size() / 2];
+    return 0;
+}
+
 static int P_device_of(const ceg_grid_h* vdw, int n_vdw, ceg_grid_h coulomb, ceg_ewald_h ewald, ceg_block_h block) {
     int device = -1;
     for (int g = 0; g < n_vdw; g++)

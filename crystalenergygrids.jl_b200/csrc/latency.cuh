@@ -130,4 +130,11 @@ __global__ void __launch_bounds__(SMALL_THREADS) energy_points_small_kernel(cons
     }
 }
 
+// The floor of the latency path on a given box: a kernel that only raises the completion flag in mapped host memory
+// (ceg_measure_launch_roundtrip: launch -> flag visible to the polling CPU).
+__global__ void flag_only_kernel(volatile unsigned long long* flag, unsigned long long gen) {
+    *flag = gen;
+    __threadfence_system();
+}
+
 }  // namespace ceg

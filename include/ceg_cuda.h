@@ -108,6 +108,10 @@ int ceg_measure_fp64_peak(int32_t device, double* tflops);
 /* Same chains with three per-thread register operands per DFMA (what real kernels issue): on B200 the
  * register-file read bandwidth caps this form ~30 % below the uniform-operand figure. */
 int ceg_measure_fp64_peak_regops(int32_t device, double* tflops);
+/* Median round trip (µs) of one EMPTY kernel launch through the single-placement latency path's machinery (launch ->
+ * completion flag in mapped host memory seen by the polling CPU): the box's floor for ceg_energy_points with one
+ * placement; bench.py reports it next to the measured latencies. */
+int ceg_measure_launch_roundtrip(int32_t device, int32_t reps, double* median_us);
 
 /* Registers per thread of the main kernels as loaded on `device`: which = 0 fused one-probe + Coulomb build kernel,
  * 1 interpolation (brick layout), 2 fused VdW + Coulomb pair interpolation, 3 reciprocal rows kernel (one atom). */

@@ -13,7 +13,8 @@
 #   initialize_ewald                      ewald.jl:195-281   -> unchanged host code; its EwaldFramework gets a device handle on
 #                                                               first use (ceg_ewald_create_from_sf), or — with the three-line patch
 #                                                               of INTEGRATION.md §2 — S_f itself comes from ceg_ewald_create
-#   setup_RASPA's grid hand-off           raspa.jl:420-439   -> create_grids_resident (ceg_grid_build_dev -> ceg_grid_upload_dev)
+#   setup_RASPA's grid hand-off           raspa.jl:420-439   -> create_grids_resident (ceg_grid_create_empty + ceg_grid_build_records:
+#                                                               the build kernel writes the interpolation records itself)
 #   single_contribution_ewald  ewald.jl:704-738  -> ceg_ewald_single_contribution   (batched over trial placements)
 #   single_contribution_vdw    energy.jl:397-427 -> ceg_guest_energy                (batched over trial placements)
 #   parse_blockfile / BlockFile(g)  coordinates.jl:112-167, grids.jl:188-204 -> ceg_block_from_spheres / _values
@@ -506,7 +507,8 @@ end
 
 # ---- setup_RASPA's hand-off without the file round trip (raspa.jl:420-439) ---------------------------------------------
 # Build the missing grids of a setup in one fused pass, keep them on the device, return EnergyGrid objects whose handles
-# are already resident (ceg_grid_build_dev -> ceg_grid_upload_dev applies parse_grid's conversion, grids.jl:78) and
+# are already resident (ceg_grid_build_records: the build kernel applies parse_grid's conversion, grids.jl:78, and writes
+# the interpolation records itself) and
 # write the `.grid` files from one downloaded copy on a background task.  `retrieve_or_create_grid` then only needs
 #     haskey(RESIDENT, grid_path) && return RESIDENT[grid_path]
 # as its first line.
@@ -522,14 +524,29 @@ function create_grids_resident(framework, forcefield::ForceField, spacing::TÅ, 
     nz, ny, nx = cset.dims[3] + 1, cset.dims[2] + 1, cset.dims[1] + 1
     bytes = 8 * nx * ny * nz * sizeof(Cfloat)
     h = ProbeHandle(probe, idx, withcoul, withcoul ? ustrip(u"Å^-1", ewald.α) : 0.0; device)
+    cell = CegCell(SMatrix{3,3,Float64,9}(ustrip.(u"Å", cset.cell.mat)), SMatrix{3,3,Float64,9}(ustrip.(u"Å^-1", cset.cell.invmat)))
+    gs = CegGridSpec(cset)
+    # empty interpolation grids: the build kernel writes their node records itself (ceg_grid_build_records) ...
+    grids = [Ref{Ptr{Cvoid}}(C_NULL) for _ in 1:n]
+    recs = Vector{Ptr{Cvoid}}(undef, n)
+    layout = Ref{Int32}(0)
+    for g in 1:n
+        check(ccall((:ceg_grid_create_empty, libceg), Cint, (Int32, Ref{CegCell}, Ref{CegGridSpec}, Int32, Ref{Ptr{Cvoid}}),
+            device, cell, gs, !(withcoul && g == n), grids[g]))
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ceg_grid_records, libceg), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ptr{Int64}, Ref{Int32}), grids[g][], r, C_NULL, layout))
+        recs[g] = r[]
+    end
+    # ... and the `.grid`-order copy for the files on the side
     d = [Ref{Ptr{Cvoid}}(C_NULL) for _ in 1:n]
     foreach(r -> check(ccall((:ceg_device_malloc, libceg), Cint, (Int32, Int64, Ref{Ptr{Cvoid}}), device, bytes, r)), d)
     ptrs = Ptr{Cfloat}[Ptr{Cfloat}(r[]) for r in d]
     λv = inv(GRID_TO_KELVIN); Tv = GRID_TO_KELVIN * 1e7
     λc = ustrip(u"K*Å/e_au^2", COULOMBIC_CONVERSION_FACTOR) / GRID_TO_KELVIN; Tc = inv(λc) * 1e7
-    check(ccall((:ceg_grid_build_dev, libceg), Cint,
-        (Ptr{Cvoid}, Ref{CegGridSpec}, Int32, Int32, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Ptr{Cfloat}}, Ptr{Cvoid}),
-        h.ptr, CegGridSpec(cset), 0, nx, λv, Tv, λc, Tc, ptrs, C_NULL))
+    check(ccall((:ceg_grid_build_records, libceg), Cint,
+        (Ptr{Cvoid}, Ref{CegGridSpec}, Int32, Int32, Cdouble, Cdouble, Cdouble, Cdouble, Int32, Ptr{Ptr{Cvoid}}, Int32,
+         Ptr{Cdouble}, Ptr{Ptr{Cfloat}}, Ptr{Cvoid}),
+        h.ptr, gs, 0, nx, λv, Tv, λc, Tc, 1, recs, layout[], fill(Float64(GRID_TO_KELVIN), n), ptrs, C_NULL))
     check(ccall((:ceg_device_synchronize, libceg), Cint, (Int32,), device))
     out = EnergyGrid[]
     for g in 1:n
@@ -537,11 +554,11 @@ function create_grids_resident(framework, forcefield::ForceField, spacing::TÅ, 
         prec = iscoul ? ewald.precision : Inf
         host = Array{Cfloat,4}(undef, nz, ny, nx, 8)                                  # `.grid` units, for the file
         check(ccall((:ceg_device_download, libceg), Cint, (Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}), device, d[g][], bytes, host))
+        check(ccall((:ceg_device_free, libceg), Cint, (Ptr{Cvoid},), d[g][]))
         eg = EnergyGrid(cset, num_unitcell, prec, true, Float32.(host .* GRID_TO_KELVIN))   # parse_grid's view (grids.jl:78)
         lock(GRID_LOCK) do
-            GRID_HANDLES[eg.grid] = handle_from_device(cset, ptrs[g], !iscoul; device)      # resident before any file exists
+            GRID_HANDLES[eg.grid] = grids[g][]                                          # resident before any file exists
         end
-        check(ccall((:ceg_device_free, libceg), Cint, (Ptr{Cvoid},), d[g][]))
         path = iscoul ? coulomb_path : paths[g]
         Threads.@spawn begin                                                            # the file, in the reference's byte layout
             mkpath(dirname(path))

@@ -2,6 +2,7 @@
 energy_grid orientation contract (grids.jl:385-390), _set_gridpoint! on arrays (grids.jl:118-135) against the oracle,
 the EnergyGrid host-copy hand-shake, the setup_montecarlo argument checks."""
 import dataclasses
+import os
 import threading
 import time
 
@@ -70,3 +71,25 @@ def test_energy_grid_host_copy_waits_for_its_writer():
 def test_setup_montecarlo_argument_checks(raspa_dir):  # noqa: F811
     with pytest.raises(ValueError, match="one blockfiles element per system"):
         ceg.setup_montecarlo("Toy", "ToyFF", ["Na"], blockfiles=[None, None])
+
+
+def test_julia_shim_binds_only_declared_and_exported_symbols():
+    """julia/CEGCuda.jl (the reference-side binding) may only `ccall` entry points that include/ceg_cuda.h
+    declares and libceg_cuda.so exports; every method override INTEGRATION.md lists is present in the file."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jl = open(os.path.join(root, "julia", "CEGCuda.jl"), encoding="utf-8").read()
+    header = open(os.path.join(root, "include", "ceg_cuda.h"), encoding="utf-8").read()
+    called = set(re.findall(r"ccall\(\(:(ceg_[a-z0-9_]+)", jl))
+    assert len(called) >= 25
+    declared = set(re.findall(r"\b(ceg_[a-z0-9_]+)\s*\(", header))
+    assert called <= declared, called - declared
+    assert called <= set(ceg._lib.EXPORTS), called - set(ceg._lib.EXPORTS)
+    lib = ceg._lib.load()
+    for name in called:
+        assert hasattr(lib, name)
+    for method in ("create_grid_vdw", "create_grid_coulomb", "interpolate_grid", "energy_point", "energy_grid", "compute_ewald"):
+        assert re.search(r"function CrystalEnergyGrids\." + method + r"\(", jl), method
+    for fn in ("create_grids_fused", "create_grids_resident", "structure_factor", "single_contributions", "guest_energies",
+               "block_from_spheres", "block_from_values", "handle_from_device", "interpolate_sweep"):
+        assert re.search(r"function " + fn + r"\(", jl), fn
