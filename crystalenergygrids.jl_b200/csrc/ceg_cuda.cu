@@ -2062,13 +2062,12 @@ extern "C" int ceg_block_free(ceg_block_h h) {
     return 0;
 }
 
-// Per-thread pinned staging block (mapped into the device address space), stream and completion counter for small
+// Per-thread pinned staging block (mapped into the device address space) and stream for small
 // ceg_energy_points calls (one device per thread at a time).
 struct SmallStage {
     static constexpr size_t BYTES = 1u << 20;
     void* host = nullptr;
     void* host_dev = nullptr;          // device view of `host`
-    unsigned int* counter = nullptr;   // device
     unsigned long long gen = 0;
     cudaStream_t stream = nullptr;
     int device = -1;
@@ -2076,24 +2075,19 @@ struct SmallStage {
         if (dev < 0) return false;
         if (device != dev) {                       // (re)create for this device
             if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
-            if (counter) { cudaFree(counter); counter = nullptr; }
             if (host) { cudaFreeHost(host); host = nullptr; }
             if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { stream = nullptr; cudaGetLastError(); return false; }
-            if (cudaMalloc(&counter, sizeof(unsigned int)) != cudaSuccess || cudaMemset(counter, 0, sizeof(unsigned int)) != cudaSuccess) {
-                counter = nullptr; cudaGetLastError(); return false;
-            }
             device = dev;
         }
         if (!host) {
             if (cudaHostAlloc(&host, BYTES, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) { host = nullptr; cudaGetLastError(); return false; }
             if (cudaHostGetDevicePointer(&host_dev, host, 0) != cudaSuccess) { cudaFreeHost(host); host = nullptr; cudaGetLastError(); return false; }
-            memset(host, 0, 64);                    // completion flag
+            memset(host, 0, BYTES);                 // result slots carry generation numbers: none matches before its call
         }
         return true;
     }
     ~SmallStage() {                                 // thread exit; the context may already be gone: ignore errors
         if (host) cudaFreeHost(host);
-        if (counter) cudaFree(counter);
         if (stream) cudaStreamDestroy(stream);
         cudaGetLastError();
     }
@@ -2212,14 +2206,15 @@ extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_
         for (int64_t i = 0; i < n_pos; i++) { out_vdw[i] = 0.0; out_coulomb[i] = 0.0; }
         return 0;
     }
-    // Latency path (single Monte-Carlo steps): ONE kernel launch per call.  Inputs and outputs sit in a pinned block mapped
-    // into the device address space (the kernel reads positions and writes energies over PCIe itself) and the host waits on
-    // a flag raised by the last CTA — no copies, no stream synchronisation (csrc/latency.cuh).
+    // Latency path (single Monte-Carlo steps): ONE kernel launch per call.  Small inputs travel inside the kernel
+    // parameters, larger ones and all outputs sit in a pinned block mapped into the device address space (the kernel
+    // writes the energies over PCIe itself) and the host polls the result slots — no copies, no stream synchronisation,
+    // no completion counter (csrc/latency.cuh).
     constexpr int64_t LATENCY_MAX_POS = 256;
     if (n_pos <= LATENCY_MAX_POS && n_atoms <= SMALL_MAX_ATOMS) {
         SmallStage& stg = small_stage();
         const size_t n_idx8 = ((size_t)n_atoms + 1) / 2;
-        const size_t need = sizeof(double) * (8 + n_idx8 + (size_t)n_atoms + (size_t)3 * n_atoms * n_pos + (size_t)2 * n_pos);
+        const size_t need = sizeof(double) * (8 + n_idx8 + (size_t)n_atoms + (size_t)3 * n_atoms * n_pos + (size_t)4 * n_pos + 2);
         size_t smem = 0;
         bool tables_fit = true;
         if (coulomb && ewald && ewald->n_k > 0) {
@@ -2229,8 +2224,8 @@ extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_
         if (need <= SmallStage::BYTES && tables_fit && stg.ready(P_device_of(vdw, n_vdw, coulomb, ewald, block))) {
             double* hb = static_cast<double*>(stg.host);
             double* db = static_cast<double*>(stg.host_dev);
-            volatile unsigned long long* hflag = reinterpret_cast<volatile unsigned long long*>(hb);
-            const size_t o_idx = 8, o_q = o_idx + n_idx8, o_xyz = o_q + n_atoms, o_v = o_xyz + (size_t)3 * n_atoms * n_pos, o_c = o_v + n_pos;
+            const size_t o_idx = 8, o_q = o_idx + n_idx8, o_xyz = o_q + n_atoms;
+            const size_t o_out = (o_xyz + (size_t)3 * n_atoms * n_pos + 1) & ~(size_t)1;     // 16-byte aligned result slots
             SmallParams S;
             S.E = P;
             S.E.n_pos = n_pos;
@@ -2254,27 +2249,28 @@ extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_
             }
             S.energy_net_charges = energy_net_charges;
             S.static_contribution = static_contribution;
-            S.out_vdw = db + o_v;
-            S.out_coul = db + o_c;
-            S.flag = reinterpret_cast<volatile unsigned long long*>(db);
-            S.counter = stg.counter;
+            S.out = reinterpret_cast<double2*>(db + o_out);
             S.gen = ++stg.gen;
             energy_points_small_kernel<<<(unsigned)n_pos, SMALL_THREADS, smem, stg.stream>>>(S);
             count_launch();
             CEG_CK(cudaGetLastError());
+            // every result slot is {value, generation}, written by one 16-byte store: a slot that shows this call's
+            // generation holds this call's value
+            const volatile unsigned long long* slot = reinterpret_cast<const volatile unsigned long long*>(hb + o_out);
             unsigned long long spins = 0;
-            while (*hflag != S.gen) {
-                if ((++spins & 0xfffff) == 0) {            // every ~1M polls: has the launch failed?
-                    cudaError_t q = cudaStreamQuery(stg.stream);
-                    if (q != cudaErrorNotReady && q != cudaSuccess) return fail_cuda(q, "energy_points_small_kernel", __FILE__, __LINE__);
-                    if (q == cudaSuccess && *hflag != S.gen) {     // finished without raising the flag: cannot happen, do not hang
-                        return fail("ceg_energy_points: latency kernel finished without completing");
+            for (int64_t i = 0; i < n_pos; i++) {
+                while (slot[4 * i + 1] != S.gen || slot[4 * i + 3] != S.gen) {
+                    if ((++spins & 0xfffff) == 0) {            // every ~1M polls: has the launch failed?
+                        cudaError_t q = cudaStreamQuery(stg.stream);
+                        if (q != cudaErrorNotReady && q != cudaSuccess) return fail_cuda(q, "energy_points_small_kernel", __FILE__, __LINE__);
+                        if (q == cudaSuccess && (slot[4 * i + 1] != S.gen || slot[4 * i + 3] != S.gen))
+                            return fail("ceg_energy_points: latency kernel finished without completing");   // cannot happen; do not hang
                     }
                 }
+                std::atomic_thread_fence(std::memory_order_acquire);
+                out_vdw[i] = hb[o_out + 4 * i];
+                out_coulomb[i] = hb[o_out + 4 * i + 2];
             }
-            std::atomic_thread_fence(std::memory_order_acquire);
-            memcpy(out_vdw, hb + o_v, sizeof(double) * n_pos);
-            memcpy(out_coulomb, hb + o_c, sizeof(double) * n_pos);
             return 0;
         }
     }

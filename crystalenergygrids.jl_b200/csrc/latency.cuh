@@ -4,11 +4,13 @@
 // kernels then cost five API calls and two launches for a few microseconds of work (round 1: 69 us per call).  Here a
 // call is one kernel launch and nothing else: inputs and outputs live in a pinned host block that is MAPPED into the
 // device address space, so the kernel reads the positions and writes the energies over PCIe itself, and the host
-// waits on a flag the last CTA raises instead of synchronising a stream.
+// polls the result slots instead of synchronising a stream: every energy travels in one 16-byte store together with
+// the call's generation number, so a slot whose generation matches holds its value — no completion counter, no
+// system-scope fence between "data" and "flag" on the critical path.
 //
-// One CTA (16 warps) per placement: grid terms (warp 0, one lane per atom, grids.jl:311-318), block test (warp 1) and the
-// reciprocal-space term (ewald.jl:555-577, the k-list spread over the CTA) run side by side — power tables by sincospi in shared
-// memory as in reciprocal_kernel, fixed-order reduction.
+// One CTA (16 warps) per placement: VdW grid terms (warp 0, one lane per atom, grids.jl:311-318), Coulomb grid terms
+// (warp 2), block test (warp 1) and the reciprocal-space term (ewald.jl:555-577, the k-list spread over the CTA) run side by
+// side — power tables by sincospi in shared memory as in reciprocal_kernel, fixed-order reduction.
 #pragma once
 #include "ewald.cuh"
 #include "interp.cuh"
@@ -19,6 +21,21 @@ constexpr int SMALL_THREADS = 512;
 constexpr int SMALL_MAX_ATOMS = 32;       // one lane per atom for the grid terms and the block test
 
 constexpr int SMALL_INLINE_DOUBLES = 160;   // inputs up to this size travel inside the kernel parameters
+
+// The two halves of atom_grid_terms for grids without fused pair records (the latency kernel evaluates them on
+// different warps; same operations, same bits)
+__device__ __forceinline__ double atom_vdw_term(const EnergyPointsParams& P, int gi, const double* p) {
+    if (!P.vdw_present[gi]) return 0.0;
+    Stencil st;
+    make_stencil(P.vdw[gi].uc, P.vdw[gi].gs, p, st);
+    return interp_any(P.vdw[gi], st);
+}
+__device__ __forceinline__ double atom_coulomb_term(const EnergyPointsParams& P, double qa, const double* p) {
+    if (!P.has_coulomb) return 0.0;
+    Stencil st;
+    make_stencil(P.coulomb.uc, P.coulomb.gs, p, st);
+    return qa * interp_any(P.coulomb, st);
+}
 
 struct SmallParams {
     EnergyPointsParams E;            // grids, block mask, n_atoms (its atomsidx / charges / xyz pointers are not used)
@@ -34,10 +51,7 @@ struct SmallParams {
     int64_t n_k;
     const KVecDev* kv;
     double energy_net_charges, static_contribution;
-    double* out_vdw;                 // mapped host
-    double* out_coul;                // mapped host
-    volatile unsigned long long* flag;   // mapped host: receives `gen` when every placement is done
-    unsigned int* counter;           // device: CTAs finished
+    double2* out;                    // mapped host: per placement {vdw, gen}, {coulomb, gen} (gen = bits of the call's number)
     unsigned long long gen;
 };
 
@@ -59,9 +73,16 @@ __global__ void __launch_bounds__(SMALL_THREADS) energy_points_small_kernel(cons
     __syncthreads();
     // The three parts of energy_point are independent until the final sum and run side by side: warp 0 interpolates
     // (one lane per atom), warp 1 tests the blocking mask, every warp then fills the Ewald phase tables.
-    if (warp == 0 && lane < P.n_atoms) {
+    if ((warp == 0 || warp == 2) && lane < P.n_atoms) {
         const double p[3] = {mol[3 * lane], mol[3 * lane + 1], mol[3 * lane + 2]};
-        atom_grid_terms(P, idx[lane], s_q[lane], p, s_v[lane], s_c[lane]);
+        const int gi = idx[lane];
+        if (P.pair_data[gi]) {          // fused {VdW, Coulomb} records: one stencil gives both
+            if (warp == 0) atom_grid_terms(P, gi, s_q[lane], p, s_v[lane], s_c[lane]);
+        } else if (warp == 0) {         // the two grids of an atom are independent lookups: side by side
+            s_v[lane] = atom_vdw_term(P, gi, p);
+        } else {
+            s_c[lane] = atom_coulomb_term(P, s_q[lane], p);
+        }
     }
     if (warp == 1 && lane < P.n_atoms && P.has_block) {
         const double p[3] = {mol[3 * lane], mol[3 * lane + 1], mol[3 * lane + 2]};
@@ -119,14 +140,10 @@ __global__ void __launch_bounds__(SMALL_THREADS) energy_points_small_kernel(cons
                 coul += 2.0 * (f + S.energy_net_charges) + (q + S.static_contribution);   // ewald.jl:572-576
             }
         }
-        S.out_vdw[i] = vdw;
-        S.out_coul[i] = coul;
-        __threadfence_system();
-        if (atomicAdd(S.counter, 1u) == gridDim.x - 1) {
-            *S.counter = 0;
-            __threadfence_system();
-            *S.flag = S.gen;
-        }
+        const double g = __longlong_as_double((long long)S.gen);
+        S.out[2 * i] = make_double2(vdw, g);            // one 16-byte store each: value and generation arrive together
+        S.out[2 * i + 1] = make_double2(coul, g);
+        __threadfence_system();                         // push them out now rather than at kernel exit
     }
 }
 
