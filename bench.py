@@ -403,29 +403,48 @@ def run_product(args):
         dist.all_gather_object(got, o)
         return got
 
-    sb4 = ceg.ShardedGridBuild(inp, cset4, inp.supercell, (np.inf, 1e-6), rank, world, exchange, device=dev)
+    def sharded_build(inputs_, cset_):
+        """ShardedGridBuild on every rank, or (None, why) on every rank if any of them could not set it up (e.g. CUDA IPC
+        refused by the container): the bench then still reports the NCCL hand-off, with the error in the JSON line."""
+        sb, err = None, None
+        try:
+            if os.environ.get("CEG_BENCH_NO_FUSED"):       # exercises the reporting of a refused set-up
+                raise RuntimeError("disabled by CEG_BENCH_NO_FUSED")
+            sb = ceg.ShardedGridBuild(inputs_, cset_, inputs_.supercell, (np.inf, 1e-6), rank, world, exchange, device=dev)
+        except Exception as e:  # noqa: BLE001
+            err = repr(e)
+        if min_over_ranks(0.0 if sb is None else 1.0) < 1.0:
+            if sb is not None:
+                sb.close()
+                for eg in sb.grids:
+                    eg.close()
+            return None, err or "ShardedGridBuild failed on another rank"
+        return sb, None
 
-    def device_resident_step():
-        sb4.build(stream)
-        torch.cuda.synchronize()
-        barrier()                    # every rank's slab has landed in every replica
-
-    for _ in range(2):
-        device_resident_step()
-    n_dr = max(3, K // 2)
-    t0 = time.perf_counter()
-    for i in range(n_dr):
-        device_resident_step()
-    dr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_dr
-    # proof of use: the same 1000 queries on every rank's replica
+    sb4, fused_error = sharded_build(inp, cset4)
     chk_pos = wl.random_positions(cset4.cell.mat, 1000, 5)
 
     def checksum(eg):
         v = ceg.interpolate_grid(eg, chk_pos)
         return float(np.where(v == 1e100, 0.0, v).sum())
 
-    chk = checksum(sb4.grids[0]) + checksum(sb4.grids[1])
-    chk_same = (min_over_ranks(chk) == max_over_ranks(chk))
+    dr_ms, chk, chk_same = None, None, True
+    if sb4 is not None:
+        def device_resident_step():
+            sb4.build(stream)
+            torch.cuda.synchronize()
+            barrier()                    # every rank's slab has landed in every replica
+
+        for _ in range(2):
+            device_resident_step()
+        n_dr = max(3, K // 2)
+        t0 = time.perf_counter()
+        for i in range(n_dr):
+            device_resident_step()
+        dr_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_dr
+        # proof of use: the same 1000 queries on every rank's replica
+        chk = checksum(sb4.grids[0]) + checksum(sb4.grids[1])
+        chk_same = (min_over_ranks(chk) == max_over_ranks(chk))
 
     # The library-collective baseline of the same hand-off (round-2 first version, kept as the comparison): sub-slab
     # ceg_grid_build_dev -> NCCL all-gather overlapped with the next sub-slab's build -> ceg_grid_upload_parts_dev.
@@ -445,13 +464,18 @@ def run_product(args):
     barrier()
     nccl_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_nc
     chk_nccl = checksum(egs[0]) + checksum(egs[1])
-    chk_same = chk_same and (chk_nccl == chk)          # both hand-offs produce the same grids
+    chk_same = chk_same and (min_over_ranks(chk_nccl) == max_over_ranks(chk_nccl))
+    if chk is not None:
+        chk_same = chk_same and (chk_nccl == chk)      # both hand-offs produce the same grids
     for eg in egs:
         eg.close()
     del d_out, handoff4
-    sb4.close(barrier=barrier)
-    for eg in sb4.grids:
-        eg.close()
+    if sb4 is not None:
+        sb4.close(barrier=barrier)
+        for eg in sb4.grids:
+            eg.close()
+    else:
+        dr_ms = nccl_ms                                # reported with "fused_error" below
     del sb4
 
     # ================= C1 (0.15 Å) on this GPU: the "< 1 s" headline, and the grids for C2 ============
@@ -658,18 +682,31 @@ def run_product(args):
         c5_tflops = fl5 * st5["n_points"] / (c5_mine * 1e-3) / 1e12
         del d5
         ps5.close()
-        sb5 = ceg.ShardedGridBuild(inp5, cs5, inp5.supercell, (np.inf, 1e-6), rank, world, exchange, device=dev)
-        sb5.build(stream)          # warm-up: image list, peer mappings touched
-        torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        sb5.build(stream)
-        torch.cuda.synchronize()
-        barrier()
-        c5_total_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        sb5, c5_fused_error = sharded_build(inp5, cs5)
+        if sb5 is not None:
+            sb5.build(stream)          # warm-up: image list, peer mappings touched
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            sb5.build(stream)
+            torch.cuda.synchronize()
+            barrier()
+            c5_total_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            grids5 = sb5.grids
+            sb5.close(barrier=barrier)
+        else:                          # NCCL hand-off (see e2e_device.nccl_baseline)
+            ps5 = ceg.ProbeSystem(None, None, inputs=inp5, device=dev)
+            ho5 = Handoff(ps5, inp5, cs5, (np.inf, 1e-6), pieces=n_pieces)
+            for eg in ho5.step():
+                eg.close()
+            barrier()
+            t0 = time.perf_counter()
+            grids5 = ho5.step()
+            barrier()
+            c5_total_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            ps5.close()
+            del ho5
         c5_handoff_ms = max(0.0, c5_total_ms - c5_ms)
-        grids5 = sb5.grids
-        sb5.close(barrier=barrier)
         q0, q1 = slabs(N_SWEEP, world)[rank]
         for eg in grids5:
             ceg.interpolate_sweep(eg, 10 ** 6, 4)
@@ -695,7 +732,7 @@ def run_product(args):
                                      "algorithmic_flop_per_point": fl5, "pairs_in_cutoff_per_point": nin5,
                                      "kernel": "grid_build_tiled_kernel<256,1,true,true>"},
                         "gpu_launches": int(c5_launches)},
-              "build_and_handoff_ms": c5_total_ms, "handoff_ms_beyond_build": c5_handoff_ms,
+              "build_and_handoff_ms": c5_total_ms, "handoff_ms_beyond_build": c5_handoff_ms, "fused_error": c5_fused_error,
               "handoff_note": "ceg_grid_build_records: every rank's build kernel writes its x-slab as interpolation records into the grids of all ranks (NVLink peer stores); "
                               "no all-gather, no re-layout pass",
               "sweep": {"value": 2 * N_SWEEP / (c5_sweep_ms * 1e-3), "unit": "interpolations/s", "ms": c5_sweep_ms,
@@ -742,7 +779,7 @@ def run_product(args):
                     "breakdown_ms": breakdown},
             "e2e_device": {"value": total_points / (dr_ms * 1e-3), "unit": "grid points/s", "ms_per_step": dr_ms,
                            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                           "replicas_identical": bool(chk_same),
+                           "replicas_identical": bool(chk_same), "fused_error": fused_error,
                            "note": "per step: ceg_grid_build_records of this rank's x-slab — the build kernel writes every node as a "
                                    "finished interpolation record into the grids of all ranks (NVLink peer stores; all-gather and "
                                    "re-layout fused into the kernel) — device synchronize, barrier -> the VdW + Coulomb grid pair is "

@@ -964,8 +964,6 @@ extern "C" int ceg_ipc_export(int32_t device, const void* d_ptr, uint8_t* handle
     if (!d_ptr || !handle64 || !offset) return fail("ceg_ipc_export: null argument");
     if (use_device(device)) return 1;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ceg_ipc_export: 64-byte handles");
-    cudaIpcMemHandle_t hd;
-    CEG_CK(cudaIpcGetMemHandle(&hd, const_cast<void*>(d_ptr)));
     // base of the allocation d_ptr lies in (driver entry point fetched through the runtime: the library does not link libcuda)
     typedef int (*range_fn_t)(unsigned long long*, size_t*, unsigned long long);
     void* fn = nullptr;
@@ -975,7 +973,9 @@ extern "C" int ceg_ipc_export(int32_t device, const void* d_ptr, uint8_t* handle
     unsigned long long base = 0;
     size_t size = 0;
     if (reinterpret_cast<range_fn_t>(fn)(&base, &size, (unsigned long long)(uintptr_t)d_ptr) != 0)
-        return fail("ceg_ipc_export: cuMemGetAddressRange failed");
+        return fail("ceg_ipc_export: not a device allocation");
+    cudaIpcMemHandle_t hd;
+    CEG_CK(cudaIpcGetMemHandle(&hd, reinterpret_cast<void*>((uintptr_t)base)));
     memcpy(handle64, &hd, 64);
     *offset = (int64_t)((unsigned long long)(uintptr_t)d_ptr - base);
     return 0;

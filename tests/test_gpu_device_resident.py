@@ -368,3 +368,48 @@ def test_sharded_build_across_processes_writes_every_replica(cuda_lib, tmp_path)
         port = s.getsockname()[1]
     mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_record_build_and_ipc_argument_errors(cuda_lib):
+    """Error behaviour of the round-2 entry points: nothing is dereferenced before the checks pass."""
+    inp, cset, _ = wl.load_fixture("cha_na")
+    cs = wl.respace(cset, 1.0)
+    gs = ceg._lib.make_gridspec(cs)
+    uc = ceg.grids.unitcell_struct(cs.cell)
+    h = ceg._lib.grid_create_empty(0, uc, gs, True)
+    ptr, nbytes, layout = ceg._lib.grid_records(h)
+    assert ptr % 32 == 0 and nbytes >= 32 * int(np.prod(cs.nodes)) and layout in (0, 4)
+    hd, off = ceg._lib.ipc_export(0, ptr)
+    assert len(hd) == 64 and off == 0
+    hd2, off2 = ceg._lib.ipc_export(0, ptr + 4096)       # an interior pointer: same allocation, its offset
+    assert off2 == 4096
+    with pytest.raises(ceg.CegError):
+        ceg._lib.ipc_export(0, 0)
+    with pytest.raises(ceg.CegError):
+        ceg._lib.ipc_close(0, ptr)                         # not a mapping obtained from ceg_ipc_open
+    with pytest.raises(ceg.CegError):
+        ceg._lib.ipc_open(0, bytes(64), 0)                 # not a handle
+    lam = ceg.vdw_scaling() + ceg.coulomb_scaling()
+    ps = ceg.ProbeSystem(None, None, inputs=inp)
+    with pytest.raises(ceg.CegError):                      # host memory as a record destination
+        buf = np.zeros(1 << 16, dtype=np.uint8)
+        a = (buf.ctypes.data + 31) & ~31
+        ceg._lib.grid_build_records(ps.handle, gs, 0, 2, *lam, [[a, a]], layout, [1.0, 1.0], None, 0)
+    with pytest.raises(ceg.CegError):                      # bad slab
+        ceg._lib.grid_build_records(ps.handle, gs, 3, 3, *lam, [[ptr, ptr]], layout, [1.0, 1.0], None, 0)
+    ps.close()
+    ceg._lib.grid_free(h)
+    # a ShardedGridBuild of one rank is the single-GPU device-resident build
+    sb = ceg.ShardedGridBuild(inp, cs, (1, 1, 1), (np.inf, 1e-6), 0, 1, exchange=None, device=0)
+    sb.build()
+    sb.close()
+    outs = [np.zeros((8,) + tuple(cs.nodes), dtype=np.float32) for _ in range(2)]
+    ps = ceg.ProbeSystem(None, None, inputs=inp)
+    ceg._lib.grid_build(ps.handle, gs, 0, cs.nodes[0], *lam, outs, None)
+    ps.close()
+    pos = wl.random_positions(cs.cell.mat, 5000, 3)
+    for g, eg in enumerate(sb.grids):
+        ref = ceg.EnergyGrid(cs, (1, 1, 1), eg.ewald_precision, True,
+                             (outs[g].astype(np.float64) * ceg.GRID_TO_KELVIN).astype(np.float32))
+        assert np.array_equal(ceg.interpolate_grid(eg, pos), ceg.interpolate_grid(ref, pos))
+        ref.close(); eg.close()
