@@ -413,3 +413,38 @@ def test_record_build_and_ipc_argument_errors(cuda_lib):
                              (outs[g].astype(np.float64) * ceg.GRID_TO_KELVIN).astype(np.float32))
         assert np.array_equal(ceg.interpolate_grid(eg, pos), ceg.interpolate_grid(ref, pos))
         ref.close(); eg.close()
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["separate_grids", "pair_records"])
+def test_latency_path_equals_batch_path(cuda_lib, fused):
+    """ceg_energy_points takes its one-launch latency path (csrc/latency.cuh) for <= 256 placements of <= 32 atoms and
+    the batched kernels above: the same placements must give the same VdW bits (blocked placements included) and the
+    same Coulomb energy to 1e-9 (the reciprocal sum is reduced in a different fixed order), for a monatomic and a
+    three-atom molecule, with and without the reciprocal term, from inline (kernel parameter) and mapped-memory inputs."""
+    inp, cs, ex, outs, gK = _two_grids(0.5)
+    n_fw = len(ex["site_charge"])
+    fw = ceg.RASPASystem(ex["unit_mat"], ex["positions"][:n_fw], ["X"] * n_fw, np.ones(n_fw), ex["charges"][:n_fw], False)
+    q = float(ex["probe_charge"])
+    eg_v = ceg.EnergyGrid(cs, (1, 1, 1), np.inf, True, gK[0])
+    eg_c = ceg.EnergyGrid(cs, (1, 1, 1), 1e-6, True, gK[1])
+    ef = ceg.initialize_ewald(fw)
+    block = ceg.blockfile_from_grid(eg_v)
+    rng = np.random.default_rng(3)
+    for charges, idx in ((np.array([q]), [0]), (np.array([q, -0.5 * q, -0.5 * q]), [0, 0, 0])):
+        na = len(idx)
+        template = np.array([[0.0, 0.0, 0.0], [1.1, 0.0, 0.0], [-1.1, 0.0, 0.0]])[:na]       # rigid-molecule geometry (static term)
+        mol = ceg.RASPASystem(np.diag([np.inf] * 3), template, ["Na"] * na, np.ones(na), charges, True)
+        setup = ceg.CrystalEnergySetup(fw, mol, eg_c, charges, [eg_v], idx, ef, None, block)
+        setup.fused_pairs = fused
+        centers = wl.random_positions(fw.mat, 20000, 17)
+        pos = centers[:, None, :] + (rng.normal(size=(20000, na, 3)) * 0.8 if na > 1 else 0.0)
+        for recip in (True, False):
+            vb, cb = ceg.energy_points(setup, pos, reciprocal=recip)                 # batched kernels
+            assert 0.02 < (vb == 1e100).mean() < 0.9 and np.isfinite(cb).all()
+            for n in (1, 2, 5, 17, 64, 256):                                          # 17 x 3 atoms: beyond the inline limit
+                off = 100 * n
+                v, c = ceg.energy_points(setup, pos[off:off + n], reciprocal=recip)   # latency kernel
+                assert np.array_equal(v, vb[off:off + n])
+                assert (np.abs(c - cb[off:off + n]) <= 1e-9 * np.abs(cb[off:off + n]) + 1e-6).all()
+        eg_v.unpair()
+    eg_v.close(); eg_c.close()
