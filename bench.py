@@ -901,30 +901,35 @@ def bench_guest(ceg, wl, dev):
     env_pos = (envc[:, None, :] + mol[None, :, :]).reshape(-1, 3)
     env = ceg.GuestEnvironment(cell, 12.0, tab, env_pos, np.tile(idx, n_guests), np.repeat(np.arange(n_guests, dtype=np.int32), 3))
     trials = wl.random_positions(cell, n_trials, 11)[:, None, :] + mol[None, :, :]
-    ceg.single_contribution_vdw(env, idx, trials[:1000], -1)
+    ceg.single_contribution_vdw(env, idx, trials, -1)           # warm-up at full size: staging buffers allocated
     torch.cuda.synchronize()
+    reps = 5
+    k_ms = []
     t0 = time.perf_counter()
-    reps = 3
     for _ in range(reps):
         e = ceg.single_contribution_vdw(env, idx, trials, -1)
+        k_ms.append(ceg._lib.guest_env_last_kernel_ms(env.handle))
     ms = (time.perf_counter() - t0) * 1e3 / reps
+    kernel_ms = float(np.mean(k_ms))
     pairs = n_trials * 3 * 3 * n_guests
     vol = abs(float(np.linalg.det(cell)))
     frac_in = (4.0 / 3.0) * np.pi * 12.0 ** 3 / vol              # expected share of the pairs inside the cutoff
     flop = pairs * (24.0 + frac_in * 70.0)                       # wrap + fused 3x3 product + norm; LJ + real-space Ewald rule
     peak = ceg._lib.measure_fp64_peak(dev)
-    return {"roofline": {"bound": "fp64", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                         "frac": flop / (ms * 1e-3) / 1e12 / peak if peak else None,
+    return {"roofline": {"bound": "fp64", "achieved": flop / (kernel_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": flop / (kernel_ms * 1e-3) / 1e12 / peak if peak else None,
                          "algorithmic_flop_per_pair_test": 24, "algorithmic_flop_per_in_cutoff_pair": 70,
-                         "expected_in_cutoff_fraction": frac_in, "kernel": "guest_energy_kernel",
-                         "note": "time of the host call (H2D of 7.2 MB of trial positions and D2H included); the kernel is bound by "
-                                 "dependent-issue latency (one thread per trial placement), not by the FP64 pipe"},
+                         "expected_in_cutoff_fraction": frac_in, "kernel": "guest_energy_fast_kernel", "kernel_ms": kernel_ms,
+                         "note": "kernel time from CUDA events on the handle's stream (ceg_guest_env_last_kernel_ms)"},
             "workload": "10^5 trial CO2 placements x 10^3 CO2 guests (3000 environment atoms), LJ + real-space Ewald rules, 12 Å cutoff",
-            "ms_per_step": ms, "pair_tests_per_s": pairs / (ms * 1e-3), "placements_per_s": n_trials / (ms * 1e-3),
+            "ms_per_step": ms, "kernel_ms": kernel_ms, "pair_tests_per_s": pairs / (ms * 1e-3),
+            "pair_tests_per_s_kernel": pairs / (kernel_ms * 1e-3), "placements_per_s": n_trials / (ms * 1e-3),
             "checksum_K": float(np.where(np.isfinite(e), e, 0.0).sum()),
-            "note": "host positions in, host energies out (ceg_guest_env_energy); every (trial atom, guest atom) pair goes through "
-                    "a rint-wrap in fractional coordinates and one fused 3x3 product; pairs within 1e-9 A^2 of the cutoff are re-measured "
-                    "with the reference's literal sequence; in-cutoff pairs are queued per thread and evaluated warp-wide"}
+            "note": "ms_per_step: host positions in, host energies out (ceg_guest_env_energy, H2D of 7.2 MB of pageable trial "
+                    "positions included).  A trial placement is shared by one thread per molecule atom; every (trial atom, guest "
+                    "atom) pair goes through a rint-wrap in fractional coordinates and one fused 3x3 product; pairs within 1e-9 A^2 "
+                    "of the cutoff are re-measured with the reference's literal sequence; in-cutoff pairs are queued per thread "
+                    "and evaluated warp-wide out of line"}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -43,7 +43,7 @@ EXPORTS = [
     "ceg_host_unregister", "ceg_probe_create", "ceg_probe_free", "ceg_probe_num_grids", "ceg_compute_derivatives",
     "ceg_grid_build", "ceg_grid_build_dev", "ceg_probe_last_stats", "ceg_grid_upload", "ceg_grid_upload_dev", "ceg_grid_free",
     "ceg_interpolate", "ceg_interpolate_dev", "ceg_interpolate_multi", "ceg_interpolate_sweep", "ceg_energy_lattice", "ceg_set_interp_layout", "ceg_grid_layout", "ceg_ewald_create", "ceg_ewald_free", "ceg_ewald_reciprocal",
-    "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_guest_env_create", "ceg_guest_env_free", "ceg_guest_env_update", "ceg_guest_env_energy", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
+    "ceg_ewald_single_contribution", "ceg_ewald_reciprocal_dev", "ceg_guest_energy", "ceg_guest_env_create", "ceg_guest_env_free", "ceg_guest_env_update", "ceg_guest_env_energy", "ceg_guest_env_last_kernel_ms", "ceg_block_upload", "ceg_block_free", "ceg_block_from_spheres", "ceg_block_from_values", "ceg_energy_points",
     "ceg_probe_last_timing", "ceg_grid_gather", "ceg_kernel_registers", "ceg_device_malloc", "ceg_device_free",
     "ceg_device_download", "ceg_device_synchronize", "ceg_grid_pair_create", "ceg_grid_pair_free", "ceg_interpolate_pair",
     "ceg_interpolate_pair_dev", "ceg_ewald_create_from_sf", "ceg_grid_upload_parts_dev",
@@ -533,6 +533,12 @@ def guest_env_energy(h, mol_species, skip_mol: int, trial_xyz) -> np.ndarray:
                                        C.c_int32(skip_mol), _p(trial_xyz, C.c_double), _p(out, C.c_double)))
     return out
 
+
+
+def guest_env_last_kernel_ms(h) -> float:
+    t = C.c_double(0.0)
+    _check(load().ceg_guest_env_last_kernel_ms(h, C.byref(t)))
+    return t.value
 
 
 def guest_energy(device: int, cell: ceg_cell_t, cutoff2: float, table: np.ndarray, env_xyz, env_species, env_mol,

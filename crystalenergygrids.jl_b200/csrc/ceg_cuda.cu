@@ -1886,7 +1886,10 @@ struct ceg_guest_s {
     int n_species = 0;
     int64_t n_env = 0;
     DevBuf d_tab, d_exyz, d_esp, d_emol, d_msp, d_txyz, d_out;
+    cudaEvent_t ev[2] = {nullptr, nullptr};      // around the kernel of the last ceg_guest_env_energy
+    float last_kernel_ms = 0.f;
     ~ceg_guest_s() {
+        for (auto e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -1969,15 +1972,38 @@ extern "C" int ceg_guest_env_energy(ceg_guest_h h, int64_t n_trials, int32_t n_a
     CEG_CK(cudaMemcpyAsync(h->d_txyz.p, trial_xyz, sizeof(double) * 3 * n_atoms * n_trials, cudaMemcpyHostToDevice, s));
     GuestParams P;
     P.cell = h->cell; P.cutoff2 = h->cutoff2; P.n_species = h->n_species; P.table = h->d_tab.as<PairEnergyDev>();
+    P.cut_lo = h->cutoff2 - GUEST_BAND; P.cut_hi = h->cutoff2 + GUEST_BAND;
     P.fast_ok = (2.0 * std::sqrt(h->cutoff2) <= perp_width_min(h->cell.mat) * (1.0 - 1e-9)) ? 1 : 0;
     P.n_env = (int)h->n_env; P.env_xyz = h->d_exyz.as<double>(); P.env_species = h->d_esp.as<int>(); P.env_mol = h->d_emol.as<int>();
     P.n_trials = n_trials; P.n_atoms = n_atoms; P.mol_species = h->d_msp.as<int>(); P.skip_mol = skip_mol;
     P.trial_xyz = h->d_txyz.as<double>(); P.out = h->d_out.as<double>();
-    guest_energy_kernel<<<(unsigned)((n_trials + 127) / 128), 128, 0, s>>>(P);
+    for (auto& e : h->ev) if (!e) CEG_CK(cudaEventCreate(&e));
+    CEG_CK(cudaEventRecord(h->ev[0], s));
+    if (P.fast_ok) {
+        const int tpt = std::min<int>(n_atoms, 32);                  // threads sharing one trial placement
+        const int per_cta = GUEST_THREADS / tpt;
+        const unsigned nb = (unsigned)((n_trials + per_cta - 1) / per_cta);
+        if (h->cell.mat[1] == 0.0 && h->cell.mat[2] == 0.0 && h->cell.mat[5] == 0.0)
+            guest_energy_fast_kernel<true><<<nb, GUEST_THREADS, 0, s>>>(P, tpt);
+        else
+            guest_energy_fast_kernel<false><<<nb, GUEST_THREADS, 0, s>>>(P, tpt);
+    } else {
+        guest_energy_kernel<<<(unsigned)((n_trials + 127) / 128), 128, 0, s>>>(P);
+    }
     count_launch();
     CEG_CK(cudaGetLastError());
+    CEG_CK(cudaEventRecord(h->ev[1], s));
     CEG_CK(cudaMemcpyAsync(out, h->d_out.p, sizeof(double) * n_trials, cudaMemcpyDeviceToHost, s));
     CEG_CK(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&h->last_kernel_ms, h->ev[0], h->ev[1]);
+    return 0;
+}
+
+// Device time (ms, CUDA events on the handle's stream) of the kernel of the last ceg_guest_env_energy call.
+extern "C" int ceg_guest_env_last_kernel_ms(ceg_guest_h h, double* ms) {
+    if (!h || !ms) return fail("ceg_guest_env_last_kernel_ms: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *ms = h->last_kernel_ms;
     return 0;
 }
 

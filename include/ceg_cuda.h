@@ -318,6 +318,8 @@ int ceg_guest_env_free(ceg_guest_h h);
 int ceg_guest_env_update(ceg_guest_h h, int64_t first, int64_t n, const double* xyz /* n x 3 */);
 int ceg_guest_env_energy(ceg_guest_h h, int64_t n_trials, int32_t n_atoms, const int32_t* mol_species, int32_t skip_mol,
                          const double* trial_xyz, double* out);
+/* Device time (ms, CUDA events) of the kernel launched by the last ceg_guest_env_energy call on this handle. */
+int ceg_guest_env_last_kernel_ms(ceg_guest_h h, double* ms);
 int ceg_guest_energy(int32_t device, const ceg_cell_t* cell, double cutoff2, int32_t n_species,
                      const ceg_pair_energy_t* table /* n_species x n_species */, int64_t n_env, const double* env_xyz,
                      const int32_t* env_species, const int32_t* env_mol, int64_t n_trials, int32_t n_atoms,

@@ -155,3 +155,45 @@ def test_resident_environment_update_and_stateless_form(cuda_lib, orc):
     assert np.array_equal(np.isinf(e1), np.isinf(want)) and (np.abs(e1[fin] - want[fin]) <= 1e-9 * np.abs(want[fin]) + 1e-6).all()
     assert not np.array_equal(e0, e1)
     env.close()
+
+
+def test_guest_kernel_shapes_rotated_cell_and_cutoff_band(cuda_lib, orc):
+    """The round-2 guest kernel (one thread per molecule atom, queued in-cutoff pairs): molecules whose atom count does
+    not divide the CTA (5), exceeds the threads per placement (40 > 32), a cell that is not upper triangular (the general
+    3x3 product instead of the triangular one), a skipped molecule, and pairs sitting on the cutoff, where the literal
+    re-measurement decides exactly as the oracle does."""
+    import dataclasses
+    ff, names = _forcefield()
+    env, geom = _environment(ff, names, 400, 11)              # > 512 atoms: several tiles
+    rng = np.random.default_rng(12)
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))           # a proper rotation of the whole system
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    rot = dataclasses.replace(env, mat=q @ env.mat, positions=env.positions @ q.T)
+    assert abs(rot.mat[1, 0]) > 1e-3 and abs(rot.mat[2, 1]) > 1e-3        # not triangular
+    for n_at in (5, 40):
+        sp = rng.integers(0, 4, n_at).astype(np.int32)
+        shape = rng.standard_normal((n_at, 3)) * 1.5
+        centers = (env.mat @ rng.random((3, 700))).T
+        trials = centers[:, None, :] + shape[None]
+        want = orc.guest_energy(env, sp, trials, 7)
+        got = ceg.single_contribution_vdw(env, sp, trials, skip_molecule=7)
+        got_rot = ceg.single_contribution_vdw(rot, sp, trials @ q.T, skip_molecule=7)
+        fin = np.isfinite(want)
+        assert fin.sum() > 50 and np.array_equal(np.isfinite(got), fin) and np.array_equal(np.isfinite(got_rot), fin)
+        for g in (got, got_rot):
+            assert (np.abs(g[fin] - want[fin]) <= 1e-9 * np.abs(want[fin]) + 1e-6).all()
+    # pairs on the cutoff: one O_co2 guest alone in a big cell, Na trials at 12 Å -/+ a few ulps along several directions.
+    # The pair energy is -0.031 K just inside the cutoff and 0 beyond it, so the in/out decision is visible.
+    tab = env.table
+    big = ceg.GuestEnvironment(np.diag([40.0, 41.0, 42.0]), 12.0, tab, np.array([[20.0, 20.0, 20.0]]),
+                               np.array([1], dtype=np.int32), np.array([0], dtype=np.int32))
+    dirs = rng.standard_normal((200, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    r = 12.0 * (1.0 + rng.integers(-3, 4, 200) * 2.2e-16)
+    trials = (20.0 + dirs * r[:, None])[:, None, :]
+    want = orc.guest_energy(big, [2], trials, -1)
+    got = ceg.single_contribution_vdw(big, [2], trials, -1)
+    assert (want == 0).any() and (want < -0.01).any()
+    assert np.array_equal(got == 0, want == 0)
+    assert (np.abs(got - want) <= 1e-9 * np.abs(want) + 1e-6).all()

@@ -6,4 +6,4 @@ import ceg_b200 as ceg
 from ceg_b200 import workloads as wl
 import bench
 r = bench.bench_guest(ceg, wl, 0)
-print(r["ms_per_step"], "ms per call;", r["pair_tests_per_s"] / 1e9, "G pair tests/s; checksum", r["checksum_K"])
+print(r["ms_per_step"], "ms per call; kernel", r["kernel_ms"], "ms;", r["pair_tests_per_s_kernel"] / 1e9, "G pair tests/s (kernel); frac", r["roofline"]["frac"], "checksum", r["checksum_K"])
