@@ -629,6 +629,8 @@ def run_product(args):
             "framework_interactions_1_placement": med_us(lambda: ceg.energy_points(setup, one, reciprocal=False)),
             "interpolate_grid_1_point": med_us(lambda: ceg._lib.interpolate(hv, one[0])),
             "ewald_reciprocal_1_placement": med_us(lambda: ceg._lib.ewald_reciprocal(ef.handle, one, qarr, 0.0, 0.0)),
+            "ewald_single_contribution_1_placement": med_us(
+                lambda: ceg.single_contribution_ewald(ef, ef.StoreRigidChargeFramework, qarr, one)),
             "unit": "us per call through the host API (median of 300), host positions in, host energies out",
             "note": "the reference's CPU call is ~1-2 us: a serial Markov chain should keep single-point interpolate_grid on the "
                     "CPU and hand batches of trial placements to this path",

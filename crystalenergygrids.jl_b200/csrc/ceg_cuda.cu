@@ -1824,6 +1824,18 @@ extern "C" int ceg_ewald_reciprocal_dev(ceg_ewald_h h, int64_t n_pos, int32_t n_
                              d_out, nullptr, 0, s, nullptr, q_host);
 }
 
+static int small_energy_points(const EnergyPointsParams& P, int device, ceg_ewald_h ewald, const double* rest_reim,
+                               int64_t n_pos, int n_atoms, const int32_t* atomsidx, const double* charges, const double* xyz,
+                               double energy_net_charges, double static_contribution, double* out_vdw, double* out_coulomb);
+// the reciprocal-space term alone through the one-launch latency path (no grids, no block mask)
+static int small_reciprocal(ceg_ewald_h h, const double* rest_reim, int64_t n_pos, int n_atoms, const double* xyz, const double* q,
+                            double energy_net_charges, double static_contribution, double* out) {
+    EnergyPointsParams P;
+    memset(&P, 0, sizeof P);
+    return small_energy_points(P, h->device, h, rest_reim, n_pos, n_atoms, nullptr, q, xyz, energy_net_charges,
+                               static_contribution, nullptr, out);
+}
+
 extern "C" int ceg_ewald_reciprocal(ceg_ewald_h h, int64_t n_pos, int32_t n_atoms, const double* xyz, const double* q,
                                     double energy_net_charges, double static_contribution, double* out) {
     if (!h || n_pos < 0 || n_atoms <= 0 || !q || (n_pos > 0 && (!xyz || !out)))
@@ -1831,6 +1843,10 @@ extern "C" int ceg_ewald_reciprocal(ceg_ewald_h h, int64_t n_pos, int32_t n_atom
     if (n_pos == 0) return 0;
     std::lock_guard<std::mutex> lk(h->mu);
     if (use_device(h->device)) return 1;
+    {   // single Monte-Carlo steps: one launch, mapped I/O (csrc/latency.cuh)
+        const int rc = small_reciprocal(h, nullptr, n_pos, n_atoms, xyz, q, energy_net_charges, static_contribution, out);
+        if (rc != 2) return rc;
+    }
     CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * n_atoms * n_pos));
     CEG_CK(h->d_out.reserve(sizeof(double) * n_pos));
     CEG_CK(h->d_q.reserve(sizeof(double) * n_atoms));
@@ -1854,6 +1870,10 @@ extern "C" int ceg_ewald_single_contribution(ceg_ewald_h h, const double* rest_r
     if (n_pos == 0) return 0;
     std::lock_guard<std::mutex> lk(h->mu);
     if (use_device(h->device)) return 1;
+    {   // single Monte-Carlo steps: one launch, `rest` read from mapped host memory (csrc/latency.cuh)
+        const int rc = small_reciprocal(h, rest_reim, n_pos, n_atoms, xyz, q, 0.0, 0.0, out);
+        if (rc != 2) return rc;
+    }
     DevBuf d_rest;
     CEG_CK(d_rest.reserve(sizeof(double) * 2 * std::max<int64_t>(1, h->n_k)));
     CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * n_atoms * n_pos));
@@ -2122,6 +2142,89 @@ static SmallStage& small_stage() {
     static thread_local SmallStage st;
     return st;
 }
+// Latency path (single Monte-Carlo steps): ONE kernel launch per call.  Small inputs travel inside the kernel
+// parameters, larger ones and all outputs sit in a pinned block mapped into the device address space (the kernel
+// writes the energies over PCIe itself) and the host polls the result slots — no copies, no stream synchronisation,
+// no completion counter (csrc/latency.cuh).  Serves ceg_energy_points, ceg_ewald_reciprocal and
+// ceg_ewald_single_contribution (`rest`: the structure factor the placement interacts with instead of the framework's).
+// Returns 0 done, 1 error, 2 not applicable (the caller takes its batch path).
+static int small_energy_points(const EnergyPointsParams& P, int device, ceg_ewald_h ewald, const double* rest_reim,
+                               int64_t n_pos, int n_atoms, const int32_t* atomsidx, const double* charges, const double* xyz,
+                               double energy_net_charges, double static_contribution, double* out_vdw, double* out_coulomb) {
+    constexpr int64_t LATENCY_MAX_POS = 256;
+    if (n_pos > LATENCY_MAX_POS || n_atoms > SMALL_MAX_ATOMS) return 2;
+    const bool recip = ewald && ewald->n_k > 0;
+    if (rest_reim && !recip) return 2;
+    SmallStage& stg = small_stage();
+    const size_t n_idx8 = ((size_t)n_atoms + 1) / 2;
+    const size_t n_rest = rest_reim ? (size_t)2 * ewald->n_k : 0;
+    const size_t need = sizeof(double) * (8 + n_idx8 + (size_t)n_atoms + (size_t)3 * n_atoms * n_pos + (size_t)4 * n_pos + 4 + n_rest);
+    size_t smem = 0;
+    if (recip) {
+        smem = sizeof(double2) * (size_t)n_atoms * ((size_t)(ewald->kmax[0] + 1) + (2 * ewald->kmax[1] + 1) + (2 * ewald->kmax[2] + 1));
+        if (smem > 40 * 1024) return 2;
+    }
+    if (need > SmallStage::BYTES || !stg.ready(device)) return 2;
+    double* hb = static_cast<double*>(stg.host);
+    double* db = static_cast<double*>(stg.host_dev);
+    const size_t o_idx = 8, o_q = o_idx + n_idx8, o_xyz = o_q + n_atoms;
+    const size_t o_out = (o_xyz + (size_t)3 * n_atoms * n_pos + 1) & ~(size_t)1;     // 16-byte aligned result slots
+    const size_t o_rest = o_out + (size_t)4 * n_pos;                                  // 16-byte aligned as well
+    SmallParams S;
+    S.E = P;
+    S.E.n_pos = n_pos;
+    S.E.n_atoms = n_atoms;
+    S.n_idx8 = (int)n_idx8;
+    const size_t n_in = n_idx8 + (size_t)n_atoms + (size_t)3 * n_atoms * n_pos;
+    S.n_inline = n_in <= (size_t)SMALL_INLINE_DOUBLES ? (int)n_in : 0;
+    double* dst = S.n_inline ? S.inl : hb + o_idx;      // by value in the launch, or through the mapped block
+    dst[n_idx8 - 1] = 0.0;                              // padding word of an odd atom count
+    if (atomsidx) memcpy(dst, atomsidx, sizeof(int32_t) * n_atoms);
+    else memset(dst, 0, sizeof(double) * n_idx8);       // no grids: species index 0 for every atom
+    memcpy(dst + n_idx8, charges, sizeof(double) * n_atoms);
+    memcpy(dst + n_idx8 + n_atoms, xyz, sizeof(double) * 3 * n_atoms * n_pos);
+    S.in = db + o_idx;
+    S.has_ewald = recip ? 1 : 0;
+    S.rest = nullptr;
+    if (recip) {
+        memcpy(S.invmat, ewald->invmat, sizeof S.invmat);
+        S.kx = ewald->kmax[0]; S.ky = ewald->kmax[1]; S.kz = ewald->kmax[2];
+        S.n_k = ewald->n_k;
+        S.kv = ewald->d_kv.as<KVecDev>();
+        if (rest_reim) {
+            memcpy(hb + o_rest, rest_reim, sizeof(double) * n_rest);
+            S.rest = reinterpret_cast<const double2*>(db + o_rest);
+        }
+    } else {
+        S.n_k = 0; S.kv = nullptr; S.kx = S.ky = S.kz = 0;
+    }
+    S.energy_net_charges = energy_net_charges;
+    S.static_contribution = static_contribution;
+    S.out = reinterpret_cast<double2*>(db + o_out);
+    S.gen = ++stg.gen;
+    energy_points_small_kernel<<<(unsigned)n_pos, SMALL_THREADS, smem, stg.stream>>>(S);
+    count_launch();
+    CEG_CK(cudaGetLastError());
+    // every result slot is {value, generation}, written by one 16-byte store: a slot that shows this call's
+    // generation holds this call's value
+    const volatile unsigned long long* slot = reinterpret_cast<const volatile unsigned long long*>(hb + o_out);
+    unsigned long long spins = 0;
+    for (int64_t i = 0; i < n_pos; i++) {
+        while (slot[4 * i + 1] != S.gen || slot[4 * i + 3] != S.gen) {
+            if ((++spins & 0xfffff) == 0) {            // every ~1M polls: has the launch failed?
+                cudaError_t q = cudaStreamQuery(stg.stream);
+                if (q != cudaErrorNotReady && q != cudaSuccess) return fail_cuda(q, "energy_points_small_kernel", __FILE__, __LINE__);
+                if (q == cudaSuccess && (slot[4 * i + 1] != S.gen || slot[4 * i + 3] != S.gen))
+                    return fail("latency kernel finished without completing");   // cannot happen; do not hang
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (out_vdw) out_vdw[i] = hb[o_out + 4 * i];
+        out_coulomb[i] = hb[o_out + 4 * i + 2];
+    }
+    return 0;
+}
+
 // Median round trip of ONE empty launch on the latency path's machinery (same stream, same mapped flag, same polling
 // loop): what any single-launch evaluation pays on this box before its kernel does any work.
 extern "C" int ceg_measure_launch_roundtrip(int32_t device, int32_t reps, double* median_us) {
@@ -2232,73 +2335,12 @@ extern "C" int ceg_energy_points(int32_t n_vdw, const ceg_grid_h* vdw, ceg_grid_
         for (int64_t i = 0; i < n_pos; i++) { out_vdw[i] = 0.0; out_coulomb[i] = 0.0; }
         return 0;
     }
-    // Latency path (single Monte-Carlo steps): ONE kernel launch per call.  Small inputs travel inside the kernel
-    // parameters, larger ones and all outputs sit in a pinned block mapped into the device address space (the kernel
-    // writes the energies over PCIe itself) and the host polls the result slots — no copies, no stream synchronisation,
-    // no completion counter (csrc/latency.cuh).
-    constexpr int64_t LATENCY_MAX_POS = 256;
-    if (n_pos <= LATENCY_MAX_POS && n_atoms <= SMALL_MAX_ATOMS) {
-        SmallStage& stg = small_stage();
-        const size_t n_idx8 = ((size_t)n_atoms + 1) / 2;
-        const size_t need = sizeof(double) * (8 + n_idx8 + (size_t)n_atoms + (size_t)3 * n_atoms * n_pos + (size_t)4 * n_pos + 2);
-        size_t smem = 0;
-        bool tables_fit = true;
-        if (coulomb && ewald && ewald->n_k > 0) {
-            smem = sizeof(double2) * (size_t)n_atoms * ((size_t)(ewald->kmax[0] + 1) + (2 * ewald->kmax[1] + 1) + (2 * ewald->kmax[2] + 1));
-            tables_fit = smem <= 40 * 1024;
-        }
-        if (need <= SmallStage::BYTES && tables_fit && stg.ready(P_device_of(vdw, n_vdw, coulomb, ewald, block))) {
-            double* hb = static_cast<double*>(stg.host);
-            double* db = static_cast<double*>(stg.host_dev);
-            const size_t o_idx = 8, o_q = o_idx + n_idx8, o_xyz = o_q + n_atoms;
-            const size_t o_out = (o_xyz + (size_t)3 * n_atoms * n_pos + 1) & ~(size_t)1;     // 16-byte aligned result slots
-            SmallParams S;
-            S.E = P;
-            S.E.n_pos = n_pos;
-            S.n_idx8 = (int)n_idx8;
-            const size_t n_in = n_idx8 + (size_t)n_atoms + (size_t)3 * n_atoms * n_pos;
-            S.n_inline = n_in <= (size_t)SMALL_INLINE_DOUBLES ? (int)n_in : 0;
-            double* dst = S.n_inline ? S.inl : hb + o_idx;      // by value in the launch, or through the mapped block
-            if (S.n_inline) dst[n_idx8 - 1] = 0.0;              // padding word of an odd atom count
-            memcpy(dst, atomsidx, sizeof(int32_t) * n_atoms);
-            memcpy(dst + n_idx8, charges, sizeof(double) * n_atoms);
-            memcpy(dst + n_idx8 + n_atoms, xyz, sizeof(double) * 3 * n_atoms * n_pos);
-            S.in = db + o_idx;
-            S.has_ewald = (coulomb && ewald && ewald->n_k > 0) ? 1 : 0;
-            if (S.has_ewald) {
-                memcpy(S.invmat, ewald->invmat, sizeof S.invmat);
-                S.kx = ewald->kmax[0]; S.ky = ewald->kmax[1]; S.kz = ewald->kmax[2];
-                S.n_k = ewald->n_k;
-                S.kv = ewald->d_kv.as<KVecDev>();
-            } else {
-                S.n_k = 0; S.kv = nullptr; S.kx = S.ky = S.kz = 0;
-            }
-            S.energy_net_charges = energy_net_charges;
-            S.static_contribution = static_contribution;
-            S.out = reinterpret_cast<double2*>(db + o_out);
-            S.gen = ++stg.gen;
-            energy_points_small_kernel<<<(unsigned)n_pos, SMALL_THREADS, smem, stg.stream>>>(S);
-            count_launch();
-            CEG_CK(cudaGetLastError());
-            // every result slot is {value, generation}, written by one 16-byte store: a slot that shows this call's
-            // generation holds this call's value
-            const volatile unsigned long long* slot = reinterpret_cast<const volatile unsigned long long*>(hb + o_out);
-            unsigned long long spins = 0;
-            for (int64_t i = 0; i < n_pos; i++) {
-                while (slot[4 * i + 1] != S.gen || slot[4 * i + 3] != S.gen) {
-                    if ((++spins & 0xfffff) == 0) {            // every ~1M polls: has the launch failed?
-                        cudaError_t q = cudaStreamQuery(stg.stream);
-                        if (q != cudaErrorNotReady && q != cudaSuccess) return fail_cuda(q, "energy_points_small_kernel", __FILE__, __LINE__);
-                        if (q == cudaSuccess && (slot[4 * i + 1] != S.gen || slot[4 * i + 3] != S.gen))
-                            return fail("ceg_energy_points: latency kernel finished without completing");   // cannot happen; do not hang
-                    }
-                }
-                std::atomic_thread_fence(std::memory_order_acquire);
-                out_vdw[i] = hb[o_out + 4 * i];
-                out_coulomb[i] = hb[o_out + 4 * i + 2];
-            }
-            return 0;
-        }
+    // Latency path (single Monte-Carlo steps): ONE kernel launch per call (small_energy_points below the staging block).
+    {
+        const int rc = small_energy_points(P, P_device_of(vdw, n_vdw, coulomb, ewald, block), (coulomb && ewald) ? ewald : nullptr,
+                                           nullptr, n_pos, n_atoms, atomsidx, charges, xyz, energy_net_charges,
+                                           static_contribution, out_vdw, out_coulomb);
+        if (rc != 2) return rc;
     }
     // Small batches (single Monte-Carlo steps): latency is what matters.  Inputs are packed into one pinned, thread-local
     // staging block and uploaded with ONE copy, the two outputs come back with ONE copy, and the stream is kept per

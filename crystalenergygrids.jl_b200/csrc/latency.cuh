@@ -50,6 +50,7 @@ struct SmallParams {
     int kx, ky, kz;
     int64_t n_k;
     const KVecDev* kv;
+    const double2* rest;             // null: the framework's S_f inside kv; else the structure factor to interact with (mapped host)
     double energy_net_charges, static_contribution;
     double2* out;                    // mapped host: per placement {vdw, gen}, {coulomb, gen} (gen = bits of the call's number)
     unsigned long long gen;
@@ -117,7 +118,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) energy_points_small_kernel(cons
                 sre += qa * (ex.x * yzr - ex.y * yzi);
                 sim += qa * (ex.x * yzi + ex.y * yzr);
             }
-            fa += kv.kf * (kv.sf_re * sre + kv.sf_im * sim);
+            const double2 sf = S.rest ? S.rest[k] : make_double2(kv.sf_re, kv.sf_im);
+            fa += kv.kf * (sf.x * sre + sf.y * sim);
             aa += kv.kf * (sre * sre + sim * sim);
         }
 #pragma unroll

@@ -37,10 +37,11 @@ def test_structure_factor_and_reciprocal_vs_oracle(cuda_lib, orc):
              (np.array([0.9094]), np.zeros((1, 3)))]
     for na in (2, 4, 5):
         cases.append((rng.standard_normal(na), rng.standard_normal((na, 3)) * 1.5))
-    # 500 placements: latency path (warp per placement for every size); 20000: throughput path (>= 16384 placements)
+    # 1 / 64 / 256 placements: one-launch latency kernel (csrc/latency.cuh); 500: warp per placement; 20000: throughput
+    # path (>= 16384 placements)
     many = wl.random_positions(fw.mat, 20000, 32) * 3.0 - 20.0
     for q, offs in cases:
-        for ctr in (centers, many):
+        for ctr in (centers[:1], centers[:64], centers[:256], centers, many):
             pos = ctr[:, None, :] + offs[None, :, :]
             enc, stat = 12.5, -3.25
             got = ceg._lib.ewald_reciprocal(ef.handle, pos, q, enc, stat)
@@ -206,8 +207,11 @@ def test_single_contribution_ewald_batched(cuda_lib, orc):
     oe.S = rest
     want = oe.reciprocal(trials, q, 0.0, 0.0)
     assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
-    small = ceg.single_contribution_ewald(ef, rest, q, trials[:300])     # latency path: warp per placement
+    small = ceg.single_contribution_ewald(ef, rest, q, trials[:300])     # warp per placement
     assert np.abs(small - want[:300]).max() <= 1e-9 * np.abs(want).max()
+    for n in (1, 33, 256):                                               # one-launch latency kernel, `rest` in mapped memory
+        tiny = ceg.single_contribution_ewald(ef, rest, q, trials[1000:1000 + n])
+        assert np.abs(tiny - want[1000:1000 + n]).max() <= 1e-9 * np.abs(want).max()
     # identity: E(A, B_new) - E(A, B_old) == single(B_new) - single(B_old)
     old = ceg.single_contribution_ewald(ef, rest, q, B_old[None])[0]
     for i in (0, 17, 123):
