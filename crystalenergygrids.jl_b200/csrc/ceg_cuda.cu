@@ -160,6 +160,8 @@ struct ceg_probe_s {
     int device = 0;
     std::mutex mu;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaStream_t s_compute2 = nullptr;      // odd chunks of ceg_grid_build: the tail of one chunk's launch overlaps the head of the next
+    cudaEvent_t ev_join = nullptr;
     CellDev cell;
     double cutoff2 = 0, alpha = 0;
     int n_probes = 0, want_coulomb = 0, n_types = 0;
@@ -173,7 +175,8 @@ struct ceg_probe_s {
     // cached expanded image lists, one per (slab, grid spec) recently built — callers alternate between a few slabs (the
     // halves of a pipelined build, C1 and C4 of one framework): least recently used of EXT_CACHE entries is replaced
     struct ExtList {
-        DevBuf d_ext, d_ext_meta, d_ext_range;
+        DevBuf d_ext;                      // [images | meta | per-plane ranges]
+        size_t off_meta = 0, off_range = 0;
         int n_ext = 0, plane0 = 0, planes = 0;
         double key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int key_planes[2] = {-1, -1};
@@ -201,7 +204,9 @@ struct ceg_probe_s {
             if (ev_free[r]) cudaEventDestroy(ev_free[r]);
             if (ev_time[r]) cudaEventDestroy(ev_time[r]);
         }
+        if (ev_join) cudaEventDestroy(ev_join);
         if (s_compute) release_stream(s_compute);
+        if (s_compute2) release_stream(s_compute2);
         if (s_copy) release_stream(s_copy);
     }
 };
@@ -485,6 +490,7 @@ extern "C" int ceg_probe_create(int32_t device, const ceg_cell_t* supercell, int
             if (s.flags & CEG_PAIR_HS) h->max_hs_r2 = std::max(h->max_hs_r2, d.hs_r2);
         }
     CEG_CK(acquire_stream(&h->s_compute));
+    CEG_CK(acquire_stream(&h->s_compute2));
     CEG_CK(acquire_stream(&h->s_copy));
     CEG_CK(h->d_xyz.reserve(sizeof(double) * 3 * std::max<int64_t>(1, n_atoms)));
     CEG_CK(h->d_type.reserve(sizeof(int) * std::max<int64_t>(1, n_atoms)));
@@ -564,6 +570,8 @@ static void build_ext_list(const ceg_probe_s* h, const double lo[3], const doubl
     }
     ext.clear();
     meta.clear();
+    ext.reserve((size_t)h->n_atoms * 8);
+    meta.reserve((size_t)h->n_atoms * 8);
     for (int64_t a = 0; a < h->n_atoms; a++) {
         const double* p = &h->h_xyz[3 * a];
         double f[3];
@@ -576,20 +584,24 @@ static void build_ext_list(const ceg_probe_s* h, const double lo[3], const doubl
         for (int i1 = n0[0]; i1 <= n1[0]; i1++)
             for (int i2 = n0[1]; i2 <= n1[1]; i2++)
                 for (int i3 = n0[2]; i3 <= n1[2]; i3++) {
-                    double q[3];
-                    for (int r = 0; r < 3; r++) q[r] = p[r] + ((double)i1 * m[r] + (double)i2 * m[3 + r] + (double)i3 * m[6 + r]);
-                    if (q[0] < blo[0] || q[0] > bhi[0] || q[1] < blo[1] || q[1] > bhi[1] || q[2] < blo[2] || q[2] > bhi[2])
-                        continue;
-                    ext.push_back(ExtAtom{q[0], q[1], q[2], h->h_q[a]});
+                    // (the same expression for every image, whatever loop it sits in: positions are bit-reproducible)
+                    const double q0 = p[0] + ((double)i1 * m[0] + (double)i2 * m[3] + (double)i3 * m[6]);
+                    if (q0 < blo[0] || q0 > bhi[0]) continue;
+                    const double q1 = p[1] + ((double)i1 * m[1] + (double)i2 * m[4] + (double)i3 * m[7]);
+                    if (q1 < blo[1] || q1 > bhi[1]) continue;
+                    const double q2 = p[2] + ((double)i1 * m[2] + (double)i2 * m[5] + (double)i3 * m[8]);
+                    if (q2 < blo[2] || q2 > bhi[2]) continue;
+                    ext.push_back(ExtAtom{q0, q1, q2, h->h_q[a]});
                     meta.push_back(ExtMeta{h->h_type[a], (int)a});
                 }
     }
-    std::vector<int> order(ext.size());
-    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ext[a].x < ext[b].x; });
+    // sorted by x, ties in generation order (= a stable sort): the summation order inside a tile is the list order
+    std::vector<std::pair<double, int>> order(ext.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = {ext[i].x, (int)i};
+    std::sort(order.begin(), order.end());
     std::vector<ExtAtom> ext2(ext.size());
     std::vector<ExtMeta> meta2(meta.size());
-    for (size_t i = 0; i < order.size(); i++) { ext2[i] = ext[order[i]]; meta2[i] = meta[order[i]]; }
+    for (size_t i = 0; i < order.size(); i++) { ext2[i] = ext[order[i].second]; meta2[i] = meta[order[i].second]; }
     ext.swap(ext2);
     meta.swap(meta2);
 }
@@ -792,14 +804,20 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
         if (L->valid) CEG_CK(cudaDeviceSynchronize());   // an earlier asynchronous build may still be reading the list being replaced
         L->valid = false;
         L->n_ext = (int)ext.size();
-        CEG_CK(L->d_ext.reserve(sizeof(ExtAtom) * std::max<size_t>(1, ext.size())));
-        CEG_CK(L->d_ext_meta.reserve(sizeof(ExtMeta) * std::max<size_t>(1, meta.size())));
-        CEG_CK(L->d_ext_range.reserve(sizeof(int) * range.size()));
+        // one device buffer, one upload: [images | meta | per-plane ranges]
+        const size_t b_ext = sizeof(ExtAtom) * std::max<size_t>(1, ext.size());
+        const size_t b_meta = (sizeof(ExtMeta) * std::max<size_t>(1, meta.size()) + 15) & ~(size_t)15;
+        const size_t b_range = sizeof(int) * range.size();
+        L->off_meta = b_ext;
+        L->off_range = b_ext + b_meta;
+        std::vector<char> blob(b_ext + b_meta + b_range);
         if (!ext.empty()) {
-            CEG_CK(cudaMemcpy(L->d_ext.p, ext.data(), sizeof(ExtAtom) * ext.size(), cudaMemcpyHostToDevice));
-            CEG_CK(cudaMemcpy(L->d_ext_meta.p, meta.data(), sizeof(ExtMeta) * meta.size(), cudaMemcpyHostToDevice));
+            memcpy(blob.data(), ext.data(), sizeof(ExtAtom) * ext.size());
+            memcpy(blob.data() + L->off_meta, meta.data(), sizeof(ExtMeta) * meta.size());
         }
-        CEG_CK(cudaMemcpy(L->d_ext_range.p, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice));
+        memcpy(blob.data() + L->off_range, range.data(), b_range);
+        CEG_CK(L->d_ext.reserve(blob.size()));
+        CEG_CK(cudaMemcpy(L->d_ext.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
         memcpy(L->key, key, sizeof key);
         L->key_planes[0] = i0; L->key_planes[1] = i1;
         L->plane0 = i0; L->planes = planes;
@@ -808,10 +826,10 @@ static int prepare_build(ceg_probe_s* h, const ceg_gridspec_t* gs, int i0, int i
     }
     L->used = ++h->ext_clock;
     P.ext = L->d_ext.as<ExtAtom>();
-    P.ext_meta = L->d_ext_meta.as<ExtMeta>();
+    P.ext_meta = reinterpret_cast<const ExtMeta*>(static_cast<const char*>(L->d_ext.p) + L->off_meta);
     P.n_ext = L->n_ext;
-    P.ext_lo = L->d_ext_range.as<int>();
-    P.ext_hi = L->d_ext_range.as<int>() + L->planes;
+    P.ext_lo = reinterpret_cast<const int*>(static_cast<const char*>(L->d_ext.p) + L->off_range);
+    P.ext_hi = P.ext_lo + L->planes;
     P.ext_plane0 = L->plane0;
     return 0;
 }
@@ -1036,7 +1054,8 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
     auto next_chunk = [&](int remaining) {
         if (remaining >= big + small) return big;
         if (remaining > 2 * small) return std::max(small, (remaining / 2) / mtx * mtx);
-        return std::min(remaining, small);
+        if (remaining > mtx) return std::min(small, std::max(mtx, (remaining - mtx) / mtx * mtx));   // the last chunk is one tile row:
+        return remaining;                                                            // its copy is the only one not overlapped
     };
     const int64_t chunk_slab = (int64_t)big * plane;
     if (any_out) CEG_CK(h->d_out.reserve(sizeof(float) * 8 * chunk_slab * ng * RING));
@@ -1050,7 +1069,9 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
     }
     cudaEvent_t* ev_done = h->ev_done;
     cudaEvent_t* ev_free = h->ev_free;
+    if (!h->ev_join) CEG_CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CEG_CK(cudaEventRecord(h->ev_time[0], h->s_compute));
+    CEG_CK(cudaStreamWaitEvent(h->s_compute2, h->ev_time[0], 0));      // (after the statistics reset)
     int rc = 0, c = 0;
     for (size_t wi = 0; wi < win.size() && !rc; wi++) {
     BuildParams P;   // image list of this window (prepare_build drains the device before replacing the list)
@@ -1070,11 +1091,14 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
             Q.raw_slab = slab;
             Q.raw_plane0 = a - i0;
         }
-        if (c >= RING) cudaStreamWaitEvent(h->s_compute, ev_free[slot], 0);   // slot drained?
-        cudaError_t e = launch_planes(h, Q, gs, std::sqrt(h->cutoff2), a, b, h->s_compute);
+        // chunks alternate between two compute streams: the last, partly filled wave of one chunk's launch shares the SMs
+        // with the first CTAs of the next instead of draining alone (13 launches x half a wave was 1 ms of 62 on C4)
+        cudaStream_t cs = (c & 1) ? h->s_compute2 : h->s_compute;
+        if (c >= RING) cudaStreamWaitEvent(cs, ev_free[slot], 0);   // slot drained?
+        cudaError_t e = launch_planes(h, Q, gs, std::sqrt(h->cutoff2), a, b, cs);
         if (e != cudaSuccess) { rc = fail_cuda(e, "grid_build_tiled_kernel", __FILE__, __LINE__); break; }
         if (any_out) {
-            cudaEventRecord(ev_done[slot], h->s_compute);
+            cudaEventRecord(ev_done[slot], cs);
             cudaStreamWaitEvent(h->s_copy, ev_done[slot], 0);
             for (int g = 0; g < ng && !rc; g++) {
                 if (!Q.out[g]) continue;
@@ -1090,6 +1114,8 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
         }
     }
     }
+    cudaEventRecord(h->ev_join, h->s_compute2);
+    cudaStreamWaitEvent(h->s_compute, h->ev_join, 0);
     cudaEventRecord(h->ev_time[1], h->s_compute);
     cudaStreamWaitEvent(h->s_copy, h->ev_time[1], 0);
     cudaEventRecord(h->ev_time[2], h->s_copy);

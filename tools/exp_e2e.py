@@ -22,3 +22,10 @@ for it in range(4):
     ps.close()
     t4 = time.perf_counter()
     print(f"create {1e3*(t1-t0):.1f} ms  build#1 {1e3*(t2-t1):.1f} ms  build#2 {1e3*(t3-t2):.1f} ms  free {1e3*(t4-t3):.1f} ms")
+tm = ceg._lib.probe_last_timing
+ps = ceg.ProbeSystem(None, None, inputs=inp)
+for it in range(6):
+    ceg._lib.grid_build(ps.handle, gs, 0, nx, lam_v, thr_v, lam_c, thr_c, hn, None)
+    print("timing (list, kernel span, copy tail, call) ms:", {k: round(v, 3) for k, v in tm(ps.handle).items()})
+ps.close()
+print("checksum", float(hn[0][0].astype(np.float64).sum()), float(hn[1][0].astype(np.float64).sum()))
