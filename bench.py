@@ -490,7 +490,7 @@ def run_product(args):
     c1_e2e_ms = (time.perf_counter() - t0) * 1e3
     d1 = [torch.empty((8, nx1, ny1, nz1), dtype=torch.float32, device="cuda") for _ in range(2)]
     p1 = [t.data_ptr() for t in d1]
-    c1_kernel_ms, _, _ = timed_build(ps, gs1, 0, nx1, p1, 3, 1)
+    c1_kernel_ms, _, _ = timed_build(ps, gs1, 0, nx1, p1, 6, 3)
     del d1
     ps.close()
 

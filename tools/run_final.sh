@@ -9,4 +9,3 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2f_bench_n1.json
 echo "bench rc $?" >> $L
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2f_bench_ref_n1.json 2>> $L
 echo "ref rc $?" >> $L
-timeout 300 python tools/exp_latency.py >> $L 2>&1
