@@ -553,22 +553,21 @@ grid_build_tiled_kernel(const BuildParams P) {
             // recurrence g_{k+1} = g_k rho_k, rho_{k+1} = rho_k c with rho_0 = exp(-alpha^2 D (2 t0 + D)), c = exp(-2 alpha^2 D^2)
             // (two exponentials per chain instead of one per node).  Chains are anchored at the nodes whose GLOBAL index is a
             // multiple of 8, whatever the tile origin or shape, so a node's factor — and with it every grid value — does not
-            // depend on how the grid is split into slabs and tiles.  One thread per (image, chain): 8 chain slots per image.
+            // depend on how the grid is split into slabs and tiles.  One thread per (image, chain).
             const double na2 = -P.alpha2;
-            const int j = tid & 7;
-            if (j < s_nchain) {
+            const int nchain = s_nchain;
+            for (int idx = tid; idx < cnt * nchain; idx += NT) {      // every thread busy: (image, chain) pairs in dense order
+                const int e = idx / nchain, j = idx - e * nchain;
                 const int ax = s_chain_axis[j], lo = s_chain_lo[j], hi = s_chain_hi[j];
                 const double node0 = s_chain_node[j], dlt = P.gs.delta[ax], cc = P.gauss_step[ax];
-                for (int e = tid >> 3; e < cnt; e += NT / 8) {
-                    const double t0 = node0 - reinterpret_cast<const double*>(s_atom + e)[ax];
-                    double g = exp_acc((na2 * t0) * t0);
-                    double rho = exp_acc((na2 * dlt) * fma(2.0, t0, dlt));
-                    double* dst = s_g + e * NAX + s_chain_off[j];     // position of the anchor in the image's row (may precede it)
-                    for (int k = 0; k < hi; k++) {
-                        if (k >= lo) dst[k] = g;
-                        g *= rho;
-                        rho *= cc;
-                    }
+                const double t0 = node0 - reinterpret_cast<const double*>(s_atom + e)[ax];
+                double g = exp_acc((na2 * t0) * t0);
+                double rho = exp_acc((na2 * dlt) * fma(2.0, t0, dlt));
+                double* dst = s_g + e * NAX + s_chain_off[j];     // position of the anchor in the image's row (may precede it)
+                for (int k = 0; k < hi; k++) {
+                    if (k >= lo) dst[k] = g;
+                    g *= rho;
+                    rho *= cc;
                 }
             }
             __syncthreads();
