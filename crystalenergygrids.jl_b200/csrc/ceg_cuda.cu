@@ -1051,7 +1051,17 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
     const int mtx = main_tx(h->n_probes);
     const int small = std::max(mtx, ((int)((48ll << 20) / (plane * 8 * 4 * ng)) / mtx) * mtx);
     const int big = (i1 - i0 >= 16 * small) ? 4 * small : small;
+    // A call that builds the WHOLE grid has the host link to itself: its copies take about half a chunk's kernel time, and
+    // chunks alternate between two compute streams so that the last, partly filled wave of one launch shares the SMs
+    // with the first CTAs of the next (13 launches x half a wave was 1 ms of 62 on C4).  Co-resident chunks can delay
+    // the older chunk's completion and with it its copy, though: an x-slab of a sharded build — where the ranks compete
+    // for the host's ingest bandwidth and the copies, not the kernels, set the pace — keeps one stream and starts with
+    // a single tile row instead, so that the copy engine gets work as early as possible
+    // (on a box whose two-GPU ingest is 51 GB/s the call takes 35.5 ms = the copy time under every chunk policy tried).
+    const bool whole_grid = (i0 == 0 && i1 == (int)nx);
+    bool first_chunk = !whole_grid;
     auto next_chunk = [&](int remaining) {
+        if (first_chunk) { first_chunk = false; if (remaining > 2 * mtx) return mtx; }
         if (remaining >= big + small) return big;
         if (remaining > 2 * small) return std::max(small, (remaining / 2) / mtx * mtx);
         if (remaining > mtx) return std::min(small, std::max(mtx, (remaining - mtx) / mtx * mtx));   // the last chunk is one tile row:
@@ -1091,9 +1101,7 @@ extern "C" int ceg_grid_build(ceg_probe_h h, const ceg_gridspec_t* gs, int32_t i
             Q.raw_slab = slab;
             Q.raw_plane0 = a - i0;
         }
-        // chunks alternate between two compute streams: the last, partly filled wave of one chunk's launch shares the SMs
-        // with the first CTAs of the next instead of draining alone (13 launches x half a wave was 1 ms of 62 on C4)
-        cudaStream_t cs = (c & 1) ? h->s_compute2 : h->s_compute;
+        cudaStream_t cs = ((c & 1) && whole_grid) ? h->s_compute2 : h->s_compute;
         if (c >= RING) cudaStreamWaitEvent(cs, ev_free[slot], 0);   // slot drained?
         cudaError_t e = launch_planes(h, Q, gs, std::sqrt(h->cutoff2), a, b, cs);
         if (e != cudaSuccess) { rc = fail_cuda(e, "grid_build_tiled_kernel", __FILE__, __LINE__); break; }
