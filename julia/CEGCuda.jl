@@ -15,6 +15,8 @@
 #                                                               of INTEGRATION.md §2 — S_f itself comes from ceg_ewald_create
 #   setup_RASPA's grid hand-off           raspa.jl:420-439   -> create_grids_resident (ceg_grid_create_empty + ceg_grid_build_records:
 #                                                               the build kernel writes the interpolation records itself)
+#   multi-GPU, one process per GPU         raspa.jl:430-438   -> ShardedGridBuild / build! (ceg_ipc_export/open + ceg_grid_build_records:
+#                                                               every rank's kernel writes its slab into every rank's grids)
 #   single_contribution_ewald  ewald.jl:704-738  -> ceg_ewald_single_contribution   (batched over trial placements)
 #   single_contribution_vdw    energy.jl:397-427 -> ceg_guest_energy                (batched over trial placements)
 #   parse_blockfile / BlockFile(g)  coordinates.jl:112-167, grids.jl:188-204 -> ceg_block_from_spheres / _values
@@ -573,6 +575,85 @@ function create_grids_resident(framework, forcefield::ForceField, spacing::TÅ, 
         push!(out, eg)
     end
     out
+end
+
+# ---- one process per GPU: construction and hand-off in one kernel (DESIGN §5b) ---------------------------------------------
+# Every rank allocates its replica of the grids, the record buffers are exchanged once as CUDA IPC handles
+# (`allgather(x)::Vector` = all-gather of a serialisable value over the ranks, indexed by rank + 1, e.g. MPI.jl's
+# `MPI.Allgather` on the serialised bytes), and each rank's build kernel then writes its x-slab as finished
+# interpolation records into the grids of ALL ranks over NVLink (ceg_grid_build_records).  After `build!` on every
+# rank + a device synchronisation + a barrier, `grids` (one EnergyGrid per probe, Coulomb last) are complete on every
+# GPU; the reference exchanges `.grid` files instead (raspa.jl:430-438).
+mutable struct ShardedGridBuild
+    probe::ProbeHandle
+    cset::GridCoordinatesSetup
+    xrange::UnitRange{Int}                 # this rank's planes (0-based, inclusive)
+    handles::Vector{Ptr{Cvoid}}            # this rank's ceg_grid_h, one per grid
+    dest::Vector{Ptr{Cvoid}}               # world x n_grids record pointers (rank-major)
+    peers::Vector{Ptr{Cvoid}}              # ceg_ipc_open mappings, to close before the owners free their grids
+    layout::Int32
+    device::Int
+end
+
+function ShardedGridBuild(framework, forcefield::ForceField, spacing::TÅ, atoms::Vector{Symbol},
+                          ewald::Union{Nothing,EwaldFramework}, rank::Int, world::Int, allgather; device=0)
+    cset, _ = _setup_grid_common(framework, spacing, forcefield.cutoff)
+    probe = ProbeSystem(framework, forcefield)
+    idx = [forcefield.sdict[Symbol(CrystalEnergyGrids.get_atom_name(a))] for a in atoms]
+    withcoul = !(ewald isa Nothing)
+    n = length(idx) + withcoul
+    h = ProbeHandle(probe, idx, withcoul, withcoul ? ustrip(u"Å^-1", ewald.α) : 0.0; device)
+    cell = CegCell(SMatrix{3,3,Float64,9}(ustrip.(u"Å", cset.cell.mat)), SMatrix{3,3,Float64,9}(ustrip.(u"Å^-1", cset.cell.invmat)))
+    gs = CegGridSpec(cset)
+    handles = Ptr{Cvoid}[]; mine = Tuple{Vector{UInt8},Int64}[]; recs = Ptr{Cvoid}[]
+    layout = Ref{Int32}(0)
+    for g in 1:n
+        gh = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ceg_grid_create_empty, libceg), Cint, (Int32, Ref{CegCell}, Ref{CegGridSpec}, Int32, Ref{Ptr{Cvoid}}),
+            device, cell, gs, !(withcoul && g == n), gh))
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ceg_grid_records, libceg), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ptr{Int64}, Ref{Int32}), gh[], r, C_NULL, layout))
+        hd = Vector{UInt8}(undef, 64); off = Ref{Int64}(0)
+        check(ccall((:ceg_ipc_export, libceg), Cint, (Int32, Ptr{Cvoid}, Ptr{UInt8}, Ref{Int64}), device, r[], hd, off))
+        push!(handles, gh[]); push!(recs, r[]); push!(mine, (hd, off[]))
+    end
+    dest = Ptr{Cvoid}[]; peers = Ptr{Cvoid}[]
+    for (r, theirs) in enumerate(world > 1 ? allgather(mine) : [mine])
+        if r == rank + 1
+            append!(dest, recs)
+        else
+            for (hd, off) in theirs
+                p = Ref{Ptr{Cvoid}}(C_NULL)
+                check(ccall((:ceg_ipc_open, libceg), Cint, (Int32, Ptr{UInt8}, Int64, Ref{Ptr{Cvoid}}), device, hd, off, p))
+                push!(dest, p[]); push!(peers, p[])
+            end
+        end
+    end
+    nx = Int(cset.dims[1]) + 1
+    lo = (nx * rank) ÷ world; hi = (nx * (rank + 1)) ÷ world - 1
+    ShardedGridBuild(h, cset, lo:hi, handles, dest, peers, layout[], device)
+end
+
+# launch this rank's slab (asynchronous on the default stream); synchronise the device and the ranks before using the grids
+function build!(sb::ShardedGridBuild)
+    isempty(sb.xrange) && return sb
+    n = length(sb.handles)
+    λv = inv(GRID_TO_KELVIN); Tv = GRID_TO_KELVIN * 1e7
+    λc = ustrip(u"K*Å/e_au^2", COULOMBIC_CONVERSION_FACTOR) / GRID_TO_KELVIN; Tc = inv(λc) * 1e7
+    check(ccall((:ceg_grid_build_records, libceg), Cint,
+        (Ptr{Cvoid}, Ref{CegGridSpec}, Int32, Int32, Cdouble, Cdouble, Cdouble, Cdouble, Int32, Ptr{Ptr{Cvoid}}, Int32,
+         Ptr{Cdouble}, Ptr{Ptr{Cfloat}}, Ptr{Cvoid}),
+        sb.probe.ptr, CegGridSpec(sb.cset), first(sb.xrange), last(sb.xrange) + 1, λv, Tv, λc, Tc,
+        length(sb.dest) ÷ n, sb.dest, sb.layout, fill(Float64(GRID_TO_KELVIN), n), C_NULL, C_NULL))
+    check(ccall((:ceg_device_synchronize, libceg), Cint, (Int32,), sb.device))
+    sb
+end
+
+# unmap the peers' buffers (call on every rank, then barrier, before any rank frees its grids)
+function close_peers!(sb::ShardedGridBuild)
+    foreach(p -> check(ccall((:ceg_ipc_close, libceg), Cint, (Int32, Ptr{Cvoid}), sb.device, p)), sb.peers)
+    empty!(sb.peers)
+    sb
 end
 
 end # module

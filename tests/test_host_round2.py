@@ -90,6 +90,9 @@ def test_julia_shim_binds_only_declared_and_exported_symbols():
         assert hasattr(lib, name)
     for method in ("create_grid_vdw", "create_grid_coulomb", "interpolate_grid", "energy_point", "energy_grid", "compute_ewald"):
         assert re.search(r"function CrystalEnergyGrids\." + method + r"\(", jl), method
+    assert {"ceg_ipc_export", "ceg_ipc_open", "ceg_ipc_close", "ceg_grid_build_records", "ceg_grid_create_empty"} <= called
+    for fn in ("build!", "close_peers!"):
+        assert ("function " + fn + "(") in jl, fn
     for fn in ("create_grids_fused", "create_grids_resident", "structure_factor", "single_contributions", "guest_energies",
                "block_from_spheres", "block_from_values", "handle_from_device", "interpolate_sweep"):
         assert re.search(r"function " + fn + r"\(", jl), fn
