@@ -96,3 +96,23 @@ def test_julia_shim_binds_only_declared_and_exported_symbols():
     for fn in ("create_grids_fused", "create_grids_resident", "structure_factor", "single_contributions", "guest_energies",
                "block_from_spheres", "block_from_values", "handle_from_device", "interpolate_sweep"):
         assert re.search(r"function " + fn + r"\(", jl), fn
+
+
+def test_committed_ncu_traffic_table_belongs_to_the_committed_kernels():
+    """profiles/traffic.json (DRAM bytes per unit from `ncu --set full`, quoted by bench.py as roofline.traffic) carries
+    the digest of the kernel sources it was captured on; bench.py drops the figure when the digest or the register count
+    of the loaded library differs.  The committed table must belong to the committed sources."""
+    import json
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    table = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+    assert set(table) >= {"build", "interp", "interp_pair"}
+    for key, row in table.items():
+        assert row["csrc_digest"] == bench.csrc_digest(key), key
+        assert row["dram_bytes_per_unit"] > 0 and row["registers"] > 0
+        assert os.path.exists(os.path.join(root, row["source"].split(" ")[0])), row["source"]
+    # the build kernel writes 64 B per grid point and reads next to nothing; the interpolation kernel moves ~400 B per query
+    assert 64.0 <= table["build"]["dram_bytes_per_unit"] < 72.0
+    assert 288.0 < table["interp"]["dram_bytes_per_unit"] < 450.0
