@@ -1786,8 +1786,9 @@ static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const d
     // Small batches (single Monte-Carlo steps) do not fill the GPU with one thread per placement, and that thread walks
     // the whole k-list alone; the warp-per-placement kernel spreads the k-list over 32 lanes and returns sooner.
     constexpr int64_t ROWS_MIN_PLACEMENTS = 16384;
-    if (h->rows_ok && n_atoms <= ROWS_MAX_ATOMS && n_pos >= ROWS_MIN_PLACEMENTS) {
+    if (h->rows_ok && n_atoms <= RECIP_QV && n_pos >= ROWS_MIN_PLACEMENTS) {
         RowsParams R;
+        R.n_atoms = n_atoms;
         memcpy(R.invmat, h->invmat, sizeof R.invmat);
         R.ky = h->kmax[1]; R.kz = h->kmax[2];
         R.rows = h->d_rows.as<RowDev>();
@@ -1807,11 +1808,21 @@ static int launch_reciprocal(ceg_ewald_s* h, int64_t n_pos, int n_atoms, const d
         R.energy_net_charges = enc; R.static_contribution = stat;
         R.out = d_out; R.skip = d_skip; R.accumulate = accumulate;
         const unsigned blocks = (unsigned)((n_pos + ROWS_THREADS - 1) / ROWS_THREADS);
-        switch (n_atoms) {
-            case 1: reciprocal_rows_kernel<1><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
-            case 2: reciprocal_rows_kernel<2><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
-            case 3: reciprocal_rows_kernel<3><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
-            default: reciprocal_rows_kernel<4><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
+        const int groups = n_atoms <= 8 ? 2 : n_atoms <= 16 ? 4 : 8;             // lanes per placement beyond 4 atoms
+        const unsigned gblocks = (unsigned)((n_pos * groups + ROWS_THREADS - 1) / ROWS_THREADS);
+        if (n_atoms <= ROWS_MAX_ATOMS) {
+            switch (n_atoms) {
+                case 1: reciprocal_rows_kernel<1><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
+                case 2: reciprocal_rows_kernel<2><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
+                case 3: reciprocal_rows_kernel<3><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
+                default: reciprocal_rows_kernel<4><<<blocks, ROWS_THREADS, 0, s>>>(R); break;
+            }
+        } else if (groups == 2) {
+            reciprocal_rows_group_kernel<2><<<gblocks, ROWS_THREADS, 0, s>>>(R);
+        } else if (groups == 4) {
+            reciprocal_rows_group_kernel<4><<<gblocks, ROWS_THREADS, 0, s>>>(R);
+        } else {
+            reciprocal_rows_group_kernel<8><<<gblocks, ROWS_THREADS, 0, s>>>(R);
         }
         count_launch();
         CEG_CK(cudaGetLastError());

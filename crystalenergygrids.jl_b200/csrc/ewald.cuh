@@ -195,7 +195,8 @@ struct RowsParams {
     int64_t n_pos;
     const double* xyz;
     const double* q;       // device; null: qv
-    double qv[4];
+    double qv[RECIP_QV];
+    int n_atoms;           // grouped kernel: atoms of the molecule (the plain kernel's count is its template argument)
     double energy_net_charges, static_contribution;
     double* out;
     const uint8_t* skip;
@@ -289,6 +290,85 @@ __global__ void __launch_bounds__(ROWS_THREADS) reciprocal_rows_kernel(const Row
     if (NA == 1) { const double q0 = P.q ? P.q[0] : P.qv[0]; aa = (q0 * q0) * P.sum_kf; }
     // ewald.jl:572-576
     const double E = 2.0 * (fa + P.energy_net_charges) + (aa + P.static_contribution);
+    if (P.accumulate) P.out[i] += E; else P.out[i] = E;
+}
+
+// Molecules of 5 to 32 atoms: the placement is shared by G = 2, 4 or 8 adjacent lanes, lane g carrying atoms 4g .. 4g + 3
+// through the same row walk as above (absent atoms: charge 0); per k-vector the lanes' partial S_a are summed by
+// xor-shuffles, so every lane of the group holds the molecule's S_a(k) and accumulates the same energy.  (The
+// warp-per-placement kernel spends 4 times as many FP64 instructions per (atom, k).)
+template <int G>
+__global__ void __launch_bounds__(ROWS_THREADS) reciprocal_rows_group_kernel(const RowsParams P) {
+    constexpr int NA = 4;
+    const int64_t tg = blockIdx.x * (int64_t)ROWS_THREADS + threadIdx.x;
+    const int64_t i_raw = tg / G;
+    const int g = (int)(tg - i_raw * G);
+    const bool live = i_raw < P.n_pos;                       // every lane walks the loops: the shuffles need full warps
+    const int64_t i = live ? i_raw : P.n_pos - 1;
+    const int ny = 2 * P.ky + 1, nz = 2 * P.kz + 1;
+    double2 e1x[NA], e1y[NA], e1z[NA], ey[NA], ez0[NA], w[NA], t[NA];
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+        const int ag = 4 * g + a;
+        const bool have = ag < P.n_atoms;
+        const double* r = P.xyz + ((int64_t)P.n_atoms * i + (have ? ag : 0)) * 3;
+        const double x = r[0], y = r[1], z = r[2];
+        double f[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double v = P.invmat[d] * x + P.invmat[3 + d] * y + P.invmat[6 + d] * z;
+            f[d] = v - floor(v);
+        }
+        e1x[a] = cis2pi(f[0]);
+        e1y[a] = cis2pi(f[1]);
+        e1z[a] = cis2pi(f[2]);
+        ey[a] = cis2pi(red_prod(-(double)P.ky, f[1]));
+        const double2 ez = cis2pi(red_prod(-(double)P.kz, f[2]));
+        const double qa = have ? (P.q ? P.q[ag] : P.qv[ag]) : 0.0;
+        ez0[a] = make_double2(qa * ez.x, qa * ez.y);
+    }
+    double fa = 0.0, aa = 0.0;
+    const RowDev* row = P.rows;
+    for (int jy = 0; jy < ny; jy++) {
+#pragma unroll
+        for (int a = 0; a < NA; a++) w[a] = cmul(ey[a], ez0[a]);
+        for (int jz = 0; jz < nz; jz++, row++) {
+            const RowDev rd = *row;
+            if (rd.count > 0) {
+#pragma unroll
+                for (int a = 0; a < NA; a++) t[a] = w[a];
+                for (int s = 0; s < rd.ix0; s++) {
+#pragma unroll
+                    for (int a = 0; a < NA; a++) t[a] = cmul(t[a], e1x[a]);
+                }
+                const double* kf = P.kf + rd.offset;
+                const double2* ksf = P.ksf + rd.offset;
+                for (int c = 0; c < rd.count; c++) {
+                    double sre = (t[0].x + t[1].x) + (t[2].x + t[3].x), sim = (t[0].y + t[1].y) + (t[2].y + t[3].y);
+#pragma unroll
+                    for (int o = 1; o < G; o <<= 1) {
+                        sre += __shfl_xor_sync(0xffffffffu, sre, o);
+                        sim += __shfl_xor_sync(0xffffffffu, sim, o);
+                    }
+                    const double2 ks = ksf[c];
+                    fa = fma(ks.x, sre, fma(ks.y, sim, fa));
+                    aa = fma(kf[c], fma(sim, sim, sre * sre), aa);
+#pragma unroll
+                    for (int a = 0; a < NA; a++) t[a] = cmul(t[a], e1x[a]);
+                }
+            }
+            if (jz + 1 < nz) {
+#pragma unroll
+                for (int a = 0; a < NA; a++) w[a] = cmul(w[a], e1z[a]);
+            }
+        }
+        if (jy + 1 < ny) {
+#pragma unroll
+            for (int a = 0; a < NA; a++) ey[a] = cmul(ey[a], e1y[a]);
+        }
+    }
+    if (!live || g != 0 || (P.skip && P.skip[i])) return;
+    const double E = 2.0 * (fa + P.energy_net_charges) + (aa + P.static_contribution);      // ewald.jl:572-576
     if (P.accumulate) P.out[i] += E; else P.out[i] = E;
 }
 

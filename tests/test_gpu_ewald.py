@@ -32,10 +32,11 @@ def test_structure_factor_and_reciprocal_vs_oracle(cuda_lib, orc):
     # batched placements of a 3-site molecule (CO2 geometry) and of a single ion
     rng = np.random.default_rng(3)
     centers = wl.random_positions(fw.mat, 500, 31) * 3.0 - 20.0
-    # 1-4 atoms: thread-per-placement kernel (rows of the k-list, recurrences); 5: warp-per-placement kernel
+    # 1-4 atoms: thread-per-placement kernel (rows of the k-list, recurrences)
     cases = [(np.array([-0.3256, 0.6512, -0.3256]), np.array([[0, 0, 1.149], [0, 0, 0], [0, 0, -1.149]])),
              (np.array([0.9094]), np.zeros((1, 3)))]
-    for na in (2, 4, 5):
+    # 5-8 / 9-16 / 17-32 atoms at >= 16384 placements: 2 / 4 / 8 lanes per placement (reciprocal_rows_group_kernel)
+    for na in (2, 4, 5, 9, 17, 32):
         cases.append((rng.standard_normal(na), rng.standard_normal((na, 3)) * 1.5))
     # 1 / 64 / 256 placements: one-launch latency kernel (csrc/latency.cuh); 500: warp per placement; 20000: throughput
     # path (>= 16384 placements)
