@@ -1530,9 +1530,25 @@ static int interpolate_pipelined(int n_grids, ceg_grid_s* const* grids, int64_t 
     return 0;
 }
 
+static int small_energy_points(const EnergyPointsParams& P, int device, ceg_ewald_h ewald, const double* rest_reim,
+                               int64_t n_pos, int n_atoms, const int32_t* atomsidx, const double* charges, const double* xyz,
+                               double energy_net_charges, double static_contribution, double* out_vdw, double* out_coulomb);
+
 extern "C" int ceg_interpolate(ceg_grid_h h, int64_t n, const double* xyz, double* out) {
     if (!h || n < 0 || (n > 0 && (!xyz || !out))) return fail("ceg_interpolate: bad argument");
     if (n == 0) return 0;
+    if (n <= 256) {     // a handful of points: the one-launch latency path (csrc/latency.cuh), one "atom" of charge 1 per point
+        if (use_device(h->device)) return 1;
+        EnergyPointsParams P;
+        memset(&P, 0, sizeof P);
+        if (h->g.is_vdw) { P.n_vdw = 1; P.vdw[0] = h->g; P.vdw_present[0] = 1; }
+        else { P.coulomb = h->g; P.has_coulomb = 1; }
+        const double one = 1.0;
+        double other[256];
+        const int rc = small_energy_points(P, h->device, nullptr, nullptr, n, 1, nullptr, &one, xyz, 0.0, 0.0,
+                                           h->g.is_vdw ? out : other, h->g.is_vdw ? other : out);
+        if (rc != 2) return rc;
+    }
     ceg_grid_s* g[1] = {h};
     double* o[1] = {out};
     return interpolate_pipelined(1, g, n, xyz, o);

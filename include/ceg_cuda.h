@@ -344,7 +344,7 @@ int ceg_block_from_spheres(int32_t device, const ceg_cell_t* unitcell, const ceg
 /* BlockFile(g::EnergyGrid) (grids.jl:188-204): voxel-dilated mask of the nodes whose VdW value exceeds
  * `threshold` (5e6 K); values = channel 0 of the grid, [nx][ny][nz]. */
 int ceg_block_from_values(int32_t device, const ceg_gridspec_t* gs, const float* values, float threshold, uint8_t* mask);
-/* Latency: ceg_energy_points, ceg_ewald_reciprocal and ceg_ewald_single_contribution calls with at most 256 placements
+/* Latency: ceg_energy_points, ceg_interpolate, ceg_ewald_reciprocal and ceg_ewald_single_contribution calls with at most 256 placements
  * of at most 32 atoms (single Monte-Carlo steps, montecarlo.jl:490-504) are ONE kernel launch with no copies: small
  * inputs travel inside the launch parameters, results come back through mapped pinned memory as {value, generation}
  * slots the host polls (csrc/latency.cuh); larger batches take the throughput kernels.  Same results within 1e-9. */

@@ -228,3 +228,22 @@ def test_non_finite_positions_are_memory_safe(cuda_lib, orc, layout):
     assert np.allclose(got, want, rtol=1e-9, atol=1e-9)
     assert np.allclose(ceg.interpolate_grid(eg, good), want, rtol=1e-9, atol=1e-9)
     eg.close()
+
+
+def test_small_batches_take_the_latency_path_with_the_same_bits(cuda_lib, orc, layout):
+    """ceg_interpolate with at most 256 points is one launch of the latency kernel (csrc/latency.cuh) instead of the
+    pipelined batch path: same stencil code, so the same bits — for every record layout, VdW (blocked corners included)
+    and Coulomb grids, wrapped and far-away positions, non-finite positions."""
+    cset = ceg.GridCoordinatesSetup.from_cell(ceg.mat_from_parameters((13.0187, 11.2063, 9.3758), (92.82, 107.2, 103.26)), 0.41)
+    grid = _random_grid(cset, 9, hot_fraction=0.02)
+    pos = np.concatenate([wl.random_positions(cset.cell.mat, 3000, 23), wl.random_positions(cset.cell.mat, 300, 24) * 7.0 - 30.0,
+                          np.array([[np.nan, 0.0, 0.0], [np.inf, 1.0, 2.0]])])
+    for is_vdw in (True, False):
+        eg = ceg.EnergyGrid(cset, (1, 1, 1), np.inf if is_vdw else 1e-6, True, grid)
+        batch = ceg._lib.interpolate(eg.handle, pos)
+        if is_vdw:
+            assert (batch == 1e100).any()
+        for a, n in ((0, 1), (5, 2), (40, 31), (1000, 256), (len(pos) - 40, 40)):
+            small = ceg._lib.interpolate(eg.handle, pos[a:a + n])
+            assert np.array_equal(small, batch[a:a + n], equal_nan=True), (is_vdw, a, n)
+        eg.close()
