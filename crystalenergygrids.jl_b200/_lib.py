@@ -608,6 +608,37 @@ def energy_points(vdw_handles, coulomb, ewald, block, atomsidx, charges, xyz, en
     return out_v, out_c
 
 
+class EnergyPointsCall:
+    """ceg_energy_points with everything but the positions marshalled once: a Monte-Carlo loop calls it with the same
+    setup at every step, and for one placement the ctypes conversions cost as much as the library call itself."""
+
+    def __init__(self, vdw_handles, coulomb, ewald, block, atomsidx, charges, energy_net_charges, static_contribution):
+        self.atomsidx = np.ascontiguousarray(atomsidx, dtype=np.int32)
+        self.na = int(self.atomsidx.shape[0])
+        self.charges = _f64(charges, (self.na,))
+        nv = len(vdw_handles)
+        self.arr = (C.c_void_p * max(nv, 1))(*[h if h is not None else C.c_void_p(0) for h in vdw_handles])
+        self.f = load().ceg_energy_points
+        null = C.c_void_p(0)
+        self.head = (C.c_int32(nv), self.arr, coulomb if coulomb is not None else null, ewald if ewald is not None else null,
+                     block if block is not None else null)
+        self.mid = (C.c_int32(self.na), _p(self.atomsidx, C.c_int32), _p(self.charges, C.c_double))
+        self.tail = (C.c_double(energy_net_charges), C.c_double(static_contribution))
+
+    def __call__(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        n = xyz.size // (3 * self.na)
+        if n * 3 * self.na != xyz.size:
+            raise ValueError("positions must have shape (n_pos, n_atoms, 3)")
+        out = np.empty((2, n), dtype=np.float64)
+        po = out.ctypes.data
+        rc = self.f(*self.head, C.c_int64(n), *self.mid, C.c_void_p(xyz.ctypes.data), *self.tail, C.c_void_p(po),
+                    C.c_void_p(po + 8 * n))
+        if rc:
+            _check(rc)
+        return out[0], out[1]
+
+
 def energy_points_prepared(vdw_handles, coulomb, ewald, block, atomsidx, charges, xyz, energy_net_charges, static_contribution):
     """-> (call, out_vdw, out_coulomb): `call()` re-issues ceg_energy_points on the SAME argument buffers with no Python
     marshalling — what a compiled host (the Julia shim's ccall) pays per call; used to time the library's latency path."""

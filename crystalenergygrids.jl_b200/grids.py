@@ -575,6 +575,7 @@ class CrystalEnergySetup:
     # 1.69 vs 1.06 ms and 270 MB 2.25 vs 1.26 ms — one launch then sweeps a working set of twice the grid size, and beyond
     # about twice the 126 MB L2 the random-sector rate of the memory system collapses.
     fused_pairs: object = "auto"
+    _ep_cache: object = None        # marshalled arguments of the last energy_points configuration
 
     def block_handle(self, device=0):
         if self.block.empty:
@@ -629,10 +630,15 @@ def energy_points(setup: CrystalEnergySetup, positions, reciprocal: bool = True)
     """Batched energy_point: positions (n_pos, n_atoms, 3) -> (vdw[n_pos], coulomb[n_pos]).
     With reciprocal=False the Coulomb part is only the interpolated real-space grid term, i.e.
     framework_interactions of the Monte-Carlo loop (montecarlo.jl:490-504)."""
-    na = len(setup.atomsidx)
-    pos = np.asarray(positions, dtype=np.float64).reshape(-1, na, 3)
-    vdw_handles, coul, ew, blk, enc, static = _energy_args(setup, reciprocal)
-    return _lib.energy_points(vdw_handles, coul, ew, blk, setup.atomsidx, setup.charges, pos, enc, static)
+    key = (bool(reciprocal), setup.fused_pairs)
+    c = setup._ep_cache
+    if (c is None or c[0] != key or setup.coulomb._handle is not c[2] or len(c[1]) != len(setup.grids)
+            or any(g._handle is not h or g._pair is not p for g, (h, p) in zip(setup.grids, c[1]))):
+        # (re)marshal the setup: handles, fused pair records, Ewald constants — once per setup, not once per Monte-Carlo step
+        vdw_handles, coul, ew, blk, enc, static = _energy_args(setup, reciprocal)
+        call = _lib.EnergyPointsCall(vdw_handles, coul, ew, blk, setup.atomsidx, setup.charges, enc, static)
+        c = setup._ep_cache = (key, tuple((g._handle, g._pair) for g in setup.grids), setup.coulomb._handle, call)
+    return c[3](positions)
 
 
 def energy_point(setup: CrystalEnergySetup, positions, ctx=None):

@@ -1,31 +1,29 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-L=gpurun_out/r2_lat3.log
+L=gpurun_out/r2_lat4.log
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > $L
+timeout 200 python examples/mfi_co2_trials.py >> $L 2>&1
 timeout 200 python - >> $L 2>&1 <<'PY'
 import sys, time, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import ceg_b200 as ceg
 from ceg_b200 import workloads as wl
-inp, cset, ex = wl.load_fixture("cha_na")
-cs = wl.respace(cset, 0.3)
-nx, ny, nz = cs.nodes
-ps = ceg.ProbeSystem(None, None, inputs=inp)
-outs = [np.zeros((8, nx, ny, nz), dtype=np.float32) for _ in range(2)]
-ceg._lib.grid_build(ps.handle, ceg._lib.make_gridspec(cs), 0, nx, *(ceg.vdw_scaling() + ceg.coulomb_scaling()), outs, None)
-ps.close()
-for g, prec in enumerate((np.inf, 1e-6)):
-    eg = ceg.EnergyGrid(cs, (1, 1, 1), prec, True, (outs[g].astype(np.float64) * ceg.GRID_TO_KELVIN).astype(np.float32))
-    pos = wl.random_positions(cs.cell.mat, 5000, 3)
-    big = ceg._lib.interpolate(eg.handle, pos)                       # batch kernels
-    for n in (1, 7, 256):
-        small = ceg._lib.interpolate(eg.handle, pos[100:100 + n])    # latency kernel
-        assert np.array_equal(small, big[100:100 + n]), (g, n)
-    one = pos[:1]
-    for _ in range(50): ceg._lib.interpolate(eg.handle, one)
+from test_gpu_device_resident import _two_grids
+inp, cs, ex, outs, gK = _two_grids(0.5)
+n_fw = len(ex["site_charge"])
+fw = ceg.RASPASystem(ex["unit_mat"], ex["positions"][:n_fw], ["X"] * n_fw, np.ones(n_fw), ex["charges"][:n_fw], False)
+q = float(ex["probe_charge"])
+eg_v = ceg.EnergyGrid(cs, (1, 1, 1), np.inf, True, gK[0]); eg_c = ceg.EnergyGrid(cs, (1, 1, 1), 1e-6, True, gK[1])
+ef = ceg.initialize_ewald(fw)
+mol = ceg.RASPASystem(np.diag([np.inf] * 3), np.zeros((1, 3)), ["Na"], np.ones(1), np.array([q]), True)
+setup = ceg.CrystalEnergySetup(fw, mol, eg_c, np.array([q]), [eg_v], [0], ef, None, ceg.blockfile_from_grid(eg_v))
+one = wl.random_positions(fw.mat, 1, 3)[:, None, :]
+for name, fn in (("energy_points 1 placement", lambda: ceg.energy_points(setup, one)),
+                 ("framework_interactions 1 placement", lambda: ceg.energy_points(setup, one, reciprocal=False)),
+                 ("energy_point", lambda: ceg.energy_point(setup, one[0]))):
+    for _ in range(50): fn()
     ts = []
-    for _ in range(500):
-        t0 = time.perf_counter(); ceg._lib.interpolate(eg.handle, one); ts.append(time.perf_counter() - t0)
-    print("grid", g, "interpolate 1 point:", round(float(np.median(ts)) * 1e6, 1), "us; small == batch bitwise")
-    eg.close()
+    for _ in range(1000):
+        t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+    print(name, round(float(np.median(ts)) * 1e6, 1), "us")
 PY
